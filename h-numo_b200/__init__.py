@@ -1,0 +1,218 @@
+"""hnumo_b200 -- Python host side of libhnumo_b200.so (ctypes over the C-ABI of include/hnumo_b200.h).
+
+The product is the CUDA library; this package only (1) builds it in-tree for sm_100a, (2) binds the C entry points
+the Fortran driver would bind through ISO_C_BINDING and (3) provides brick decks (decks.py) so
+tests and bench.py can drive the hot path without the Fortran program.  There is no CPU fallback: creating a Solver
+without the CUDA library or without a GPU raises.
+
+The directory name contains a hyphen, so import it through ``hnumo_loader`` at the repo root
+(``from hnumo_loader import hnumo_b200``) or ``__graft_entry__``.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from . import decks  # noqa: F401
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libhnumo_b200.so")
+_LIB = None
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+              "-shared", "-diag-suppress", "177,550"]
+
+
+def build_library(force=False, verbose=False):
+    """nvcc cross-compile of the single translation unit into h-numo_b200/libhnumo_b200.so (in-tree)."""
+    src = os.path.join(_HERE, "csrc", "hnumo_b200.cu")
+    deps = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))]
+    deps.append(os.path.join(_ROOT, "include", "hnumo_b200.h"))
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, src, "-lpthread", "-ldl"]
+    env = dict(os.environ)
+    env.pop("CXX", None); env.pop("CC", None)
+    subprocess.check_call(cmd, env=env)
+    return LIB_PATH
+
+
+class Desc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("nelem", C.c_int32), ("ngl", C.c_int32), ("nq", C.c_int32), ("nlayers", C.c_int32), ("nface", C.c_int32),
+        ("kstages", C.c_int32), ("N_btp", C.c_int32),
+        ("dt", C.c_double), ("dt_btp", C.c_double),
+        ("botfr", C.c_int32), ("method_visc", C.c_int32),
+        ("gravity", C.c_double), ("cd_mlswe", C.c_double), ("visc_mlswe", C.c_double), ("ad_mlswe", C.c_double),
+        ("psiq", C.c_void_p), ("dpsiq", C.c_void_p), ("wnq", C.c_void_p), ("wgl", C.c_void_p), ("dpsi", C.c_void_p),
+        ("face", C.c_void_p), ("elem_metrics", C.c_void_p), ("face_geom", C.c_void_p),
+        ("pbprime_df", C.c_void_p), ("massinv", C.c_void_p), ("coriolis_df", C.c_void_p), ("tau_wind_df", C.c_void_p),
+        ("zbot_df", C.c_void_p), ("alpha_mlswe", C.c_void_p), ("ssprk_a", C.c_void_p), ("ssprk_beta", C.c_void_p),
+        ("rank", C.c_int32), ("nranks", C.c_int32), ("num_nbh", C.c_int32),
+        ("nbh_proc", C.c_void_p), ("num_send_recv", C.c_void_p), ("nbh_send_recv", C.c_void_p),
+        ("device", C.c_int32), ("stage_kernel_variant", C.c_int32),
+    ]
+
+
+EXPORTS = ["hnumo_init", "hnumo_finalize", "hnumo_last_error", "hnumo_upload_state", "hnumo_download_state",
+           "hnumo_step", "hnumo_ti_rk_bcl", "hnumo_btp_bcl_coeffs", "hnumo_btp_substeps", "hnumo_rhs_btp",
+           "hnumo_get_array", "hnumo_comm_get_unique_id", "hnumo_comm_init", "hnumo_timing", "hnumo_set_option"]
+
+
+def load_library():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libhnumo_b200.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.hnumo_last_error.restype = C.c_char_p
+        L.hnumo_init.argtypes = [C.POINTER(Desc), C.POINTER(C.c_void_p)]
+        L.hnumo_finalize.argtypes = [C.c_void_p]
+        L.hnumo_upload_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hnumo_download_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hnumo_step.argtypes = [C.c_void_p, C.c_int32]
+        L.hnumo_ti_rk_bcl.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hnumo_btp_bcl_coeffs.argtypes = [C.c_void_p]
+        L.hnumo_btp_substeps.argtypes = [C.c_void_p]
+        L.hnumo_rhs_btp.argtypes = [C.c_void_p, C.c_void_p]
+        L.hnumo_get_array.restype = C.c_int64
+        L.hnumo_get_array.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
+        L.hnumo_comm_get_unique_id.argtypes = [C.c_void_p]
+        L.hnumo_comm_init.argtypes = [C.c_void_p, C.c_void_p]
+        L.hnumo_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        L.hnumo_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        _LIB = L
+    return _LIB
+
+
+class HnumoError(RuntimeError):
+    pass
+
+
+class Solver:
+    """Device-resident hot path for one partition; mirrors the reference call sequence around ti_rk_bcl."""
+
+    def __init__(self, deck, device=0, variant=0):
+        self.L = load_library()
+        self.deck = deck
+        self._keep = []
+        d = Desc()
+        d.abi_version = 1
+        for k in ("nelem", "ngl", "nq", "nlayers", "nface", "kstages", "N_btp", "botfr", "method_visc", "rank", "nranks"):
+            setattr(d, k, int(deck[k]))
+        for k in ("dt", "dt_btp", "gravity", "cd_mlswe", "visc_mlswe", "ad_mlswe"):
+            setattr(d, k, float(deck[k]))
+
+        def ptr(a, dtype):
+            a = np.ascontiguousarray(a, dtype=dtype) if not (isinstance(a, np.ndarray) and a.flags.f_contiguous and a.dtype == dtype and a.ndim == 2) else a
+            self._keep.append(a)
+            return a.ctypes.data
+
+        # 2-D operator tables are column-major (Fortran); np arrays given as F-ordered keep that layout
+        for k in ("psiq", "dpsiq", "dpsi", "ssprk_a"):
+            a = np.asfortranarray(deck[k], dtype=np.float64)
+            self._keep.append(a)
+            setattr(d, k, a.ctypes.data)
+        for k in ("wnq", "wgl", "elem_metrics", "face_geom", "pbprime_df", "massinv", "coriolis_df", "tau_wind_df", "zbot_df",
+                  "alpha_mlswe", "ssprk_beta"):
+            setattr(d, k, ptr(deck[k], np.float64))
+        d.face = ptr(deck["face"], np.int32)
+        d.num_nbh = len(deck["nbh_proc"])
+        d.nbh_proc = ptr(deck["nbh_proc"], np.int32) if d.num_nbh else None
+        d.num_send_recv = ptr(deck["num_send_recv"], np.int32) if d.num_nbh else None
+        d.nbh_send_recv = ptr(deck["nbh_send_recv"], np.int32) if d.num_nbh else None
+        d.device = device
+        d.stage_kernel_variant = variant
+        self.h = C.c_void_p()
+        rc = self.L.hnumo_init(C.byref(d), C.byref(self.h))
+        if rc != 0:
+            raise HnumoError("hnumo_init failed (%d): %s" % (rc, self.L.hnumo_last_error().decode()))
+        self.npoin, self.nl = int(deck["npoin"]), int(deck["nlayers"])
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.hnumo_finalize(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise HnumoError("%s failed (%d): %s" % (what, rc, self.L.hnumo_last_error().decode()))
+        return rc
+
+    def upload_state(self, q_df, qb_df, qprime_df):
+        q = np.ascontiguousarray(q_df, dtype=np.float64)
+        qb = np.ascontiguousarray(qb_df, dtype=np.float64)
+        qp = np.ascontiguousarray(qprime_df, dtype=np.float64)
+        return self._check(self.L.hnumo_upload_state(self.h, q.ctypes.data, qb.ctypes.data, qp.ctypes.data), "upload_state")
+
+    def download_state(self, out=None):
+        if out is None:
+            out = (np.empty((self.nl, self.npoin, 3)), np.empty((self.npoin, 4)), np.empty((self.nl, self.npoin, 3)))
+        q, qb, qp = out
+        self._check(self.L.hnumo_download_state(self.h, q.ctypes.data, qb.ctypes.data, qp.ctypes.data), "download_state")
+        return q, qb, qp
+
+    def step(self, n=1):
+        """n calls of ti_rk_bcl on the resident state; returns 1 if a layer thickness went negative."""
+        return self._check(self.L.hnumo_step(self.h, int(n)), "step")
+
+    def ti_rk_bcl(self, q_df, qb_df, qprime_df):
+        """Drop-in with the reference signature: arrays are updated in place (host buffers)."""
+        return self._check(self.L.hnumo_ti_rk_bcl(self.h, q_df.ctypes.data, qb_df.ctypes.data, qprime_df.ctypes.data), "ti_rk_bcl")
+
+    def btp_bcl_coeffs(self):
+        return self._check(self.L.hnumo_btp_bcl_coeffs(self.h), "btp_bcl_coeffs")
+
+    def btp_substeps(self):
+        return self._check(self.L.hnumo_btp_substeps(self.h), "btp_substeps")
+
+    def rhs_btp(self):
+        out = np.empty((self.npoin, 3))
+        self._check(self.L.hnumo_rhs_btp(self.h, out.ctypes.data), "rhs_btp")
+        return out
+
+    def get_array(self, name):
+        cap = 8 * max(self.deck["nelem"] * self.deck["nq"] ** 2, self.deck["nface"] * self.deck["nq"] * 4)
+        out = np.empty(cap)
+        n = self.L.hnumo_get_array(self.h, name.encode(), out.ctypes.data, cap)
+        if n < 0:
+            raise HnumoError("get_array(%s) failed (%d): %s" % (name, n, self.L.hnumo_last_error().decode()))
+        return out[:n].copy()
+
+    def comm_init(self, id128):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(id128).ljust(128, b"\0"))
+        return self._check(self.L.hnumo_comm_init(self.h, buf), "comm_init")
+
+    def timing(self, reset=False):
+        out = (C.c_double * 8)()
+        self.L.hnumo_timing(self.h, out, 1 if reset else 0)
+        return dict(ms_btp=out[0], stages=int(out[1]), ms_step=out[2], steps=int(out[3]), launches=int(out[4]),
+                    ms_btp_last=out[5], ms_step_last=out[6])
+
+    def set_option(self, key, value):
+        return self._check(self.L.hnumo_set_option(self.h, key.encode(), float(value)), "set_option")
+
+
+def nccl_unique_id():
+    buf = (C.c_char * 128)()
+    rc = load_library().hnumo_comm_get_unique_id(buf)
+    if rc != 0:
+        raise HnumoError("hnumo_comm_get_unique_id failed: %s" % load_library().hnumo_last_error().decode())
+    return bytes(buf)
+
+
+def local_group_id(gid):
+    """128-byte id selecting the in-process back end (several partitions on one GPU; tests only)."""
+    import struct
+    return b"LOCAL\0\0\0" + struct.pack("i", gid)

@@ -1,0 +1,781 @@
+// hnumo_b200.cu -- host side of libhnumo_b200.so: C-ABI entry points (include/hnumo_b200.h), device set-up,
+// and the drivers that sequence the kernels of one ti_rk_bcl step (reference src/ti_rk_bcl.F90:9-87).
+#include <cstdio>
+#include <cstring>
+
+#include "bcl_kernels.cuh"
+#include "btp_kernels.cuh"
+#include "halo.cuh"
+#include "stage_fused.cuh"
+
+namespace hn {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* what, const char* detail) { snprintf(g_err, sizeof(g_err), "%s: %s", what, detail); }
+
+double* dalloc(Solver& S, size_t n) {
+    void* p = nullptr;
+    if (n == 0) n = 1;
+    if (cudaMalloc(&p, n * sizeof(double)) != cudaSuccess) { set_error("cudaMalloc", "out of device memory"); return nullptr; }
+    cudaMemsetAsync(p, 0, n * sizeof(double), S.stream);
+    S.allocs.push_back(p);
+    return (double*)p;
+}
+Planes palloc(Solver& S, int nplanes, size_t stride) {
+    Planes P; P.p = dalloc(S, (size_t)nplanes * stride); P.stride = stride; P.n = nplanes; return P;
+}
+void upload_ops(const Ops& ops) { cudaMemcpyToSymbol(c_ops, &ops, sizeof(Ops)); }
+
+static int threads_for(const Solver& S) {
+    int t = S.nq2;
+    if (t < 4 * S.nq + 4 * S.ngl) t = 4 * S.nq + 4 * S.ngl;
+    if (t < S.npts + 4 * S.ngl) t = S.npts + 4 * S.ngl;
+    return ((t + 31) / 32) * 32;
+}
+
+// ---- init-time derivations, same formulas as the reference set-up ------------------------------------------
+// mode 0: interpolate (psih), 1: d/dx, 2: d/dy  (Tensor_product.F90:71-81, mod_Tensorproduct.F90:57-111)
+__global__ void k_nodal_to_quad(Mesh M, const double* in, double* out, int mode) {
+    int e = blockIdx.x, tid = threadIdx.x;
+    if (tid >= M.nq2) return;
+    int j = tid / M.nq, i = tid - j * M.nq, ngl = M.ngl;
+    double ksx = M.em[e * 5 + 0], ksy = M.em[e * 5 + 1], etx = M.em[e * 5 + 2], ety = M.em[e * 5 + 3];
+    double v = 0.0;
+    for (int m = 0; m < ngl; ++m)
+        for (int n = 0; n < ngl; ++n) {
+            double f = in[(size_t)e * M.npts + m * ngl + n];
+            double An = c_ops.A[n + ngl * i], Am = c_ops.A[m + ngl * j];
+            if (mode == 0) v += f * (An * Am);
+            else {
+                double h_e = c_ops.B[n + ngl * i] * Am, h_n = An * c_ops.B[m + ngl * j];
+                v += (mode == 1 ? (h_e * ksx + h_n * etx) : (h_e * ksy + h_n * ety)) * f;
+            }
+        }
+    out[(size_t)e * M.nq2 + tid] = v;
+}
+__global__ void k_recip_guard(const double* in, double* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] > 0.0 ? 1.0 / in[i] : 0.0;
+}
+struct FaceStatArgs {
+    Mesh M;
+    const double *pbprime_df, *pbprime_q, *zbot_q;
+    double *cL, *cR, *cLR, *lam, *oop_edge, *pbf_l, *pbf_r, *zbf_l, *zbf_r, *pbl, *pbr, *pbn;
+    double alpha_bot;
+};
+// interpolate_pbprime_init, bot_topo_derivatives, compute_reference_edge_variables
+// (mod_initial_mlswe.F90:29-120,170-262,355-401; initial_conditions.F90:337-348)
+__global__ void k_face_statics(FaceStatArgs a) {
+    int e = blockIdx.x, tid = threadIdx.x;
+    const int ngl = a.M.ngl, nq = a.M.nq;
+    if (tid < 4 * ngl) {
+        int s = tid / ngl, n = tid - s * ngl, slot = e * 4 + s, nb = a.M.nbr[slot], nbs = a.M.nbslot[slot];
+        double own = a.pbprime_df[(size_t)e * a.M.npts + face_node(s, n, ngl)];
+        a.pbn[(size_t)slot * ngl + n] = (nb >= 0) ? a.pbprime_df[(size_t)nb * a.M.npts + face_node(nbs, n, ngl)] : own;
+    }
+    if (tid < 4 * nq) {
+        int s = tid / nq, iq = tid - s * nq, slot = e * 4 + s, nb = a.M.nbr[slot], nbs = a.M.nbslot[slot];
+        bool left = (nb < 0) || (e < nb);
+        if (!left) return;
+        size_t fo = (size_t)slot * nq + iq;
+        double pl = a.pbprime_q[(size_t)e * a.M.nq2 + face_quad(s, iq, nq)];
+        double zl = a.zbot_q[(size_t)e * a.M.nq2 + face_quad(s, iq, nq)];
+        double pr = pl, zr = zl;
+        if (nb >= 0) { pr = a.pbprime_q[(size_t)nb * a.M.nq2 + face_quad(nbs, iq, nq)]; zr = a.zbot_q[(size_t)nb * a.M.nq2 + face_quad(nbs, iq, nq)]; }
+        a.pbf_l[fo] = pl; a.pbf_r[fo] = pr; a.zbf_l[fo] = zl; a.zbf_r[fo] = zr;
+        a.oop_edge[fo] = pl > 0.0 ? 1.0 / pl : 0.0;
+        double c_minus = sqrt(a.alpha_bot * pr), c_plus = sqrt(a.alpha_bot * pl);
+        double cL = 0, cR = 0, cLR = 0, lam = 0;
+        if (c_minus > 0.0 || c_plus > 0.0) {
+            cL = c_minus / (c_minus + c_plus); cR = c_plus / (c_minus + c_plus); cLR = 1.0 / (c_minus + c_plus);
+            lam = c_minus * c_plus / (c_minus + c_plus);
+        }
+        a.cL[fo] = cL; a.cR[fo] = cR; a.cLR[fo] = cLR; a.lam[fo] = lam;
+        double il = 0.0, ir = 0.0;
+        for (int n = 0; n < ngl; ++n) {
+            double hi = c_ops.A[n + ngl * iq];
+            double own = a.pbprime_df[(size_t)e * a.M.npts + face_node(s, n, ngl)];
+            double oth = (nb >= 0) ? a.pbprime_df[(size_t)nb * a.M.npts + face_node(nbs, n, ngl)] : own;
+            il += hi * own; ir += hi * oth;
+        }
+        a.pbl[fo] = il; a.pbr[fo] = ir;
+    }
+}
+__global__ void k_coriolis_coeffs(const double* f, double dt, double* fdt2, double* ab, double* bb, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double fdt = dt * f[i];                     // mod_initial_mlswe.F90:347-350
+    double f2 = 0.5 * fdt;
+    fdt2[i] = f2; ab[i] = 1.0 / (1.0 + f2 * f2); bb[i] = f2 / (1.0 + f2 * f2);
+}
+// AoS (nv,npoin[,nl]) reference layout <-> planes
+__global__ void k_aos_to_planes(const double* aos, double* planes, int nv_in, int v0, int nv, int nl, size_t npoin, size_t stride) {
+    size_t I = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= npoin) return;
+    for (int k = 0; k < nl; ++k)
+        for (int v = 0; v < nv; ++v) planes[(size_t)(v * nl + k) * stride + I] = aos[((size_t)k * npoin + I) * nv_in + v0 + v];
+}
+__global__ void k_planes_to_aos(double* aos, const double* planes, int nv_out, int v0, int nv, int nl, size_t npoin, size_t stride) {
+    size_t I = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= npoin) return;
+    for (int k = 0; k < nl; ++k)
+        for (int v = 0; v < nv; ++v) aos[((size_t)k * npoin + I) * nv_out + v0 + v] = planes[(size_t)(v * nl + k) * stride + I];
+}
+__global__ void k_pb_to_aos(double* aos, const double* pbpert, const double* pbprime, size_t npoin) {
+    size_t I = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (I < npoin) aos[I * 4] = pbpert[I] + pbprime[I];
+}
+
+static size_t nblk(size_t n, int t = 256) { return (n + t - 1) / t; }
+
+static void harvest_events(Solver& S);
+static void take_event_pair(Solver& S, int kind, cudaEvent_t& a, cudaEvent_t& b) {
+    if (S.ev_used >= 256) harvest_events(S);
+    if (S.ev_pool.size() < 2 * (S.ev_used + 1)) {
+        cudaEvent_t x, y; cudaEventCreate(&x); cudaEventCreate(&y);
+        S.ev_pool.push_back(x); S.ev_pool.push_back(y); S.ev_kind.push_back(kind);
+    }
+    S.ev_kind[S.ev_used] = kind;
+    a = S.ev_pool[2 * S.ev_used]; b = S.ev_pool[2 * S.ev_used + 1];
+    S.ev_used++;
+}
+
+// ---- drivers ------------------------------------------------------------------------------------------------
+static void fill_stage_args(Solver& S, StageArgs& a, Planes& qb, const Planes& qprime) {
+    memset(&a, 0, sizeof(a));
+    a.M = S.mesh;
+    for (int v = 0; v < 3; ++v) { a.qb[v] = qb[v]; a.qb0[v] = S.qb0[v]; a.qb2[v] = S.qb2w[v]; }
+    a.trstride = S.trace[0].stride;
+    a.pbprime_df = S.pbprime_df; a.oop_df = S.oop_df; a.massinv = S.massinv;
+    a.oop_q = S.oop_q; a.coriolis_q = S.coriolis_q; a.tauwx_q = S.tauw_q; a.tauwy_q = S.tauw_q + S.npoin_q;
+    a.gzx_q = S.gradzb_q; a.gzy_q = S.gradzb_q + S.npoin_q;
+    a.Quu = S.Quu; a.Quv = S.Quv; a.Qvv = S.Qvv; a.Hbcl = S.Hbcl;
+    a.Quu_e = S.Quu_e; a.Quv_e = S.Quv_e; a.Qvv_e = S.Qvv_e; a.Hbcl_e = S.Hbcl_e;
+    a.cL = S.cL; a.cR = S.cR; a.cLR = S.cLR; a.lam = S.lam; a.oop_edge = S.oop_edge; a.pbl = S.pbl; a.pbr = S.pbr; a.pbn = S.pbn;
+    a.qp_dp = qprime[0 * S.nl + S.nl - 1]; a.qp_u = qprime[1 * S.nl + S.nl - 1]; a.qp_v = qprime[2 * S.nl + S.nl - 1];
+    for (int v = 0; v < 4; ++v) a.bdg[v] = S.btp_dpp_graduv[v];
+    a.pbv = S.pbprime_visc;
+    a.hstat = S.h_stat.p; a.hstat_stride = S.h_stat.stride;
+    for (int v = 0; v < 10; ++v) a.acc_n[v] = S.acc_n[v];
+    for (int v = 0; v < 8; ++v) a.acc_q[v] = S.acc_q[v];
+    for (int v = 0; v < 11; ++v) a.acc_f[v] = S.acc_f[v];
+    a.g = S.g; a.cd = S.cd; a.alpha_bot = S.alpha[S.nl - 1]; a.visc = S.visc;
+    a.botfr = S.botfr; a.has_visc = S.has_visc;
+}
+
+static int launch_stage(Solver& S, const StageArgs& a) {
+    if (S.variant == 0 && stage_fused_supported(S)) return launch_stage_fused(S, a);
+    StageSmem L(S.ngl, S.nq);
+    k_btp_stage_simple<<<S.nelem, threads_for(S), L.total * sizeof(double), S.stream>>>(a);
+    S.n_launches++;
+    return 0;
+}
+
+static int prime_traces(Solver& S, const double* const* in, int mode, double* tr_out) {
+    PrimeArgs p; memset(&p, 0, sizeof(p));
+    p.M = S.mesh;
+    for (int v = 0; v < (mode == 0 ? 3 : 7); ++v) p.in[v] = in[v];
+    p.pbprime_df = S.pbprime_df; p.tr_out = tr_out; p.trstride = S.trace[0].stride; p.has_visc = S.has_visc; p.mode = mode;
+    size_t sm = (sops_doubles_host(S.ngl, S.nq) + 2 * S.npts) * sizeof(double);
+    k_btp_prime_traces<<<S.nelem, threads_for(S), sm, S.stream>>>(p);
+    S.n_launches++;
+    return 0;
+}
+
+int rhs_btp_only(Solver& S, Planes& qb, const Planes& qprime, double* d_rhs_out) {
+    const double* in[3] = {qb[0], qb[1], qb[2]};
+    prime_traces(S, in, 0, S.trace[0].p);
+    if (halo_exchange_traces(S, S.trace[0], S.has_visc ? 7 : 3)) return -1;
+    StageArgs a; fill_stage_args(S, a, qb, qprime);
+    a.tr_in = S.trace[0].p; a.tr_out = S.trace[1].p; a.rhs_only = 1;
+    for (int v = 0; v < 3; ++v) a.rhs_out[v] = d_rhs_out + (size_t)v * S.npoin;
+    StageSmem L(S.ngl, S.nq);
+    k_btp_stage_simple<<<S.nelem, threads_for(S), L.total * sizeof(double), S.stream>>>(a);
+    S.n_launches++;
+    HN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ti_barotropic_ssprk_mlswe (mod_rk_mlswe.F90:19-151)
+int btp_solve(Solver& S, Planes& qb, const Planes& qprime) {
+    cudaMemsetAsync(S.acc_n.p, 0, S.acc_n.stride * S.acc_n.n * sizeof(double), S.stream);
+    cudaMemsetAsync(S.acc_q.p, 0, S.acc_q.stride * S.acc_q.n * sizeof(double), S.stream);
+    cudaMemsetAsync(S.acc_f.p, 0, S.acc_f.stride * S.acc_f.n * sizeof(double), S.stream);
+    cudaMemsetAsync(S.qb2w.p, 0, S.qb2w.stride * 3 * sizeof(double), S.stream);
+    const int ntr = S.has_visc ? 7 : 3;
+    int cur = 0;
+    {
+        const double* in[3] = {qb[0], qb[1], qb[2]};
+        prime_traces(S, in, 0, S.trace[cur].p);
+        if (halo_exchange_traces(S, S.trace[cur], ntr)) return -1;
+    }
+    cudaEvent_t e_start, e_stop;
+    take_event_pair(S, 0, e_start, e_stop);
+    cudaEventRecord(e_start, S.stream);
+    StageArgs a; fill_stage_args(S, a, qb, qprime);
+    for (int mstep = 1; mstep <= S.N_btp; ++mstep) {
+        for (int ik = 1; ik <= S.kstages; ++ik) {
+            a.a1 = S.ssprk_a[ik - 1][0]; a.a2 = S.ssprk_a[ik - 1][1]; a.a3 = S.ssprk_a[ik - 1][2];
+            a.dtt = S.dt_btp * S.ssprk_beta[ik - 1];
+            a.load_q0 = (ik > 1 && a.a1 != 0.0);
+            a.load_q2 = (a.a3 != 0.0);
+            a.store_q0 = (ik == 1 && S.kstages > 1);
+            a.store_q2 = (S.kstages == 5 && ik == 2);
+            a.tr_in = S.trace[cur].p; a.tr_out = S.trace[cur ^ 1].p;
+            if (launch_stage(S, a)) return -1;
+            cur ^= 1;
+            if (halo_exchange_traces(S, S.trace[cur], ntr)) return -1;
+        }
+    }
+    cudaEventRecord(e_stop, S.stream);
+    S.n_stages += (long)S.N_btp * S.kstages;
+    // time averages
+    {
+        const double* in[7];
+        for (int v = 0; v < 3; ++v) in[v] = S.acc_n[3 + v];
+        for (int v = 0; v < 4; ++v) in[3 + v] = S.acc_n[6 + v];
+        prime_traces(S, in, 1, S.trace[cur].p);
+        if (halo_exchange_traces(S, S.trace[cur], 7)) return -1;
+        FinalizeArgs f; memset(&f, 0, sizeof(f));
+        f.M = S.mesh;
+        for (int v = 0; v < 10; ++v) f.acc_n[v] = S.acc_n[v];
+        for (int v = 0; v < 8; ++v) f.acc_q[v] = S.acc_q[v];
+        for (int v = 0; v < 11; ++v) f.acc_f[v] = S.acc_f[v];
+        f.tr = S.trace[cur].p; f.trstride = S.trace[cur].stride;
+        for (int v = 0; v < 12; ++v) f.ave_q[v] = S.ave_q[v];
+        for (int v = 0; v < 16; ++v) f.ave_f[v] = S.ave_f[v];
+        for (int v = 0; v < 7; ++v) f.ave_n[v] = S.ave_n[v];
+        f.oop_q = S.oop_q; f.Hbcl = S.Hbcl; f.Hbcl_e = S.Hbcl_e; f.cL = S.cL; f.cR = S.cR; f.lam = S.lam; f.pbl = S.pbl; f.pbr = S.pbr;
+        f.qp_dp = qprime[0 * S.nl + S.nl - 1]; f.qp_u = qprime[1 * S.nl + S.nl - 1]; f.qp_v = qprime[2 * S.nl + S.nl - 1];
+        f.S = (double)(S.kstages * S.N_btp); f.N_inv = 1.0 / (double)(S.kstages * S.N_btp); f.cd_over_g = S.cd / S.g;
+        f.botfr = S.botfr;
+        size_t sm = (sops_doubles_host(S.ngl, S.nq) + 6 * S.npts + 6 * S.ngl * S.nq) * sizeof(double);
+        k_btp_finalize<<<S.nelem, threads_for(S), sm, S.stream>>>(f);
+        S.n_launches++;
+        // halo copy of the averaged LDG gradient traces (graduvb_face_ave side 2 on processor boundaries)
+        if (S.nhalo > 0) {
+            size_t hs = S.h_gub.stride;
+            for (int v = 0; v < 4; ++v)
+                cudaMemcpyAsync(S.h_gub[v], S.trace[cur].p + (size_t)(3 + v) * S.trace[cur].stride + (size_t)S.nslots * S.ngl,
+                                hs * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
+            k_scale<<<nblk(4 * hs), 256, 0, S.stream>>>(S.h_gub.p, f.N_inv, 4 * hs);
+            S.n_launches++;
+        }
+    }
+    HN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// btp_bcl_coeffs_qdf (mod_barotropic_terms.F90:219-409)
+int btp_bcl_coeffs(Solver& S, const Planes& qprime, const Planes& dpv) {
+    if (halo_exchange_nodal(S, qprime.p, 3 * S.nl, qprime.stride, S.h_q)) return -1;
+    CoeffArgs a; memset(&a, 0, sizeof(a));
+    a.M = S.mesh; a.qprime = qprime.p; a.dpv = dpv.p; a.nstride = qprime.stride; a.hq = S.h_q.p; a.hstride = S.h_q.stride;
+    a.Quu = S.Quu; a.Quv = S.Quv; a.Qvv = S.Qvv; a.Hbcl = S.Hbcl; a.Quu_e = S.Quu_e; a.Quv_e = S.Quv_e; a.Qvv_e = S.Qvv_e; a.Hbcl_e = S.Hbcl_e;
+    a.dpp_graduv = S.dpp_graduv.p; a.btp_dpp_graduv = S.btp_dpp_graduv.p; a.pbprime_visc = S.pbprime_visc;
+    for (int k = 0; k < S.nl; ++k) a.alpha[k] = S.alpha[k];
+    a.has_visc = S.has_visc;
+    size_t sm = (sops_doubles_host(S.ngl, S.nq) + 3 * S.npts + 3 * S.ngl * S.nq + 12 * S.ngl) * sizeof(double);
+    k_bcl_coeffs<<<S.nelem, threads_for(S), sm, S.stream>>>(a);
+    S.n_launches++;
+    if (S.has_visc && S.nhalo > 0) {
+        // graduv_dpp_face exchange (mod_barotropic_terms.F90:393): per-layer planes and their layer sums
+        if (halo_exchange_nodal(S, S.dpp_graduv.p, 4 * S.nl, S.dpp_graduv.stride, S.h_dpg)) return -1;
+        if (halo_exchange_nodal(S, dpv.p, S.nl, dpv.stride, S.h_dpv)) return -1;
+        if (halo_exchange_nodal(S, S.btp_dpp_graduv.p, 4, S.btp_dpp_graduv.stride, S.h_stat)) return -1;
+        Planes last; last.p = S.h_stat[4]; last.stride = S.h_stat.stride; last.n = 1;
+        if (halo_exchange_nodal(S, S.pbprime_visc, 1, S.npoin, last)) return -1;
+    }
+    HN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int layer_mass_and_consistency(Solver& S, const Planes& qprime, Planes& q) {
+    // layer_mass_rhs + update of q_df(1) (mod_splitting.F90:58-78 / 217-232)
+    MassArgs m; memset(&m, 0, sizeof(m));
+    m.M = S.mesh; m.qprime = qprime.p; m.nstride = qprime.stride; m.hq = S.h_q.p; m.hstride = S.h_q.stride;
+    for (int v = 0; v < 12; ++v) m.ave_q[v] = S.ave_q[v];
+    for (int v = 0; v < 16; ++v) m.ave_f[v] = S.ave_f[v];
+    m.qdp = q[0]; m.slmf_q[0] = S.slmf_q[0]; m.slmf_q[1] = S.slmf_q[1]; m.slmf_f[0] = S.slmf_f[0]; m.slmf_f[1] = S.slmf_f[1];
+    m.massinv = S.massinv; m.flag = S.d_flag; m.dt = S.dt;
+    size_t per = S.ngl * S.nq;
+    size_t sm = (sops_doubles_host(S.ngl, S.nq) + 3 * S.npts + 3 * per + 12 * S.ngl + 2 * S.nq2 + 2 * per + S.npts + 4 * S.nq) * sizeof(double);
+    k_layer_mass<<<S.nelem, threads_for(S), sm, S.stream>>>(m);
+    S.n_launches++;
+    // apply_consistency (mod_splitting.F90:324-366)
+    if (halo_exchange_nodal(S, q[0], S.nl, q.stride, S.h_dp)) return -1;
+    ConsArgs c; memset(&c, 0, sizeof(c));
+    c.M = S.mesh; c.qdp_in = q[0]; c.qdp_out = S.qdp_tmp.p; c.nstride = q.stride; c.hdp = S.h_dp.p; c.hstride = S.h_dp.stride;
+    c.pbprime_df = S.pbprime_df; c.pbn = S.pbn; c.pbprime_q = S.pbprime_q; c.pbf_l = S.pbf_l; c.pbf_r = S.pbf_r; c.massinv = S.massinv;
+    for (int v = 0; v < 12; ++v) c.ave_q[v] = S.ave_q[v];
+    for (int v = 0; v < 16; ++v) c.ave_f[v] = S.ave_f[v];
+    c.slmf_q[0] = S.slmf_q[0]; c.slmf_q[1] = S.slmf_q[1]; c.slmf_f[0] = S.slmf_f[0]; c.slmf_f[1] = S.slmf_f[1];
+    c.dt = S.dt;
+    sm = (sops_doubles_host(S.ngl, S.nq) + (size_t)S.nl * S.npts + 4 * S.nl * S.ngl + per + 2 * S.nq2 + 2 * per + S.npts + 4 * S.nq) * sizeof(double);
+    k_consistency<<<S.nelem, threads_for(S), sm, S.stream>>>(c);
+    S.n_launches++;
+    cudaMemcpyAsync(q[0], S.qdp_tmp.p, (size_t)S.nl * q.stride * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
+    return 0;
+}
+
+static int momentum_update(Solver& S, const Planes& qprime_in, Planes& q, Planes& qprime_out, const Planes& qb, int full_prime) {
+    size_t per = S.ngl * S.nq;
+    if (S.has_visc) {
+        LapArgs l; memset(&l, 0, sizeof(l));
+        l.M = S.mesh; l.dpv = S.dpv.p; l.dpp_graduv = S.dpp_graduv.p; l.nstride = S.dpv.stride;
+        for (int v = 0; v < 4; ++v) l.graduvb[v] = S.ave_n[3 + v];
+        l.h_dpv = S.h_dpv.p; l.h_dpg = S.h_dpg.p; l.h_gub = S.h_gub.p; l.hstride = S.h_dpv.stride;
+        l.massinv = S.massinv; l.rhs_visc = S.rhs_visc.p; l.visc = S.visc;
+        size_t sm = (sops_doubles_host(S.ngl, S.nq) + 8 * S.npts + 8 * S.ngl) * sizeof(double);
+        k_bcl_laplacian<<<S.nelem, threads_for(S), sm, S.stream>>>(l);
+        S.n_launches++;
+    }
+    MomVolArgs v; memset(&v, 0, sizeof(v));
+    v.M = S.mesh; v.qprime = qprime_in.p; v.q = q.p; v.nstride = q.stride;
+    for (int i = 0; i < 12; ++i) v.ave_q[i] = S.ave_q[i];
+    v.ope2_df = S.ave_n[0]; v.zbot_df = S.zbot_df; v.tauwx_q = S.tauw_q; v.tauwy_q = S.tauw_q + S.npoin_q; v.pbprime_q = S.pbprime_q;
+    v.rhs_mom = S.rhs_mom.p;
+    for (int k = 0; k < S.nl; ++k) v.alpha[k] = S.alpha[k];
+    v.g = S.g;
+    size_t sm = (sops_doubles_host(S.ngl, S.nq) + 5 * S.npts + 6 * per + 6 * S.nq2 + 4 * per + 2 * S.npts) * sizeof(double);
+    k_mom_volume<<<S.nelem, threads_for(S), sm, S.stream>>>(v);
+    S.n_launches++;
+    MomFaceArgs f; memset(&f, 0, sizeof(f));
+    f.M = S.mesh; f.qprime = qprime_in.p; f.q = q.p; f.qprime_out = qprime_out.p; f.nstride = q.stride; f.hq = S.h_q.p; f.hstride = S.h_q.stride;
+    for (int i = 0; i < 3; ++i) f.qb[i] = qb[i];
+    f.pbprime_df = S.pbprime_df;
+    for (int i = 0; i < 16; ++i) f.ave_f[i] = S.ave_f[i];
+    f.zbf_l = S.zbf_l; f.zbf_r = S.zbf_r; f.rhs_mom = S.rhs_mom.p; f.rhs_visc = S.rhs_visc.p;
+    f.massinv = S.massinv; f.a_bcl = S.a_bcl; f.b_bcl = S.b_bcl; f.fdt2 = S.fdt2;
+    for (int k = 0; k < S.nl; ++k) f.alpha[k] = S.alpha[k];
+    f.g = S.g; f.dt = S.dt; f.full_prime = full_prime;
+    sm = (sops_doubles_host(S.ngl, S.nq) + 24 * (size_t)S.nl * S.ngl + 8 * (size_t)S.nl * S.nq) * sizeof(double);
+    k_mom_faces_update<<<S.nelem, threads_for(S), sm, S.stream>>>(f);
+    S.n_launches++;
+    return 0;
+}
+
+static void dcopy(Solver& S, double* dst, const double* src, size_t n) {
+    cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
+}
+
+// ti_rk_bcl (ti_rk_bcl.F90:9-87)
+int bcl_step(Solver& S) {
+    const size_t NL3 = (size_t)3 * S.nl * S.npoin, NL1 = (size_t)S.nl * S.npoin;
+    cudaEvent_t e_start, e_stop;
+    take_event_pair(S, 1, e_start, e_stop);
+    cudaEventRecord(e_start, S.stream);
+    // ---- prediction
+    dcopy(S, S.qbp.p, S.qb.p, 3 * (size_t)S.npoin);
+    dcopy(S, S.dpv.p, S.qprime[0], NL1);
+    if (btp_bcl_coeffs(S, S.qprime, S.dpv)) return -1;   // also refreshes the halo copy of qprime traces
+    if (btp_solve(S, S.qbp, S.qprime)) return -1;
+    dcopy(S, S.q2.p, S.q.p, NL3);
+    if (layer_mass_and_consistency(S, S.qprime, S.q2)) return -1;
+    if (momentum_update(S, S.qprime, S.q2, S.qprime2, S.qbp, 1)) return -1;
+    // ---- correction
+    k_average<<<nblk(NL3), 256, 0, S.stream>>>(S.qprime2.p, S.qprime2.p, S.qprime.p, NL3);
+    S.n_launches++;
+    dcopy(S, S.dpv.p, S.qprime2[0], NL1);
+    if (btp_bcl_coeffs(S, S.qprime2, S.dpv)) return -1;
+    if (btp_solve(S, S.qb, S.qprime2)) return -1;
+    if (layer_mass_and_consistency(S, S.qprime2, S.q)) return -1;
+    k_thickness_finish<<<nblk(S.npoin), 256, 0, S.stream>>>(S.q[0], S.pbprime_df, S.qprime[0], S.dpprime2.p, S.qprime2[0], S.nl, S.q.stride, S.npoin);
+    S.n_launches++;
+    if (halo_exchange_nodal(S, S.qprime2.p, 3 * S.nl, S.qprime2.stride, S.h_q)) return -1;
+    if (momentum_update(S, S.qprime2, S.q, S.qprime3, S.qb, 0)) return -1;
+    dcopy(S, S.qprime[0], S.dpprime2.p, NL1);
+    dcopy(S, S.qprime[S.nl], S.qprime3[S.nl], 2 * NL1);
+    cudaEventRecord(e_stop, S.stream);
+    S.n_steps++;
+    HN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static void harvest_events(Solver& S) {
+    if (S.ev_used == 0) return;
+    cudaStreamSynchronize(S.stream);
+    for (size_t i = 0; i < S.ev_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, S.ev_pool[2 * i], S.ev_pool[2 * i + 1]) != cudaSuccess) continue;
+        if (S.ev_kind[i] == 0) { S.ms_btp += ms; S.ms_btp_last = ms; } else { S.ms_step += ms; S.ms_step_last = ms; }
+    }
+    S.ev_used = 0;
+}
+
+}  // namespace hn
+
+// =================================================================================================================
+using namespace hn;
+
+struct hnumo_handle_s { Solver S; };
+
+extern "C" {
+
+const char* hnumo_last_error(void) { return g_err; }
+
+int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
+    if (!d || !out) { set_error("hnumo_init", "null argument"); return -2; }
+    if (d->abi_version != HNUMO_ABI_VERSION) { set_error("hnumo_init", "ABI version mismatch"); return -2; }
+    if (d->ngl < 2 || d->ngl > HN_MAXNGL || d->nq > HN_MAXNQ || d->nlayers < 1 || d->nlayers > HN_MAXL || d->kstages < 1 || d->kstages > 5) {
+        set_error("hnumo_init", "unsupported sizes (ngl<=9, nq<=17, nlayers<=20, kstages<=5)"); return -2;
+    }
+    if (d->method_visc == 1 || d->ad_mlswe > 0.0) {
+        set_error("hnumo_init", "method_visc==1 and ad_mlswe>0 are not implemented (SURVEY 8(f) rank 4)"); return -3;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("hnumo_init", "no CUDA device: this library has no CPU fallback"); return -1; }
+    hnumo_handle_s* H = new hnumo_handle_s();
+    Solver& S = H->S;
+    S.desc = *d;
+    if (d->device > 0) cudaSetDevice(d->device - 1);
+    cudaGetDevice(&S.device);
+    HN_CUDA(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+    HN_CUDA(cudaStreamCreateWithFlags(&S.comm_stream, cudaStreamNonBlocking));
+    cudaEventCreate(&S.ev0); cudaEventCreate(&S.ev1); cudaEventCreate(&S.ev2); cudaEventCreate(&S.ev3);
+    S.nelem = d->nelem; S.ngl = d->ngl; S.nq = d->nq; S.npts = d->ngl * d->ngl; S.nq2 = d->nq * d->nq; S.nl = d->nlayers; S.nface = d->nface;
+    S.npoin = S.nelem * S.npts; S.npoin_q = S.nelem * S.nq2; S.nslots = S.nelem * 4;
+    S.kstages = d->kstages; S.N_btp = d->N_btp; S.botfr = d->botfr; S.dt = d->dt; S.dt_btp = d->dt_btp; S.g = d->gravity; S.cd = d->cd_mlswe;
+    S.visc = d->visc_mlswe; S.has_visc = (d->visc_mlswe != 0.0);
+    S.variant = d->stage_kernel_variant;
+    for (int k = 0; k < S.nl; ++k) S.alpha[k] = d->alpha_mlswe[k];
+    for (int ik = 0; ik < S.kstages; ++ik) {
+        for (int c = 0; c < 3; ++c) S.ssprk_a[ik][c] = d->ssprk_a[ik + S.kstages * c];
+        S.ssprk_beta[ik] = d->ssprk_beta[ik];
+    }
+    // operators
+    memset(&S.ops, 0, sizeof(S.ops));
+    for (int i = 0; i < S.ngl * S.nq; ++i) { S.ops.A[i] = d->psiq[i]; S.ops.B[i] = d->dpsiq[i]; }
+    for (int i = 0; i < S.ngl * S.ngl; ++i) S.ops.D[i] = d->dpsi[i];
+    for (int i = 0; i < S.nq; ++i) S.ops.wq[i] = d->wnq[i];
+    for (int i = 0; i < S.ngl; ++i) S.ops.wg[i] = d->wgl[i];
+    upload_ops(S.ops);
+    upload_fused_ops(S.ops, S.ngl, S.nq);
+    // connectivity from face(8,nface)
+    std::vector<int> nbr(S.nslots, -99), nbslot(S.nslots, 0);
+    std::vector<double> fgeom((size_t)S.nslots * 3, 0.0);
+    S.face_owner_slot.assign(S.nface, -1); S.face_right_slot.assign(S.nface, -1); S.face_er.assign(S.nface, 0);
+    auto slot_of = [](int iloc) { return iloc - 3; };
+    std::vector<int> halo_of_face(S.nface, -1);
+    // halo faces are numbered in the exchange order of nbh_send_recv
+    S.nhalo = 0;
+    S.nbh_rank.clear(); S.nbh_count.clear(); S.nbh_offset.clear();
+    if (d->num_nbh > 0) {
+        int off = 0;
+        for (int i = 0; i < d->num_nbh; ++i) {
+            S.nbh_rank.push_back(d->nbh_proc[i] - 1); S.nbh_count.push_back(d->num_send_recv[i]); S.nbh_offset.push_back(off);
+            for (int j = 0; j < d->num_send_recv[i]; ++j) halo_of_face[d->nbh_send_recv[off + j] - 1] = off + j;
+            off += d->num_send_recv[i];
+        }
+        S.nhalo = off;
+    }
+    S.halo_slot.assign(S.nhalo, -1);
+    for (int f = 0; f < S.nface; ++f) {
+        const int32_t* F = d->face + (size_t)8 * f;
+        int ilocl = F[4], ilocr = F[5], el = F[6] - 1, er = F[7];
+        if (ilocl < 3 || ilocl > 6 || el < 0 || el >= S.nelem) { set_error("hnumo_init", "face table: only 2-D xy faces (local face 3..6) are supported"); delete H; return -2; }
+        int sl = el * 4 + slot_of(ilocl);
+        S.face_owner_slot[f] = sl; S.face_er[f] = er;
+        const double* G = d->face_geom + (size_t)3 * f;
+        fgeom[(size_t)sl * 3 + 0] = G[0]; fgeom[(size_t)sl * 3 + 1] = G[1]; fgeom[(size_t)sl * 3 + 2] = G[2];
+        if (er > 0) {
+            int sr = (er - 1) * 4 + slot_of(ilocr);
+            S.face_right_slot[f] = sr;
+            nbr[sl] = er - 1; nbslot[sl] = slot_of(ilocr);
+            nbr[sr] = el; nbslot[sr] = slot_of(ilocl);
+            fgeom[(size_t)sr * 3 + 0] = G[0]; fgeom[(size_t)sr * 3 + 1] = G[1]; fgeom[(size_t)sr * 3 + 2] = G[2];
+            if (!(el < er - 1)) { set_error("hnumo_init", "face table: left element must have the lower number (p4est.c:1693)"); delete H; return -2; }
+        } else if (er == 0) {
+            if (halo_of_face[f] < 0) { set_error("hnumo_init", "processor face missing from nbh_send_recv"); delete H; return -2; }
+            nbr[sl] = NBR_HALO; nbslot[sl] = halo_of_face[f];
+            S.halo_slot[halo_of_face[f]] = sl;
+        } else if (er == -4 || er == -2) {
+            nbr[sl] = er;
+        } else { set_error("hnumo_init", "unsupported boundary code in face(8,:) (only -4 free slip, -2 no slip)"); delete H; return -2; }
+    }
+    for (int s = 0; s < S.nslots; ++s)
+        if (nbr[s] == -99) { set_error("hnumo_init", "face table does not cover every element side"); delete H; return -2; }
+    HN_CUDA(cudaMalloc(&S.d_nbr, S.nslots * sizeof(int))); HN_CUDA(cudaMalloc(&S.d_nbslot, S.nslots * sizeof(int)));
+    cudaMemcpy(S.d_nbr, nbr.data(), S.nslots * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(S.d_nbslot, nbslot.data(), S.nslots * sizeof(int), cudaMemcpyHostToDevice);
+    S.d_fgeom = dalloc(S, (size_t)S.nslots * 3); S.d_em = dalloc(S, (size_t)S.nelem * 5);
+    cudaStreamSynchronize(S.stream);
+    cudaMemcpy(S.d_fgeom, fgeom.data(), fgeom.size() * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(S.d_em, d->elem_metrics, (size_t)S.nelem * 5 * sizeof(double), cudaMemcpyHostToDevice);
+    if (S.nhalo > 0) {
+        HN_CUDA(cudaMalloc(&S.d_halo_slot, S.nhalo * sizeof(int)));
+        cudaMemcpy(S.d_halo_slot, S.halo_slot.data(), S.nhalo * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    Mesh& M = S.mesh;
+    M.nelem = S.nelem; M.ngl = S.ngl; M.nq = S.nq; M.npts = S.npts; M.nq2 = S.nq2; M.nl = S.nl; M.npoin = S.npoin; M.npoin_q = S.npoin_q;
+    M.nslots = S.nslots; M.nbr = S.d_nbr; M.nbslot = S.d_nbslot; M.fgeom = S.d_fgeom; M.em = S.d_em;
+    // nodal statics
+    const size_t NP = S.npoin, NQ = S.npoin_q, NS = (size_t)S.nslots * S.nq;
+    auto up = [&](const double* h, size_t n) { double* p = dalloc(S, n); cudaStreamSynchronize(S.stream); cudaMemcpy(p, h, n * sizeof(double), cudaMemcpyHostToDevice); return p; };
+    S.pbprime_df = up(d->pbprime_df, NP); S.massinv = up(d->massinv, NP); S.coriolis_df = up(d->coriolis_df, NP); S.zbot_df = up(d->zbot_df, NP);
+    S.tauw_df = dalloc(S, 2 * NP);
+    {
+        double* stage = up(d->tau_wind_df, 2 * NP);
+        k_aos_to_planes<<<nblk(NP), 256, 0, S.stream>>>(stage, S.tauw_df, 2, 0, 2, 1, NP, NP);
+    }
+    S.oop_df = dalloc(S, NP); S.a_bcl = dalloc(S, NP); S.b_bcl = dalloc(S, NP); S.fdt2 = dalloc(S, NP);
+    k_recip_guard<<<nblk(NP), 256, 0, S.stream>>>(S.pbprime_df, S.oop_df, NP);
+    k_coriolis_coeffs<<<nblk(NP), 256, 0, S.stream>>>(S.coriolis_df, S.dt, S.fdt2, S.a_bcl, S.b_bcl, NP);
+    // quad statics
+    S.pbprime_q = dalloc(S, NQ); S.oop_q = dalloc(S, NQ); S.coriolis_q = dalloc(S, NQ); S.tauw_q = dalloc(S, 2 * NQ); S.gradzb_q = dalloc(S, 2 * NQ);
+    double* zbot_q = dalloc(S, NQ);
+    int T = threads_for(S);
+    k_nodal_to_quad<<<S.nelem, T, 0, S.stream>>>(M, S.pbprime_df, S.pbprime_q, 0);
+    k_recip_guard<<<nblk(NQ), 256, 0, S.stream>>>(S.pbprime_q, S.oop_q, NQ);
+    k_nodal_to_quad<<<S.nelem, T, 0, S.stream>>>(M, S.coriolis_df, S.coriolis_q, 0);
+    k_nodal_to_quad<<<S.nelem, T, 0, S.stream>>>(M, S.tauw_df, S.tauw_q, 0);
+    k_nodal_to_quad<<<S.nelem, T, 0, S.stream>>>(M, S.tauw_df + NP, S.tauw_q + NQ, 0);
+    k_nodal_to_quad<<<S.nelem, T, 0, S.stream>>>(M, S.zbot_df, zbot_q, 0);
+    k_nodal_to_quad<<<S.nelem, T, 0, S.stream>>>(M, S.zbot_df, S.gradzb_q, 1);
+    k_nodal_to_quad<<<S.nelem, T, 0, S.stream>>>(M, S.zbot_df, S.gradzb_q + NQ, 2);
+    // slot statics
+    S.cL = dalloc(S, NS); S.cR = dalloc(S, NS); S.cLR = dalloc(S, NS); S.lam = dalloc(S, NS); S.oop_edge = dalloc(S, NS);
+    S.pbf_l = dalloc(S, NS); S.pbf_r = dalloc(S, NS); S.zbf_l = dalloc(S, NS); S.zbf_r = dalloc(S, NS); S.pbl = dalloc(S, NS); S.pbr = dalloc(S, NS);
+    S.pbn = dalloc(S, (size_t)S.nslots * S.ngl);
+    {
+        FaceStatArgs a; memset(&a, 0, sizeof(a));
+        a.M = M; a.pbprime_df = S.pbprime_df; a.pbprime_q = S.pbprime_q; a.zbot_q = zbot_q;
+        a.cL = S.cL; a.cR = S.cR; a.cLR = S.cLR; a.lam = S.lam; a.oop_edge = S.oop_edge; a.pbf_l = S.pbf_l; a.pbf_r = S.pbf_r;
+        a.zbf_l = S.zbf_l; a.zbf_r = S.zbf_r; a.pbl = S.pbl; a.pbr = S.pbr; a.pbn = S.pbn; a.alpha_bot = S.alpha[S.nl - 1];
+        k_face_statics<<<S.nelem, T, 0, S.stream>>>(a);
+    }
+    // state + work
+    const int nl = S.nl;
+    S.qb = palloc(S, 3, NP); S.q = palloc(S, 3 * nl, NP); S.qprime = palloc(S, 3 * nl, NP);
+    S.qbp = palloc(S, 3, NP); S.q2 = palloc(S, 3 * nl, NP); S.qprime2 = palloc(S, 3 * nl, NP); S.qprime3 = palloc(S, 3 * nl, NP);
+    S.dpv = palloc(S, nl, NP); S.qdp_tmp = palloc(S, nl, NP); S.dpprime2 = palloc(S, nl, NP);
+    S.qb0 = palloc(S, 3, NP); S.qb2w = palloc(S, 3, NP);
+    size_t trs = (size_t)(S.nslots + S.nhalo) * S.ngl;
+    S.trace[0] = palloc(S, TR_NV, trs); S.trace[1] = palloc(S, TR_NV, trs);
+    S.Quu = dalloc(S, NQ); S.Quv = dalloc(S, NQ); S.Qvv = dalloc(S, NQ); S.Hbcl = dalloc(S, NQ);
+    S.Quu_e = dalloc(S, NS); S.Quv_e = dalloc(S, NS); S.Qvv_e = dalloc(S, NS); S.Hbcl_e = dalloc(S, NS);
+    S.dpp_graduv = palloc(S, 4 * nl, NP); S.btp_dpp_graduv = palloc(S, 4, NP); S.pbprime_visc = dalloc(S, NP);
+    S.acc_n = palloc(S, 10, NP); S.acc_q = palloc(S, 8, NQ); S.acc_f = palloc(S, 11, NS);
+    S.ave_q = palloc(S, 12, NQ); S.ave_f = palloc(S, 16, NS); S.ave_n = palloc(S, 7, NP);
+    S.slmf_q = palloc(S, 2, NQ); S.slmf_f = palloc(S, 2, NS);
+    S.rhs_mom = palloc(S, 2 * nl, NP); S.rhs_visc = palloc(S, 2 * nl, NP);
+    S.stage_buf = dalloc(S, std::max((size_t)3 * nl * NP, 4 * NP));
+    size_t hs = (size_t)std::max(S.nhalo, 1) * S.ngl;
+    S.h_q = palloc(S, 3 * nl, hs); S.h_dp = palloc(S, nl, hs); S.h_dpv = palloc(S, nl, hs); S.h_dpg = palloc(S, 4 * nl, hs);
+    S.h_gub = palloc(S, 4, hs); S.h_stat = palloc(S, 5, hs);
+    S.halo_capacity = (size_t)std::max(7, 4 * nl) * hs;
+    S.d_send = dalloc(S, S.halo_capacity); S.d_recv = dalloc(S, S.halo_capacity);
+    HN_CUDA(cudaMalloc(&S.d_flag, sizeof(int)));
+    cudaMemsetAsync(S.d_flag, 0, sizeof(int), S.stream);
+    for (void* p : S.allocs) if (!p) { delete H; return -1; }
+    HN_CUDA(cudaStreamSynchronize(S.stream));
+    HN_CUDA(cudaGetLastError());
+    memset(&S.desc.psiq, 0, sizeof(void*));  // host pointers are not retained
+    *out = H;
+    return 0;
+}
+
+int hnumo_finalize(hnumo_handle_t h) {
+    if (!h) return -2;
+    Solver& S = h->S;
+    cudaStreamSynchronize(S.stream);
+    halo_comm_destroy(S);
+    for (void* p : S.allocs) cudaFree(p);
+    cudaFree(S.d_nbr); cudaFree(S.d_nbslot); cudaFree(S.d_flag); if (S.d_halo_slot) cudaFree(S.d_halo_slot);
+    cudaEventDestroy(S.ev0); cudaEventDestroy(S.ev1); cudaEventDestroy(S.ev2); cudaEventDestroy(S.ev3);
+    cudaStreamDestroy(S.stream); cudaStreamDestroy(S.comm_stream);
+    delete h;
+    return 0;
+}
+
+int hnumo_upload_state(hnumo_handle_t h, const double* q_df, const double* qb_df, const double* qprime_df) {
+    if (!h) return -2;
+    Solver& S = h->S;
+    const size_t NP = S.npoin;
+    HN_CUDA(cudaMemcpyAsync(S.stage_buf, qb_df, 4 * NP * sizeof(double), cudaMemcpyHostToDevice, S.stream));
+    k_aos_to_planes<<<nblk(NP), 256, 0, S.stream>>>(S.stage_buf, S.qb.p, 4, 1, 3, 1, NP, NP);
+    HN_CUDA(cudaMemcpyAsync(S.stage_buf, q_df, 3 * S.nl * NP * sizeof(double), cudaMemcpyHostToDevice, S.stream));
+    k_aos_to_planes<<<nblk(NP), 256, 0, S.stream>>>(S.stage_buf, S.q.p, 3, 0, 3, S.nl, NP, NP);
+    HN_CUDA(cudaMemcpyAsync(S.stage_buf, qprime_df, 3 * S.nl * NP * sizeof(double), cudaMemcpyHostToDevice, S.stream));
+    k_aos_to_planes<<<nblk(NP), 256, 0, S.stream>>>(S.stage_buf, S.qprime.p, 3, 0, 3, S.nl, NP, NP);
+    S.n_launches += 3;
+    HN_CUDA(cudaStreamSynchronize(S.stream));
+    return 0;
+}
+
+int hnumo_download_state(hnumo_handle_t h, double* q_df, double* qb_df, double* qprime_df) {
+    if (!h) return -2;
+    Solver& S = h->S;
+    const size_t NP = S.npoin;
+    k_planes_to_aos<<<nblk(NP), 256, 0, S.stream>>>(S.stage_buf, S.qb.p, 4, 1, 3, 1, NP, NP);
+    k_pb_to_aos<<<nblk(NP), 256, 0, S.stream>>>(S.stage_buf, S.qb[0], S.pbprime_df, NP);
+    HN_CUDA(cudaMemcpyAsync(qb_df, S.stage_buf, 4 * NP * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+    k_planes_to_aos<<<nblk(NP), 256, 0, S.stream>>>(S.stage_buf, S.q.p, 3, 0, 3, S.nl, NP, NP);
+    HN_CUDA(cudaMemcpyAsync(q_df, S.stage_buf, 3 * S.nl * NP * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+    k_planes_to_aos<<<nblk(NP), 256, 0, S.stream>>>(S.stage_buf, S.qprime.p, 3, 0, 3, S.nl, NP, NP);
+    HN_CUDA(cudaMemcpyAsync(qprime_df, S.stage_buf, 3 * S.nl * NP * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+    S.n_launches += 4;
+    HN_CUDA(cudaStreamSynchronize(S.stream));
+    return 0;
+}
+
+static int check_flag(Solver& S) {
+    int flag = 0;
+    if (cudaMemcpyAsync(&flag, S.d_flag, sizeof(int), cudaMemcpyDeviceToHost, S.stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(S.stream) != cudaSuccess) { set_error("hnumo_step", cudaGetErrorString(cudaGetLastError())); return -1; }
+    if (flag) { set_error("hnumo_step", "Negative mass in thickness at some points (mod_splitting.F90:74-77)"); return 1; }
+    return 0;
+}
+
+int hnumo_step(hnumo_handle_t h, int32_t nsteps) {
+    if (!h) return -2;
+    Solver& S = h->S;
+    for (int i = 0; i < nsteps; ++i) {
+        if (bcl_step(S)) return -1;
+    }
+    int rc = check_flag(S);
+    harvest_events(S);
+    return rc;
+}
+
+int hnumo_ti_rk_bcl(hnumo_handle_t h, double* q_df, double* qb_df, double* qprime_df) {
+    int rc = hnumo_upload_state(h, q_df, qb_df, qprime_df);
+    if (rc) return rc;
+    rc = hnumo_step(h, 1);
+    if (rc < 0) return rc;
+    int rc2 = hnumo_download_state(h, q_df, qb_df, qprime_df);
+    return rc2 ? rc2 : rc;
+}
+
+int hnumo_btp_bcl_coeffs(hnumo_handle_t h) {
+    if (!h) return -2;
+    Solver& S = h->S;
+    cudaMemcpyAsync(S.dpv.p, S.qprime[0], (size_t)S.nl * S.npoin * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
+    if (btp_bcl_coeffs(S, S.qprime, S.dpv)) return -1;
+    HN_CUDA(cudaStreamSynchronize(S.stream));
+    return 0;
+}
+
+int hnumo_btp_substeps(hnumo_handle_t h) {
+    if (!h) return -2;
+    Solver& S = h->S;
+    if (btp_solve(S, S.qb, S.qprime)) return -1;
+    harvest_events(S);
+    HN_CUDA(cudaStreamSynchronize(S.stream));
+    return 0;
+}
+
+int hnumo_rhs_btp(hnumo_handle_t h, double* rhs) {
+    if (!h) return -2;
+    Solver& S = h->S;
+    double* d_rhs = S.rhs_mom.p;  // scratch: 3 planes
+    if (rhs_btp_only(S, S.qb, S.qprime, d_rhs)) return -1;
+    k_planes_to_aos<<<nblk(S.npoin), 256, 0, S.stream>>>(S.stage_buf, d_rhs, 3, 0, 3, 1, S.npoin, S.npoin);
+    HN_CUDA(cudaMemcpyAsync(rhs, S.stage_buf, 3 * (size_t)S.npoin * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+    HN_CUDA(cudaStreamSynchronize(S.stream));
+    return 0;
+}
+
+// reference-layout export of work arrays (tests)
+int64_t hnumo_get_array(hnumo_handle_t h, const char* name, double* out, int64_t capacity) {
+    if (!h) return -2;
+    Solver& S = h->S;
+    cudaStreamSynchronize(S.stream);
+    const size_t NP = S.npoin, NQ = S.npoin_q;
+    std::string nm(name);
+    auto copy_planes = [&](std::vector<const double*> planes, size_t n) -> int64_t {
+        // AoS (nv, n) from nv planes
+        size_t nv = planes.size();
+        if ((int64_t)(nv * n) > capacity) return -4;
+        std::vector<double> tmp(n);
+        for (size_t v = 0; v < nv; ++v) {
+            cudaMemcpy(tmp.data(), planes[v], n * sizeof(double), cudaMemcpyDeviceToHost);
+            for (size_t i = 0; i < n; ++i) out[i * nv + v] = tmp[i];
+        }
+        return (int64_t)(nv * n);
+    };
+    // face arrays: (nv, [2 sides], nq, nface) built from slot planes
+    auto copy_face = [&](std::vector<const double*> planes, bool) -> int64_t {
+        size_t nv = planes.size(), n = (size_t)S.nface * S.nq;
+        if ((int64_t)(nv * n) > capacity) return -4;
+        std::vector<double> tmp((size_t)S.nslots * S.nq);
+        for (size_t v = 0; v < nv; ++v) {
+            cudaMemcpy(tmp.data(), planes[v], tmp.size() * sizeof(double), cudaMemcpyDeviceToHost);
+            for (int f = 0; f < S.nface; ++f)
+                for (int iq = 0; iq < S.nq; ++iq) out[((size_t)f * S.nq + iq) * nv + v] = tmp[(size_t)S.face_owner_slot[f] * S.nq + iq];
+        }
+        return (int64_t)(nv * n);
+    };
+    if (nm == "Q_uu_dp") return copy_planes({S.Quu}, NQ);
+    if (nm == "Q_uv_dp") return copy_planes({S.Quv}, NQ);
+    if (nm == "Q_vv_dp") return copy_planes({S.Qvv}, NQ);
+    if (nm == "H_bcl") return copy_planes({S.Hbcl}, NQ);
+    if (nm == "Q_uu_dp_edge") return copy_face({S.Quu_e}, false);
+    if (nm == "Q_uv_dp_edge") return copy_face({S.Quv_e}, false);
+    if (nm == "Q_vv_dp_edge") return copy_face({S.Qvv_e}, false);
+    if (nm == "H_bcl_edge") return copy_face({S.Hbcl_e}, false);
+    if (nm == "ope_ave") return copy_planes({S.ave_q[0]}, NQ);
+    if (nm == "H_ave") return copy_planes({S.ave_q[1]}, NQ);
+    if (nm == "Qu_ave") return copy_planes({S.ave_q[2]}, NQ);
+    if (nm == "Qv_ave") return copy_planes({S.ave_q[3]}, NQ);
+    if (nm == "Quv_ave") return copy_planes({S.ave_q[4]}, NQ);
+    if (nm == "ope2_ave") return copy_planes({S.ave_q[5]}, NQ);
+    if (nm == "btp_mass_flux_ave") return copy_planes({S.ave_q[6], S.ave_q[7]}, NQ);
+    if (nm == "uvb_ave") return copy_planes({S.ave_q[8], S.ave_q[9]}, NQ);
+    if (nm == "tau_bot_ave") return copy_planes({S.ave_q[10], S.ave_q[11]}, NQ);
+    if (nm == "ope2_ave_df") return copy_planes({S.ave_n[0]}, NP);
+    if (nm == "uvb_ave_df") return copy_planes({S.ave_n[1], S.ave_n[2]}, NP);
+    if (nm == "graduvb_ave") return copy_planes({S.ave_n[3], S.ave_n[4], S.ave_n[5], S.ave_n[6]}, NP);
+    if (nm == "btp_dpp_graduv") return copy_planes({S.btp_dpp_graduv[0], S.btp_dpp_graduv[1], S.btp_dpp_graduv[2], S.btp_dpp_graduv[3]}, NP);
+    if (nm == "pbprime_visc") return copy_planes({S.pbprime_visc}, NP);
+    if (nm == "btp_mass_flux_face_ave") return copy_face({S.ave_f[0], S.ave_f[1]}, false);
+    if (nm == "H_face_ave") return copy_face({S.ave_f[2]}, false);
+    if (nm == "Qu_face_ave") return copy_face({S.ave_f[3], S.ave_f[4]}, false);
+    if (nm == "Qv_face_ave") return copy_face({S.ave_f[5], S.ave_f[6]}, false);
+    if (nm == "ope_face_ave") return copy_face({S.ave_f[7], S.ave_f[8]}, false);
+    if (nm == "ope2_face_ave") return copy_face({S.ave_f[9], S.ave_f[10]}, false);
+    if (nm == "one_plus_eta_edge_2_ave") return copy_face({S.ave_f[11]}, false);
+    if (nm == "uvb_face_ave") return copy_face({S.ave_f[12], S.ave_f[14], S.ave_f[13], S.ave_f[15]}, false);  // (2 comp, 2 side)
+    if (nm == "sum_layer_mass_flux") return copy_planes({S.slmf_q[0], S.slmf_q[1]}, NQ);
+    if (nm == "sum_layer_mass_flux_face") return copy_face({S.slmf_f[0], S.slmf_f[1]}, false);
+    if (nm == "coriolis_quad") return copy_planes({S.coriolis_q}, NQ);
+    if (nm == "tau_wind") return copy_planes({S.tauw_q, S.tauw_q + NQ}, NQ);
+    if (nm == "grad_zbot_quad") return copy_planes({S.gradzb_q, S.gradzb_q + NQ}, NQ);
+    if (nm == "pbprime") return copy_planes({S.pbprime_q}, NQ);
+    if (nm == "one_over_pbprime") return copy_planes({S.oop_q}, NQ);
+    if (nm == "coeff_pbpert_L") return copy_face({S.cL}, false);
+    if (nm == "coeff_pbpert_R") return copy_face({S.cR}, false);
+    if (nm == "coeff_pbub_LR") return copy_face({S.cLR}, false);
+    if (nm == "coeff_mass_pbpert_LR") return copy_face({S.lam}, false);
+    if (nm == "one_over_pbprime_edge") return copy_face({S.oop_edge}, false);
+    if (nm == "pbprime_face") return copy_face({S.pbf_l, S.pbf_r}, false);
+    if (nm == "zbot_face") return copy_face({S.zbf_l, S.zbf_r}, false);
+    if (nm == "a_bcl") return copy_planes({S.a_bcl}, NP);
+    if (nm == "b_bcl") return copy_planes({S.b_bcl}, NP);
+    set_error("hnumo_get_array", "unknown array name");
+    return -5;
+}
+
+int hnumo_comm_get_unique_id(void* id128) { return halo_get_unique_id(id128); }
+int hnumo_comm_init(hnumo_handle_t h, const void* id128) { return h ? halo_comm_init(h->S, id128) : -2; }
+
+int hnumo_timing(hnumo_handle_t h, double* out8, int32_t reset) {
+    if (!h) return -2;
+    Solver& S = h->S;
+    harvest_events(S);
+    out8[0] = S.ms_btp; out8[1] = (double)S.n_stages; out8[2] = S.ms_step; out8[3] = (double)S.n_steps; out8[4] = (double)S.n_launches;
+    out8[5] = S.ms_btp_last; out8[6] = S.ms_step_last; out8[7] = 0.0;
+    if (reset) { S.ms_btp = 0; S.ms_step = 0; S.n_stages = 0; S.n_steps = 0; S.n_launches = 0; }
+    return 0;
+}
+
+int hnumo_set_option(hnumo_handle_t h, const char* key, double value) {
+    if (!h) return -2;
+    Solver& S = h->S;
+    if (!strcmp(key, "stage_kernel_variant")) { S.variant = (int)value; return 0; }
+    if (!strcmp(key, "use_graph")) { S.use_graph = (int)value; return 0; }
+    set_error("hnumo_set_option", "unknown key");
+    return -2;
+}
+
+}  // extern "C"

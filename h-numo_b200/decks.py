@@ -1,0 +1,358 @@
+"""Brick decks: the arrays the Fortran driver of h-NUMO hands to the hot path.
+
+This module stands in for the parts of the reference that stay Fortran (input deck, p4est brick mesh, basis,
+metrics, initial conditions) when the library is driven from Python (tests, bench.py).  It produces exactly the
+members of ``hnumo_desc_t`` (include/hnumo_b200.h) plus the initial state, for one rank of a row-block partition.
+
+Reference formulas restated here (set-up only, not on the hot path):
+  LGL nodes/weights, Lagrange tables     src/mod_legendre.F90:54-111,248-322,387-433, src/mod_basis.F90:60-186
+  brick coordinates, face table          src/p4est.c:157-242,1560-1735, src/mod_p4est.F90:344-359
+  initial conditions, statics            src/initial_conditions.F90:86-416, src/mod_initial_mlswe.F90:287-350,652-678
+"""
+import math
+
+import numpy as np
+
+GRAVITY = 9.806  # initial_conditions.F90:97,132,173
+PI_TRIG = 3.1415926535897932346
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _legendre_poly(n, x):
+    p2 = p2_1 = p2_2 = 0.0
+    p1 = p1_1 = p1_2 = 0.0
+    p0, p0_1, p0_2 = 1.0, 0.0, 0.0
+    for j in range(1, n + 1):
+        p2, p2_1, p2_2 = p1, p1_1, p1_2
+        p1, p1_1, p1_2 = p0, p0_1, p0_2
+        a = (2.0 * j - 1.0) / j
+        b = (j - 1.0) / j
+        p0 = a * x * p1 - b * p2
+        p0_1 = a * (p1 + x * p1_1) - b * p2_1
+        p0_2 = a * (2.0 * p1_1 + x * p1_2) - b * p2_2
+    return p0, p0_1, p0_2
+
+
+def lgl(ngl):
+    """Legendre-Gauss-Lobatto points and weights (mod_legendre.F90:54-111)."""
+    x = np.zeros(ngl)
+    w = np.zeros(ngl)
+    if ngl == 1:
+        return np.array([0.0]), np.array([2.0])
+    n = ngl - 1
+    nh = (n + 1) // 2
+    eps = np.finfo(float).eps
+    pi = 4.0 * math.atan(1.0)
+    for i in range(1, nh + 1):
+        xx = math.cos((2.0 * i - 1.0) / (2.0 * n + 1.0) * pi)
+        p0 = 0.0
+        for _ in range(20):
+            p0, p0_1, p0_2 = _legendre_poly(n, xx)
+            dx = -(1.0 - xx * xx) * p0_1 / (-2.0 * xx * p0_1 + (1.0 - xx * xx) * p0_2)
+            xx = xx + dx
+            if abs(dx) < eps:
+                break
+        x[n + 1 - i] = xx
+        w[n + 1 - i] = 2.0 / (n * (n + 1) * p0 * p0)
+    if n + 1 != 2 * nh:
+        p0, _, _ = _legendre_poly(n, 0.0)
+        x[nh] = 0.0
+        w[nh] = 2.0 / (n * (n + 1) * p0 * p0)
+    for i in range(1, nh + 1):
+        x[i - 1] = -x[n + 1 - i]
+        w[i - 1] = w[n + 1 - i]
+    return x, w
+
+
+def basis(nop, dg_integ_exact=True):
+    """1-D operator tables of mod_basis: psiq(ngl,nq), dpsiq(ngl,nq), dpsi(ngl,ngl), weights."""
+    ngl = nop + 1
+    nq = 2 * nop + 1 if dg_integ_exact else 2 * nop - 1
+    xgl, wgl = lgl(ngl)
+    xnq, wnq = lgl(nq)
+    # legendre_basis, reduce_round_off branch
+    bb = np.zeros(ngl)
+    for j in range(ngl):
+        for i in range(ngl):
+            if i != j:
+                bb[j] += math.log(abs(xgl[j] - xgl[i]))
+    dpsi = np.zeros((ngl, ngl))  # dpsi[i, j] = l_i'(x_j)
+    cc = np.zeros(ngl)
+    for j in range(ngl):
+        for i in range(ngl):
+            if i != j:
+                sgn = 1.0 if (i + j) % 2 == 0 else -1.0
+                dpsi[i, j] = sgn * math.exp(bb[j] - bb[i]) / (xgl[j] - xgl[i])
+                cc[j] += dpsi[i, j]
+    for j in range(ngl):
+        dpsi[j, j] = -cc[j]
+    # lagrange_basis
+    psiq = np.zeros((ngl, nq))
+    dpsiq = np.zeros((ngl, nq))
+    for l in range(nq):
+        xl = xnq[l]
+        for i in range(ngl):
+            ksi = xgl[i]
+            p = 1.0
+            dp = 0.0
+            for j in range(ngl):
+                if j != i:
+                    p = p * (xl - xgl[j]) / (ksi - xgl[j])
+                    dd = 1.0
+                    for k in range(ngl):
+                        if k != i and k != j:
+                            dd = dd * (xl - xgl[k]) / (ksi - xgl[k])
+                    dp = dp + dd / (ksi - xgl[j])
+            psiq[i, l] = p
+            dpsiq[i, l] = dp
+    return dict(ngl=ngl, nq=nq, xgl=xgl, wgl=wgl, xnq=xnq, wnq=wnq, psiq=psiq, dpsiq=dpsiq, dpsi=dpsi)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+SHIPPED = {
+    # Examples/bump/numo3d.in == CI/bump/numo3d.in
+    "bump": dict(nelx=10, nely=10, nop=4, nlayers=2, xdims=(0.0, 2e3), ydims=(0.0, 2e3), x_boundary=(4, 4),
+                 y_boundary=(4, 4), dt=100.0, dt_btp=1.8, kstages=5, botfr=0, cd_mlswe=0.0, method_visc=0,
+                 visc_mlswe=0.0, f0=0.0, beta=0.0, test_case="bump"),
+    # Examples/lake/numo3d.in
+    "lake": dict(nelx=10, nely=10, nop=4, nlayers=2, xdims=(0.0, 2e3), ydims=(0.0, 2e3), x_boundary=(4, 4),
+                 y_boundary=(4, 4), dt=100.0, dt_btp=1.8, kstages=5, botfr=0, cd_mlswe=0.0, method_visc=0,
+                 visc_mlswe=0.0, f0=0.0, beta=0.0, test_case="lakeAtrest"),
+    # Examples/double_gyre/numo3d.in
+    "double_gyre": dict(nelx=25, nely=25, nop=4, nlayers=2, xdims=(0.0, 2e6), ydims=(0.0, 2e6), x_boundary=(4, 4),
+                        y_boundary=(4, 4), dt=500.0, dt_btp=25.0, kstages=5, botfr=1, cd_mlswe=1.0e-7, method_visc=3,
+                        visc_mlswe=50.0, f0=0.93e-4, beta=2.0e-11, test_case="double-gyre"),
+}
+
+
+def synthetic_double_gyre(nelx, nely, nop=4, nlayers=3, dt=None, dt_btp=None, perturb=1.0e-3):
+    """Synthetic double gyre of SURVEY.md 8(d) / BASELINE.md configs 4 and 5 (CFL-rescaled time steps)."""
+    p = dict(SHIPPED["double_gyre"])
+    p.update(nelx=nelx, nely=nely, nop=nop, nlayers=nlayers, test_case="double-gyre-synth", synth_perturb=perturb)
+    H = 9928.0
+    if nlayers == 2:
+        z = [0.0, -1489.5, -H]
+        alpha = [9.7370e-4, 9.7350e-4]
+    elif nlayers == 3:
+        z = [0.0, -1489.5, -4000.0, -H]
+        alpha = [9.7370e-4, 9.7360e-4, 9.7350e-4]
+    else:
+        z = [0.0] + [-round(2.0 * H * (k / nlayers) ** 1.5) / 2.0 for k in range(1, nlayers)] + [-H]
+        alpha = [9.7370e-4 + (9.7350e-4 - 9.7370e-4) * k / (nlayers - 1) for k in range(nlayers)]
+    p["synth_z"] = z
+    p["synth_alpha"] = alpha
+    # keep the shipped barotropic CFL (~0.56): dt_btp scales with the minimum LGL spacing of the element
+    xg, _ = lgl(nop + 1)
+    dmin = (xg[1] - xg[0]) / 2.0 * (2.0e6 / max(nelx, nely))
+    xg4, _ = lgl(5)
+    dmin_ref = (xg4[1] - xg4[0]) / 2.0 * (2.0e6 / 25.0)
+    if dt_btp is None:
+        dt_btp = 25.0 * dmin / dmin_ref
+    if dt is None:
+        dt = 20.0 * dt_btp
+    p["dt"], p["dt_btp"] = dt, dt_btp
+    return p
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def build_deck(params, rank=0, nranks=1):
+    """Arrays for one rank of a row-block partition of the nelx x nely brick.
+
+    Returns a dict whose keys match hnumo_desc_t members, plus 'q_df', 'qb_df', 'qprime_df' (initial state in the
+    reference AoS layout), 'coord', 'elem_global' (global row-major element number of each local element).
+    """
+    p = params
+    nelx, nely, nop, nl = p["nelx"], p["nely"], p["nop"], p["nlayers"]
+    B = basis(nop, p.get("dg_integ_exact", True))
+    ngl, nq = B["ngl"], B["nq"]
+    npts = ngl * ngl
+    xg = B["xgl"]
+    Lx = p["xdims"][1] - p["xdims"][0]
+    Ly = p["ydims"][1] - p["ydims"][0]
+    if nely % nranks != 0:
+        raise ValueError("row-block partition needs nely divisible by the number of ranks")
+    rows = nely // nranks
+    ey0 = rank * rows
+    nelem = nelx * rows
+    npoin = nelem * npts
+    ex = np.tile(np.arange(nelx), rows)
+    ey = np.repeat(np.arange(ey0, ey0 + rows), nelx)
+    # coordinates (p4est.c:204-236): bilinear blend of the tree corners, then rescaled to xdims/ydims
+    rl = xg[None, :]
+    rm = xg[:, None]
+    w0 = (1 - rl) * (1 - rm); w1 = (1 + rl) * (1 - rm); w2 = (1 - rl) * (1 + rm); w3 = (1 + rl) * (1 + rm)
+    exb = ex[:, None, None].astype(float)
+    eyb = ey[:, None, None].astype(float)
+    tx = (w0 * exb + w1 * (exb + 1) + w2 * exb + w3 * (exb + 1)) / 4.0
+    ty = (w0 * eyb + w1 * eyb + w2 * (eyb + 1) + w3 * (eyb + 1)) / 4.0
+    X = (tx / nelx) * Lx + p["xdims"][0]
+    Y = (ty / nely) * Ly + p["ydims"][0]
+    x = X.reshape(-1)
+    y = Y.reshape(-1)
+    # face table (p4est.c:1590-1704): p4est faces f=0..3 (-x,+x,-y,+y) -> numa local faces 5,6,3,4
+    transform = [5, 6, 3, 4]
+    faces = []
+    halo_lo, halo_hi = [], []  # processor faces towards rank-1 / rank+1, ordered by ex
+    for q in range(nelem):
+        qx, qy = q % nelx, q // nelx
+        for f in range(4):
+            nx_ = qx + (-1 if f == 0 else 1 if f == 1 else 0)
+            ny_ = qy + (-1 if f == 2 else 1 if f == 3 else 0)
+            gy = ny_ + ey0
+            if nx_ < 0 or nx_ >= nelx or gy < 0 or gy >= nely:
+                bc = (p["x_boundary"][0] if f == 0 else p["x_boundary"][1] if f == 1 else
+                      p["y_boundary"][0] if f == 2 else p["y_boundary"][1])
+                faces.append([0, 0, 0, 0, transform[f], 0, q + 1, -bc])
+            elif ny_ < 0 or ny_ >= rows:
+                faces.append([0, 0, 0, 0, transform[f], 0, q + 1, 0])
+                (halo_lo if ny_ < 0 else halo_hi).append(len(faces))  # 1-based face number
+            else:
+                nq_ = nx_ + nelx * ny_
+                if q < nq_:
+                    faces.append([0, 0, 0, 0, transform[f], transform[f ^ 1], q + 1, nq_ + 1])
+    face = np.array(faces, dtype=np.int32)
+    nface = face.shape[0]
+    nbh_proc, num_send_recv, nbh_send_recv = [], [], []
+    if halo_lo:
+        nbh_proc.append(rank); num_send_recv.append(len(halo_lo)); nbh_send_recv += halo_lo      # rank-1, 1-based = rank
+    if halo_hi:
+        nbh_proc.append(rank + 2); num_send_recv.append(len(halo_hi)); nbh_send_recv += halo_hi  # rank+1, 1-based
+    # geometry: axis-aligned rectangles
+    dx, dy = Lx / nelx, Ly / nely
+    em = np.zeros((nelem, 5))
+    em[:, 0] = 2.0 / dx; em[:, 3] = 2.0 / dy; em[:, 4] = dx * dy / 4.0
+    fg = np.zeros((nface, 3))
+    normals = {3: (0.0, -1.0, dx / 2.0), 4: (0.0, 1.0, dx / 2.0), 5: (-1.0, 0.0, dy / 2.0), 6: (1.0, 0.0, dy / 2.0)}
+    for f in range(nface):
+        fg[f] = normals[int(face[f, 4])]
+    wg = B["wgl"]
+    massinv = np.tile(1.0 / (wg[None, :] * wg[:, None] * (dx * dy / 4.0)), (nelem, 1, 1)).reshape(-1)
+    # ---- initial conditions (initial_conditions.F90)
+    g = GRAVITY
+    pi = PI_TRIG
+    xmin, xmax = p["xdims"]
+    ymin, ymax = p["ydims"]
+    zbot = np.zeros(npoin)
+    zi = np.zeros((nl + 1, npoin))
+    alpha = np.zeros(nl)
+    tauw = np.zeros((npoin, 2))
+    tc = p["test_case"]
+    if tc == "bump":
+        H = 40.0
+        zbot[:] = -H
+        for k in range(nl + 1):
+            zi[k] = -(k) * H / float(nl)
+        xm, yl = 0.5 * (xmax + xmin), 0.5 * (ymax + ymin)
+        r = np.sqrt((x - xm) ** 2 + (y - yl) ** 2)
+        m = r < 250.0
+        zi[1][m] = zi[1][m] + 0.5 * 1.0 * (1.0 + np.cos(pi * r[m] / 250.0))
+        alpha[0] = 0.9737e-3
+        alpha[1:] = 0.9735e-3
+    elif tc == "lakeAtrest":
+        H = 40.0
+        zbot[:] = -H
+        xm, yl = 0.5 * (xmin + xmax), 0.5 * (ymin + ymax)
+        r = np.sqrt((x - xm) ** 2 + (y - yl) ** 2)
+        m = r < 250.0
+        zbot[m] = zbot[m] + 3.0 * (1.0 + np.cos(pi * r[m] / 250.0))
+        for k in range(nl + 1):
+            if nl < 5:
+                zi[k] = -(k) * H / float(nl)
+            else:
+                zi[k] = -(k) * 32 / float(nl - 1)
+        if nl >= 5:
+            zi[nl] = -H
+        rho0 = 1027.01037
+        alpha[0] = 1.0 / rho0
+        for k in range(2, nl + 1):
+            alpha[k - 1] = 1.0 / (rho0 + k * 0.2110 / float(nl))
+    elif tc == "double-gyre":
+        H = 9928.0
+        zbot[:] = -H
+        zi[1] = -1489.5
+        zi[2] = -H
+        alpha[0], alpha[1] = 9.7370e-04, 9.7350e-04
+        tauw[:, 0] = -0.1 * np.cos(2.0 * pi * y / Ly)
+    elif tc == "double-gyre-synth":
+        z = p["synth_z"]
+        zbot[:] = z[nl]
+        for k in range(nl + 1):
+            zi[k] = z[k]
+        alpha[:] = p["synth_alpha"]
+        tauw[:, 0] = -0.1 * np.cos(2.0 * pi * y / Ly)
+    else:
+        raise ValueError("unknown test case " + tc)
+    zi = np.maximum(zi, zbot[None, :])
+    pbprime = np.zeros(npoin)
+    for k in range(nl):
+        pbprime = pbprime + (g / alpha[k]) * (zi[k] - zi[k + 1])
+    q = np.zeros((nl, npoin, 3))
+    qprime = np.zeros((nl, npoin, 3))
+    ope = np.zeros(npoin)
+    for k in range(nl):
+        q[k, :, 0] = (g / alpha[k]) * (zi[k] - zi[k + 1])
+        ope = ope + q[k, :, 0] / pbprime
+    for k in range(nl):
+        qprime[k, :, 0] = q[k, :, 0] / ope
+    if tc == "double-gyre-synth" and p.get("synth_perturb", 0.0) != 0.0:
+        s = p["synth_perturb"] * np.sin(2.0 * pi * x / Lx) * np.sin(2.0 * pi * y / Ly)
+        d = q[0, :, 0] * s
+        q[0, :, 0] += d
+        q[1, :, 0] -= d
+        qprime[0, :, 0] = q[0, :, 0] / ope
+        qprime[1, :, 0] = q[1, :, 0] / ope
+    qb = np.zeros((npoin, 4))
+    for k in range(nl):
+        qb[:, 0] += q[k, :, 0]
+        qb[:, 2] += q[k, :, 1]
+        qb[:, 3] += q[k, :, 2]
+    qb[:, 1] = qb[:, 0] - pbprime
+    for k in range(nl):
+        qprime[k, :, 1] = q[k, :, 1] / q[k, :, 0] - qb[:, 2] / qb[:, 0]
+        qprime[k, :, 2] = q[k, :, 2] / q[k, :, 0] - qb[:, 3] / qb[:, 0]
+    coriolis = p.get("f0", 0.0) + p.get("beta", 0.0) * (y - 0.5 * p["ydims"][1])  # mod_initial_mlswe.F90:308-315
+    N_btp = int(math.ceil(p["dt"] / p["dt_btp"]))
+    dt_btp = p["dt"] / float(N_btp)
+    ks = p.get("kstages", 5)
+    tab = {
+        1: ([[1.0, 0.0, 0.0]], [1.0]),
+        2: ([[1.0, 0.0, 0.0], [0.5, 0.5, 0.0]], [1.0, 0.5]),
+        3: ([[1.0, 0.0, 0.0], [3.0 / 4.0, 1.0 / 4.0, 0.0], [1.0 / 3.0, 2.0 / 3.0, 0.0]], [1.0, 1.0 / 4.0, 2.0 / 3.0]),
+        4: ([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [2.0 / 3.0, 1.0 / 3.0, 0.0], [0.0, 1.0, 0.0]], [0.5, 0.5, 1.0 / 6.0, 0.5]),
+        5: ([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.355909775063326, 0.644090224936674, 0.0],
+             [0.367933791638137, 0.632066208361863, 0.0], [0.0, 0.762406163401431, 0.237593836598569]],
+            [0.377268915331368, 0.377268915331368, 0.242995220537396, 0.238458932846290, 0.287632146308408]),
+    }[ks]
+    ssprk_a = np.asfortranarray(np.array(tab[0]))  # (kstages,3) column-major
+    deck = dict(
+        nelem=nelem, ngl=ngl, nq=nq, nlayers=nl, nface=nface, kstages=ks, N_btp=N_btp, dt=float(p["dt"]), dt_btp=dt_btp,
+        botfr=p.get("botfr", 0), method_visc=p.get("method_visc", 0), gravity=g, cd_mlswe=p.get("cd_mlswe", 0.0),
+        visc_mlswe=p.get("visc_mlswe", 0.0), ad_mlswe=0.0,
+        psiq=np.asfortranarray(B["psiq"]), dpsiq=np.asfortranarray(B["dpsiq"]), wnq=B["wnq"], wgl=B["wgl"],
+        dpsi=np.asfortranarray(B["dpsi"]),
+        face=face, elem_metrics=em, face_geom=fg,
+        pbprime_df=pbprime, massinv=massinv, coriolis_df=coriolis, tau_wind_df=tauw, zbot_df=zbot, alpha_mlswe=alpha,
+        ssprk_a=ssprk_a, ssprk_beta=np.array(tab[1]),
+        rank=rank, nranks=nranks, nbh_proc=np.array(nbh_proc, dtype=np.int32),
+        num_send_recv=np.array(num_send_recv, dtype=np.int32), nbh_send_recv=np.array(nbh_send_recv, dtype=np.int32),
+        q_df=q, qb_df=qb, qprime_df=qprime, coord=np.stack([x, y], axis=1),
+        elem_global=(ex + nelx * ey), npoin=npoin, npts=npts,
+    )
+    return deck
+
+
+def diagnostics(deck, q_df):
+    """h, u, v, interface elevation per layer and layer masses (diagnostics.F90:24-45, compute_conserved.F90)."""
+    nl, npoin = deck["nlayers"], deck["npoin"]
+    g, alpha = deck["gravity"], deck["alpha_mlswe"]
+    q = np.asarray(q_df).reshape(nl, npoin, 3)
+    h = np.stack([(alpha[k] / g) * q[k, :, 0] for k in range(nl)])
+    u = q[:, :, 1] / q[:, :, 0]
+    v = q[:, :, 2] / q[:, :, 0]
+    elev = np.zeros((nl + 1, npoin))
+    elev[nl] = deck["zbot_df"]
+    for k in range(nl - 1, -1, -1):
+        elev[k] = elev[k + 1] + h[k]
+    wj = 1.0 / deck["massinv"]
+    mass = (h * wj[None, :]).sum(axis=1)
+    return dict(h=h, u=u, v=v, ssh=elev[:nl], mass=mass)

@@ -1,0 +1,144 @@
+/* ============================================================================
+ * hnumo_b200.h -- C-ABI of the B200-native h-NUMO hot path (libhnumo_b200.so).
+ *
+ * The library replaces exactly one call of the reference Fortran program:
+ *
+ *     call ti_rk_bcl(q0_df_mlswe, qb0_df_mlswe, qprime0_df)     src/mod_time_loop.F90:209
+ *
+ * i.e. one baroclinic predictor-corrector step of the multilayer shallow-water
+ * equations including both barotropic SSPRK substep loops (src/ti_rk_bcl.F90:9-87,
+ * src/mod_rk_mlswe.F90:19-151 and everything they call).  The Fortran driver keeps
+ * reading numo3d.in, building the p4est mesh, metrics and initial conditions, and
+ * hands the static arrays over once (hnumo_init).  State stays resident on the GPU
+ * between steps.  The reference-side binding (ISO_C_BINDING) is in INTEGRATION.md and
+ * h-numo_b200/fortran/.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types; all pointers are HOST pointers unless noted
+ *   - arrays are column-major with the reference's shapes; integer tables keep the
+ *     reference's 1-based element numbers (converted at init)
+ *   - the library copies what it needs during the call and never retains host pointers
+ *   - return value: 0 ok; <0 CUDA/NCCL/usage error (hnumo_last_error gives text);
+ *     >0 physics error: 1 = negative layer thickness (reference `stop`,
+ *     src/mod_splitting.F90:74-77,228-231)
+ *   - one host thread per handle, calls in program order (the reference is one MPI rank
+ *     = one thread = one GPU)
+ * ========================================================================== */
+#ifndef HNUMO_B200_H
+#define HNUMO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HNUMO_ABI_VERSION 1
+#define HNUMO_MAX_LAYERS 20 /* lakeAtrest supports 2..20 layers, src/initial_conditions.F90:130-169 */
+#define HNUMO_MAX_NGL 9     /* nop <= 8 (BASELINE config 5) */
+
+typedef struct hnumo_handle_s* hnumo_handle_t;
+
+/* Everything the hot path reads from the reference's modules, in the reference's own terms. */
+typedef struct hnumo_desc {
+    int32_t abi_version;
+    /* sizes: mod_grid nelem,nface; mod_basis ngl,nq; mod_input nlayers */
+    int32_t nelem, ngl, nq, nlayers, nface;
+    /* time stepping: mod_input kstages, dt; mod_initial N_btp and the re-derived dt_btp
+     * (src/mod_initial.F90:176-177) */
+    int32_t kstages, N_btp;
+    double dt, dt_btp;
+    /* physics switches: mod_input botfr, cd_mlswe, method_visc, visc_mlswe, ad_mlswe; gravity as reset by the
+     * test case (9.806, src/initial_conditions.F90:97). method_visc==1 and ad_mlswe>0 are rejected (-3). */
+    int32_t botfr, method_visc;
+    double gravity, cd_mlswe, visc_mlswe, ad_mlswe;
+    /* 1-D operators of mod_basis (src/mod_basis.F90:157-160): psiq(ngl,nq), dpsiq(ngl,nq), wnq(nq), wgl(ngl),
+     * dpsi(ngl,ngl) with dpsi(i,j) = d/dx l_i (x_j) */
+    const double* psiq;
+    const double* dpsiq;
+    const double* wnq;
+    const double* wgl;
+    const double* dpsi;
+    /* mesh: face(8,nface) of mod_grid (src/p4est.c:1590-1700): rows 5,6 local face of left/right element,
+     * row 7 left element, row 8 right element (>0), 0 = processor boundary, -4 free slip, -2 no slip */
+    const int32_t* face;
+    /* per-element affine geometry (bricks): elem_metrics(5,nelem) = ksiq_x, ksiq_y, etaq_x, etaq_y of
+     * mod_metrics at quadrature point (1,1,1,e) and |J| = jacq(1,1,1,e)/(wnq(1)*wnq(1)) */
+    const double* elem_metrics;
+    /* per-face geometry: face_geom(3,nface) = normal_vector_q(1:2,1,1,iface) (outward from the left element)
+     * and the edge Jacobian jac_faceq(1,1,iface)/wnq(1)   (src/create_normals_quad.F90:136-211) */
+    const double* face_geom;
+    /* nodal statics of mod_initial / mod_metrics, all (npoin) unless noted */
+    const double* pbprime_df;
+    const double* massinv;
+    const double* coriolis_df;
+    const double* tau_wind_df; /* (2,npoin) */
+    const double* zbot_df;
+    const double* alpha_mlswe; /* (nlayers) */
+    /* SSPRK tables of mod_initial: ssprk_a(kstages,3), ssprk_beta(kstages)  (src/mod_initial_mlswe.F90:652-678) */
+    const double* ssprk_a;
+    const double* ssprk_beta;
+    /* partition description of mod_parallel (src/p4est.c:1340-1420); all zero / NULL for a single rank.
+     * nbh_proc(num_nbh) 1-based neighbour ranks, num_send_recv(num_nbh) faces per neighbour,
+     * nbh_send_recv(sum) 1-based local face numbers in the agreed exchange order */
+    int32_t rank, nranks, num_nbh;
+    const int32_t* nbh_proc;
+    const int32_t* num_send_recv;
+    const int32_t* nbh_send_recv;
+    /* 0 = use the current CUDA device */
+    int32_t device;
+    /* tuning: 0 = default fused stage kernel, 1 = simple reference-form kernel (bisecting aid) */
+    int32_t stage_kernel_variant;
+} hnumo_desc_t;
+
+/* ---- life cycle ----------------------------------------------------------------------------- */
+/* replaces: module set-up consumed by ti_rk_bcl through `use` (src/ti_rk_bcl.F90:19-28) */
+int hnumo_init(const hnumo_desc_t* desc, hnumo_handle_t* out);
+int hnumo_finalize(hnumo_handle_t h);
+const char* hnumo_last_error(void);
+
+/* ---- state: the three dummy arguments of ti_rk_bcl (src/ti_rk_bcl.F90:32-34) ---------------- */
+/* q_df(3,npoin,nlayers), qb_df(4,npoin), qprime_df(3,npoin,nlayers) */
+int hnumo_upload_state(hnumo_handle_t h, const double* q_df, const double* qb_df, const double* qprime_df);
+int hnumo_download_state(hnumo_handle_t h, double* q_df, double* qb_df, double* qprime_df);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+/* nsteps calls of ti_rk_bcl on the device-resident state (src/mod_time_loop.F90:198-211) */
+int hnumo_step(hnumo_handle_t h, int32_t nsteps);
+/* drop-in with the original signature: upload -> one step -> download */
+int hnumo_ti_rk_bcl(hnumo_handle_t h, double* q_df, double* qb_df, double* qprime_df);
+
+/* ---- per-phase entries (tests; same semantics as the reference routines named) --------------- */
+/* btp_bcl_coeffs_qdf on the current qprime_df, with dpprime_visc = qprime_df(1,:,:)
+ * (src/ti_rk_bcl.F90:43-50, src/mod_barotropic_terms.F90:219-409) */
+int hnumo_btp_bcl_coeffs(hnumo_handle_t h);
+/* ti_barotropic_ssprk_mlswe(qb_df, qprime_df) on the resident state (src/mod_rk_mlswe.F90:19-151) */
+int hnumo_btp_substeps(hnumo_handle_t h);
+/* create_rhs_btp(rhs, qb_df, qprime_df): rhs(3,npoin) to host (src/mod_rhs_btp.F90:28-59).  The time-average
+ * accumulators are not touched. */
+int hnumo_rhs_btp(hnumo_handle_t h, double* rhs);
+/* copy a named mod_variables work array to the host in the reference's layout; face arrays are indexed by the
+ * face numbers of desc->face.  Names: Q_uu_dp Q_uv_dp Q_vv_dp H_bcl Q_uu_dp_edge Q_uv_dp_edge Q_vv_dp_edge
+ * H_bcl_edge ope_ave H_ave Qu_ave Qv_ave Quv_ave ope2_ave btp_mass_flux_ave uvb_ave tau_bot_ave ope2_ave_df
+ * uvb_ave_df graduvb_ave uvb_face_ave btp_mass_flux_face_ave ope_face_ave ope2_face_ave H_face_ave Qu_face_ave
+ * Qv_face_ave one_plus_eta_edge_2_ave btp_dpp_graduv pbprime_visc.  Returns the element count or <0. */
+int64_t hnumo_get_array(hnumo_handle_t h, const char* name, double* out, int64_t capacity);
+
+/* ---- multi-GPU: replaces mod_mpi_communicator / send_receive_bound (src/create_rhs_communicator.F90) ---- */
+/* 128-byte NCCL unique id; call on one rank, broadcast by the caller's own means (MPI_Bcast in the Fortran
+ * driver, torch.distributed in the Python harness) */
+int hnumo_comm_get_unique_id(void* id128);
+int hnumo_comm_init(hnumo_handle_t h, const void* id128);
+
+/* ---- measurement ------------------------------------------------------------------------------ */
+/* out[0] = GPU ms spent in barotropic stages since the last reset (CUDA events on the compute stream),
+ * out[1] = number of barotropic stages, out[2] = GPU ms in whole steps, out[3] = steps,
+ * out[4] = kernel launches issued, out[5..7] reserved.  reset != 0 clears the counters after reading. */
+int hnumo_timing(hnumo_handle_t h, double* out8, int32_t reset);
+/* enable (1) / disable (0) CUDA-graph replay of the barotropic substep loop */
+int hnumo_set_option(hnumo_handle_t h, const char* key, double value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HNUMO_B200_H */
