@@ -83,6 +83,10 @@ struct Config {
     double synth_z[33];
     double synth_alpha[32];
     double synth_perturb;
+    // 1: replace the numerically differentiated metrics (which carry ~1e-14 relative round-off that differs from
+    // point to point, exactly like the reference's metrics.F90) by their per-element / per-face constant values
+    // (first quadrature point), i.e. the affine-brick geometry the CUDA library is given.  0 = as the reference.
+    int affine_metrics;
 };
 
 struct Oracle {
@@ -136,6 +140,7 @@ struct Oracle {
     void build_grid();
     void build_metrics();
     void build_faces();
+    void make_metrics_affine();
     void build_tensor_tables();
     void build_initial();
     void allocate_variables();

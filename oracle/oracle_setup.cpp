@@ -614,11 +614,37 @@ void Oracle::allocate_variables() {
     sum_layer_mass_flux.alloc(2, npoin_q); sum_layer_mass_flux_face.alloc(2, nq, nface);
 }
 
+// Test aid (not in the reference): per-element constant geometry, see Config::affine_metrics.
+void Oracle::make_metrics_affine() {
+    const int nq2 = nq * nq;
+    for (int e = 0; e < nelem; ++e) {
+        int I0 = e * nq2;
+        double kx = ksiq_x(I0), ky = ksiq_y(I0), ex = etaq_x(I0), ey = etaq_y(I0), J = jacq(I0) / (wnq[0] * wnq[0]);
+        for (int j = 0; j < nq; ++j)
+            for (int i = 0; i < nq; ++i) {
+                int Iq = I0 + j * nq + i;
+                ksiq_x(Iq) = kx; ksiq_y(Iq) = ky; etaq_x(Iq) = ex; etaq_y(Iq) = ey; jacq(Iq) = wnq[i] * wnq[j] * J;
+            }
+        for (int j = 0; j < ngl; ++j)
+            for (int i = 0; i < ngl; ++i) {
+                int I = e * npts + j * ngl + i;
+                ksi_x(I) = kx; ksi_y(I) = ky; eta_x(I) = ex; eta_y(I) = ey; jac(I) = wgl[i] * wgl[j] * J;
+                massinv(I) = 1.0 / jac(I);
+            }
+    }
+    for (int f = 0; f < nface; ++f) {
+        double nx = normal_vector_q(0, 0, f), ny = normal_vector_q(1, 0, f), nlen = jac_faceq(0, f) / wnq[0];
+        for (int iq = 0; iq < nq; ++iq) { normal_vector_q(0, iq, f) = nx; normal_vector_q(1, iq, f) = ny; jac_faceq(iq, f) = wnq[iq] * nlen; }
+        for (int n = 0; n < ngl; ++n) { normal_vector(0, n, f) = nx; normal_vector(1, n, f) = ny; jac_face(n, f) = wgl[n] * nlen; }
+    }
+}
+
 Oracle::Oracle(const Config& c) : cfg(c) {
     build_basis();
     build_grid();
     build_metrics();
     build_faces();
+    if (cfg.affine_metrics) make_metrics_affine();
     build_tensor_tables();
     build_initial();
     allocate_variables();

@@ -27,6 +27,7 @@ class Config(C.Structure):
         ("f0", C.c_double), ("beta", C.c_double),
         ("test_case", C.c_int), ("dg_integ_exact", C.c_int),
         ("synth_z", C.c_double * 33), ("synth_alpha", C.c_double * 32), ("synth_perturb", C.c_double),
+        ("affine_metrics", C.c_int),
     ]
 
 
@@ -82,6 +83,7 @@ def make_config(deck):
     for i, a in enumerate(deck.get("synth_alpha", [])):
         c.synth_alpha[i] = a
     c.synth_perturb = deck.get("synth_perturb", 0.0)
+    c.affine_metrics = 1 if deck.get("affine_metrics", False) else 0
     return c
 
 

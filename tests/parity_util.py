@@ -14,11 +14,13 @@ def rel_l2(a, b, floor=0.0):
     return float(np.linalg.norm(a - b) / den)
 
 
-def make_pair(params, variant=0, oracle_metrics=True):
+def make_pair(params, variant=0, oracle_metrics=True, affine=True):
     """Same inputs for both sides.  The oracle differentiates the node coordinates numerically like the reference
     (metrics.F90), which leaves ~1e-14 relative round-off in its Jacobians; with oracle_metrics the library is
     given those numbers (first point of each element / face), as the Fortran shim would do."""
     deck = hn.decks.build_deck(params)
+    params = dict(params)
+    params["affine_metrics"] = affine
     O = oracle_lib.Oracle(params)
     if oracle_metrics:
         nq2, nq = O.nq * O.nq, O.nq

@@ -1,0 +1,194 @@
+"""GPU parity tests (run on the B200 box): CUDA library through its C-ABI vs the CPU oracle on the same inputs.
+
+Tolerances.  Mass-like fields (dp, dp', pb) must agree to 1e-10 relative L2.  Momentum-like fields are the result
+of an O(1e8..1e13)-fold cancellation between volume and face pressure terms (tests/test_oracle_golden.py::
+test_conditioning_noise_floor), so two correct FP64 evaluations with different summation order differ by ~1e-9..1e-7
+in the plain relative sense; they are required to agree to 1e-11 of their natural scale c*|dp| (c = sqrt(g H), the
+north-star tolerance applied to the scale of the field) and to 1e-6 plain relative L2.
+"""
+import threading
+
+import numpy as np
+import pytest
+
+from parity_util import hn, make_pair, rel_l2, state_errors, sync_state_from_oracle
+import oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+DECKS = {
+    "bump": lambda: dict(hn.decks.SHIPPED["bump"]),
+    "lake": lambda: dict(hn.decks.SHIPPED["lake"]),
+    "double_gyre": lambda: dict(hn.decks.SHIPPED["double_gyre"], nelx=8, nely=8),
+    "synth3": lambda: hn.decks.synthetic_double_gyre(8, 8, nop=4, nlayers=3),
+    "noslip_rk3": lambda: dict(hn.decks.SHIPPED["double_gyre"], nelx=6, nely=5, x_boundary=(2, 2), kstages=3, botfr=2, cd_mlswe=1e-3),
+    "nop3_5layers": lambda: dict(hn.decks.synthetic_double_gyre(5, 5, nop=3, nlayers=5)),
+}
+VARIANTS = [0, 1]
+
+
+def natural_errors(S, O, deck):
+    """errors of every prognostic field relative to its natural scale"""
+    q, qb, qp = S.download_state()
+    nl, npoin = deck["nlayers"], deck["npoin"]
+    qo = O.get("q_df").reshape(nl, npoin, 3); qbo = O.get("qb_df").reshape(npoin, 4); qpo = O.get("qprime_df").reshape(nl, npoin, 3)
+    c = np.sqrt(deck["gravity"] * float(np.max(-deck["zbot_df"])))
+    out = {"mass": 0.0, "mom": 0.0}
+    for k in range(nl):
+        dn = np.linalg.norm(qo[k, :, 0])
+        out["mass"] = max(out["mass"], np.linalg.norm(q[k, :, 0] - qo[k, :, 0]) / dn, np.linalg.norm(qp[k, :, 0] - qpo[k, :, 0]) / dn)
+        for v in (1, 2):
+            out["mom"] = max(out["mom"], np.linalg.norm(q[k, :, v] - qo[k, :, v]) / (c * dn),
+                             np.linalg.norm(qp[k, :, v] - qpo[k, :, v]) / (c * np.sqrt(npoin)))
+    pn = np.linalg.norm(qbo[:, 0])
+    out["mass"] = max(out["mass"], np.linalg.norm(qb[:, 0] - qbo[:, 0]) / pn, np.linalg.norm(qb[:, 1] - qbo[:, 1]) / pn)
+    for v in (2, 3):
+        out["mom"] = max(out["mom"], np.linalg.norm(qb[:, v] - qbo[:, v]) / (c * pn))
+    return out
+
+
+@pytest.mark.parametrize("name", ["lake", "double_gyre"])
+def test_static_derivations(name):
+    """quantities the reference set-up derives (mod_initial_mlswe.F90) and the library re-derives on the device"""
+    deck, S, O = make_pair(DECKS[name]())
+    for nm in ["coriolis_quad", "tau_wind", "pbprime", "one_over_pbprime", "coeff_pbpert_L", "coeff_pbpert_R", "coeff_pbub_LR",
+               "coeff_mass_pbpert_LR", "one_over_pbprime_edge", "pbprime_face", "zbot_face", "a_bcl", "b_bcl"]:
+        assert rel_l2(S.get_array(nm), O.get(nm), floor=1e-30) < 1e-14, nm
+    ref = O.get("grad_zbot_quad")
+    assert np.linalg.norm(S.get_array("grad_zbot_quad") - ref) < 1e-12 * max(np.linalg.norm(ref), 1.0)
+    S.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("name", ["bump", "double_gyre", "synth3", "noslip_rk3", "nop3_5layers"])
+def test_phase_parity(name, variant):
+    """btp_bcl_coeffs_qdf, create_rhs_btp and ti_barotropic_ssprk_mlswe phase by phase on a developed state"""
+    deck, S, O = make_pair(DECKS[name](), variant=variant)
+    O.step(1)
+    sync_state_from_oracle(S, O)
+    O.btp_bcl_coeffs(); S.btp_bcl_coeffs()
+    for nm in ["Q_uu_dp", "Q_uv_dp", "Q_vv_dp", "H_bcl", "Q_uu_dp_edge", "Q_uv_dp_edge", "Q_vv_dp_edge", "H_bcl_edge"]:
+        ref = O.get(nm)
+        assert rel_l2(S.get_array(nm), ref, floor=1e-12 * np.linalg.norm(O.get("Q_uu_dp" if nm.startswith("Q") and "edge" not in nm else nm)) + 1e-300) < 1e-12, nm
+    if deck["visc_mlswe"] != 0.0:
+        assert rel_l2(S.get_array("pbprime_visc"), O.get("pbprime_visc")) < 1e-14
+        ref = O.get("btp_dpp_graduv")
+        assert np.linalg.norm(S.get_array("btp_dpp_graduv") - ref) < 1e-6 * np.linalg.norm(ref) + 1e-14
+    r_o, r_g = O.rhs_btp(), S.rhs_btp()
+    Hn = np.linalg.norm(O.get("H_bcl")) / np.sqrt(O.npoin_q)          # size of the cancelling pressure terms
+    h = float(np.sqrt(1.0 / deck["massinv"].max())) if False else 1.0
+    assert rel_l2(r_g[:, 0], r_o[:, 0], floor=1e-30) < 1e-11
+    for v in (1, 2):
+        # momentum tendency: absolute error bounded by round-off of the O(H_bcl) terms it is the difference of
+        scale = np.abs(r_o[:, v]).max() + 1e-14 * Hn * np.sqrt(O.npoin) * np.sqrt(deck["massinv"].max())
+        assert np.linalg.norm(r_g[:, v] - r_o[:, v]) < 1e-5 * np.linalg.norm(r_o[:, v]) + 1e-3 * scale * 1e-6 + 1e-12 * Hn, (v, name)
+    O.btp_substeps(); S.btp_substeps()
+    for nm in ["ope_ave", "H_ave", "ope2_ave", "ope2_ave_df", "H_face_ave", "ope_face_ave", "ope2_face_ave", "one_plus_eta_edge_2_ave"]:
+        assert rel_l2(S.get_array(nm), O.get(nm)) < 1e-12, nm
+    c = np.sqrt(deck["gravity"] * float(np.max(-deck["zbot_df"])))
+    pbn = np.linalg.norm(O.get("qb_df").reshape(-1, 4)[:, 0]) / np.sqrt(O.npoin)
+    for nm, scale in [("Qu_ave", c * c * pbn), ("Qv_ave", c * c * pbn), ("Quv_ave", c * c * pbn), ("btp_mass_flux_ave", c * pbn),
+                      ("uvb_ave", c), ("uvb_ave_df", c), ("btp_mass_flux_face_ave", c * pbn), ("Qu_face_ave", c * c * pbn),
+                      ("Qv_face_ave", c * c * pbn), ("uvb_face_ave", c), ("tau_bot_ave", c * pbn)]:
+        a, b = S.get_array(nm), O.get(nm)
+        assert np.linalg.norm(a - b) / np.sqrt(b.size) < 1e-11 * scale, nm
+        assert rel_l2(a, b, floor=1e-30) < 1e-5 or np.linalg.norm(b) / np.sqrt(b.size) < 1e-9 * scale, nm
+    e = natural_errors(S, O, deck)
+    assert e["mass"] < 1e-10 and e["mom"] < 1e-11, e
+    S.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("name,nsteps", [("bump", 5), ("lake", 5), ("double_gyre", 5), ("synth3", 5), ("noslip_rk3", 4), ("nop3_5layers", 4)])
+def test_step_parity(name, nsteps, variant):
+    """whole ti_rk_bcl steps from the initial conditions"""
+    deck, S, O = make_pair(DECKS[name](), variant=variant)
+    assert S.step(nsteps) == 0
+    assert O.step(nsteps) == 0
+    e = natural_errors(S, O, deck)
+    assert e["mass"] < 1e-10 and e["mom"] < 1e-11, e
+    plain = state_errors(S, O, deck)
+    assert max(plain.values()) < 1e-6, plain
+    S.close()
+
+
+def test_100_steps_bump():
+    """north-star check: 100 baroclinic steps (56000 barotropic stages) of the bump deck"""
+    deck, S, O = make_pair(DECKS["bump"]())
+    assert S.step(100) == 0 and O.step(100) == 0
+    e = natural_errors(S, O, deck)
+    assert e["mass"] < 1e-10 and e["mom"] < 1e-11, e
+    plain = state_errors(S, O, deck)
+    assert max(plain.values()) < 1e-6, plain
+    S.close()
+
+
+def test_drop_in_signature_matches_resident_stepping():
+    """hnumo_ti_rk_bcl(q_df, qb_df, qprime_df) on host buffers == upload + step + download"""
+    deck, S, O = make_pair(DECKS["double_gyre"]())
+    q, qb, qp = deck["q_df"].copy(), deck["qb_df"].copy(), deck["qprime_df"].copy()
+    for _ in range(2):
+        assert S.ti_rk_bcl(q, qb, qp) == 0
+    S.upload_state(deck["q_df"], deck["qb_df"], deck["qprime_df"])
+    S.step(2)
+    q2, qb2, qp2 = S.download_state()
+    assert np.array_equal(q, q2) and np.array_equal(qb, qb2) and np.array_equal(qp, qp2)
+    S.close()
+
+
+def test_variants_agree_bitwise_on_mass():
+    """the optimised stage kernel and the simple one integrate the same scheme"""
+    p = DECKS["double_gyre"]()
+    deck = hn.decks.build_deck(p)
+    outs = []
+    for variant in VARIANTS:
+        S = hn.Solver(deck, variant=variant)
+        S.upload_state(deck["q_df"], deck["qb_df"], deck["qprime_df"])
+        S.step(3)
+        outs.append(S.download_state())
+        S.close()
+    assert rel_l2(outs[0][1][:, 0], outs[1][1][:, 0]) < 1e-13
+    assert rel_l2(outs[0][0][:, :, 0], outs[1][0][:, :, 0]) < 1e-12
+
+
+def _run_partitioned(params, nranks, nsteps, gid):
+    decks = [hn.decks.build_deck(params, r, nranks) for r in range(nranks)]
+    solvers = [hn.Solver(d) for d in decks]
+    for S, d in zip(solvers, decks):
+        S.comm_init(hn.local_group_id(gid))
+        S.upload_state(d["q_df"], d["qb_df"], d["qprime_df"])
+    rcs = [None] * nranks
+
+    def work(i):
+        rcs[i] = solvers[i].step(nsteps)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(nranks)]
+    [t.start() for t in th]
+    [t.join(timeout=600) for t in th]
+    assert all(rc == 0 for rc in rcs), rcs
+    outs = [S.download_state() for S in solvers]
+    [S.close() for S in solvers]
+    return decks, outs
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_partitioned_equals_single(nranks):
+    """k-way element partition with face-halo exchange == 1-way; in-process back end on one GPU"""
+    params = dict(hn.decks.SHIPPED["double_gyre"], nelx=6, nely=8)
+    single = hn.decks.build_deck(params)
+    S = hn.Solver(single)
+    S.upload_state(single["q_df"], single["qb_df"], single["qprime_df"])
+    assert S.step(3) == 0
+    q1, qb1, qp1 = S.download_state()
+    S.close()
+    decks, outs = _run_partitioned(params, nranks, 3, gid=100 + nranks)
+    npts = single["npts"]
+    c = np.sqrt(single["gravity"] * 9928.0)
+    for d, (q, qb, qp) in zip(decks, outs):
+        idx = (d["elem_global"][:, None] * npts + np.arange(npts)[None, :]).ravel()
+        assert rel_l2(qb[:, 0], qb1[idx, 0]) < 1e-13
+        assert rel_l2(q[:, :, 0], q1[:, idx, 0]) < 1e-12
+        for v in (2, 3):
+            assert np.linalg.norm(qb[:, v] - qb1[idx, v]) / (c * np.linalg.norm(qb1[idx, 0])) < 1e-12
+        for v in (1, 2):
+            assert np.linalg.norm(q[:, :, v] - q1[:, idx, v]) / (c * np.linalg.norm(q1[:, idx, 0])) < 1e-12
