@@ -130,7 +130,6 @@ static size_t nblk(size_t n, int t = 256) { return (n + t - 1) / t; }
 
 static void harvest_events(Solver& S);
 static void take_event_pair(Solver& S, int kind, cudaEvent_t& a, cudaEvent_t& b) {
-    if (S.ev_used >= 256) harvest_events(S);
     if (S.ev_pool.size() < 2 * (S.ev_used + 1)) {
         cudaEvent_t x, y; cudaEventCreate(&x); cudaEventCreate(&y);
         S.ev_pool.push_back(x); S.ev_pool.push_back(y); S.ev_kind.push_back(kind);
@@ -397,7 +396,7 @@ static void harvest_events(Solver& S) {
     cudaStreamSynchronize(S.stream);
     for (size_t i = 0; i < S.ev_used; ++i) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, S.ev_pool[2 * i], S.ev_pool[2 * i + 1]) != cudaSuccess) continue;
+        if (cudaEventElapsedTime(&ms, S.ev_pool[2 * i], S.ev_pool[2 * i + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
         if (S.ev_kind[i] == 0) { S.ms_btp += ms; S.ms_btp_last = ms; } else { S.ms_step += ms; S.ms_step_last = ms; }
     }
     S.ev_used = 0;
@@ -632,6 +631,7 @@ int hnumo_step(hnumo_handle_t h, int32_t nsteps) {
     Solver& S = h->S;
     for (int i = 0; i < nsteps; ++i) {
         if (bcl_step(S)) return -1;
+        if (S.ev_used >= 192) harvest_events(S);  // only between steps: every recorded pair is complete here
     }
     int rc = check_flag(S);
     harvest_events(S);

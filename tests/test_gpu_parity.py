@@ -171,24 +171,31 @@ def _run_partitioned(params, nranks, nsteps, gid):
     return decks, outs
 
 
+@pytest.mark.parametrize("visc", [0.0, 50.0])
 @pytest.mark.parametrize("nranks", [2, 4])
-def test_partitioned_equals_single(nranks):
-    """k-way element partition with face-halo exchange == 1-way; in-process back end on one GPU"""
-    params = dict(hn.decks.SHIPPED["double_gyre"], nelx=6, nely=8)
+def test_partitioned_equals_single(nranks, visc):
+    """k-way element partition with face-halo exchange == 1-way; in-process back end on one GPU.
+
+    With visc_mlswe == 0 every face term is antisymmetric under (L<->R, n->-n) and the two runs agree to round-off.
+    With viscosity the reference's as-written LDG face flux (mod_laplacian_quad.F90:485-486) is NOT symmetric: each
+    rank evaluates a processor face with itself as the left element, so the reference itself depends on the
+    partition at O(visc).  The library reproduces the reference in both configurations; the tolerance is wider."""
+    params = dict(hn.decks.SHIPPED["double_gyre"], nelx=6, nely=8, visc_mlswe=visc)
+    tol = 1e-13 if visc == 0.0 else 1e-10
     single = hn.decks.build_deck(params)
     S = hn.Solver(single)
     S.upload_state(single["q_df"], single["qb_df"], single["qprime_df"])
     assert S.step(3) == 0
     q1, qb1, qp1 = S.download_state()
     S.close()
-    decks, outs = _run_partitioned(params, nranks, 3, gid=100 + nranks)
+    decks, outs = _run_partitioned(params, nranks, 3, gid=100 + nranks + (10 if visc else 0))
     npts = single["npts"]
     c = np.sqrt(single["gravity"] * 9928.0)
     for d, (q, qb, qp) in zip(decks, outs):
         idx = (d["elem_global"][:, None] * npts + np.arange(npts)[None, :]).ravel()
-        assert rel_l2(qb[:, 0], qb1[idx, 0]) < 1e-13
-        assert rel_l2(q[:, :, 0], q1[:, idx, 0]) < 1e-12
+        assert rel_l2(qb[:, 0], qb1[idx, 0]) < tol
+        assert rel_l2(q[:, :, 0], q1[:, idx, 0]) < 10 * tol
         for v in (2, 3):
-            assert np.linalg.norm(qb[:, v] - qb1[idx, v]) / (c * np.linalg.norm(qb1[idx, 0])) < 1e-12
+            assert np.linalg.norm(qb[:, v] - qb1[idx, v]) / (c * np.linalg.norm(qb1[idx, 0])) < tol
         for v in (1, 2):
-            assert np.linalg.norm(q[:, :, v] - q1[:, idx, v]) / (c * np.linalg.norm(q1[:, idx, 0])) < 1e-12
+            assert np.linalg.norm(q[:, :, v] - q1[:, idx, v]) / (c * np.linalg.norm(q1[:, idx, 0])) < tol
