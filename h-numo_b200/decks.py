@@ -190,28 +190,36 @@ def build_deck(params, rank=0, nranks=1):
     x = X.reshape(-1)
     y = Y.reshape(-1)
     # face table (p4est.c:1590-1704): p4est faces f=0..3 (-x,+x,-y,+y) -> numa local faces 5,6,3,4
-    transform = [5, 6, 3, 4]
-    faces = []
-    halo_lo, halo_hi = [], []  # processor faces towards rank-1 / rank+1, ordered by ex
-    for q in range(nelem):
-        qx, qy = q % nelx, q // nelx
-        for f in range(4):
-            nx_ = qx + (-1 if f == 0 else 1 if f == 1 else 0)
-            ny_ = qy + (-1 if f == 2 else 1 if f == 3 else 0)
-            gy = ny_ + ey0
-            if nx_ < 0 or nx_ >= nelx or gy < 0 or gy >= nely:
-                bc = (p["x_boundary"][0] if f == 0 else p["x_boundary"][1] if f == 1 else
-                      p["y_boundary"][0] if f == 2 else p["y_boundary"][1])
-                faces.append([0, 0, 0, 0, transform[f], 0, q + 1, -bc])
-            elif ny_ < 0 or ny_ >= rows:
-                faces.append([0, 0, 0, 0, transform[f], 0, q + 1, 0])
-                (halo_lo if ny_ < 0 else halo_hi).append(len(faces))  # 1-based face number
-            else:
-                nq_ = nx_ + nelx * ny_
-                if q < nq_:
-                    faces.append([0, 0, 0, 0, transform[f], transform[f ^ 1], q + 1, nq_ + 1])
-    face = np.array(faces, dtype=np.int32)
-    nface = face.shape[0]
+    transform = np.array([5, 6, 3, 4], dtype=np.int32)
+    qq = np.arange(nelem)
+    qx, qy = qq % nelx, qq // nelx
+    cols = []
+    for f in range(4):
+        nx_ = qx + (-1 if f == 0 else 1 if f == 1 else 0)
+        ny_ = qy + (-1 if f == 2 else 1 if f == 3 else 0)
+        gy = ny_ + ey0
+        wall = (nx_ < 0) | (nx_ >= nelx) | (gy < 0) | (gy >= nely)
+        proc = ~wall & ((ny_ < 0) | (ny_ >= rows))
+        inter = ~wall & ~proc
+        nq_ = nx_ + nelx * ny_
+        bc = (p["x_boundary"][0] if f == 0 else p["x_boundary"][1] if f == 1 else
+              p["y_boundary"][0] if f == 2 else p["y_boundary"][1])
+        er = np.where(wall, -bc, np.where(proc, 0, nq_ + 1)).astype(np.int32)
+        ilocr = np.where(inter, transform[f ^ 1], 0).astype(np.int32)
+        keep = wall | proc | (inter & (qq < nq_))
+        side = np.where(proc & (ny_ < 0), 1, np.where(proc & (ny_ >= rows), 2, 0))
+        cols.append((np.full(nelem, transform[f], dtype=np.int32), ilocr, (qq + 1).astype(np.int32), er, keep, side))
+    ilocl = np.stack([c[0] for c in cols], axis=1).ravel()
+    ilocr = np.stack([c[1] for c in cols], axis=1).ravel()
+    el = np.stack([c[2] for c in cols], axis=1).ravel()
+    er = np.stack([c[3] for c in cols], axis=1).ravel()
+    keep = np.stack([c[4] for c in cols], axis=1).ravel()
+    side = np.stack([c[5] for c in cols], axis=1).ravel()[keep]
+    nface = int(keep.sum())
+    face = np.zeros((nface, 8), dtype=np.int32)
+    face[:, 4] = ilocl[keep]; face[:, 5] = ilocr[keep]; face[:, 6] = el[keep]; face[:, 7] = er[keep]
+    halo_lo = (np.nonzero(side == 1)[0] + 1).tolist()  # 1-based face numbers, ordered by ex
+    halo_hi = (np.nonzero(side == 2)[0] + 1).tolist()
     nbh_proc, num_send_recv, nbh_send_recv = [], [], []
     if halo_lo:
         nbh_proc.append(rank); num_send_recv.append(len(halo_lo)); nbh_send_recv += halo_lo      # rank-1, 1-based = rank
@@ -221,10 +229,9 @@ def build_deck(params, rank=0, nranks=1):
     dx, dy = Lx / nelx, Ly / nely
     em = np.zeros((nelem, 5))
     em[:, 0] = 2.0 / dx; em[:, 3] = 2.0 / dy; em[:, 4] = dx * dy / 4.0
-    fg = np.zeros((nface, 3))
-    normals = {3: (0.0, -1.0, dx / 2.0), 4: (0.0, 1.0, dx / 2.0), 5: (-1.0, 0.0, dy / 2.0), 6: (1.0, 0.0, dy / 2.0)}
-    for f in range(nface):
-        fg[f] = normals[int(face[f, 4])]
+    ntab = np.zeros((7, 3))
+    ntab[3] = (0.0, -1.0, dx / 2.0); ntab[4] = (0.0, 1.0, dx / 2.0); ntab[5] = (-1.0, 0.0, dy / 2.0); ntab[6] = (1.0, 0.0, dy / 2.0)
+    fg = ntab[face[:, 4]]
     wg = B["wgl"]
     massinv = np.tile(1.0 / (wg[None, :] * wg[:, None] * (dx * dy / 4.0)), (nelem, 1, 1)).reshape(-1)
     # ---- initial conditions (initial_conditions.F90)
