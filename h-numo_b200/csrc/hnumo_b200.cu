@@ -159,7 +159,7 @@ static void fill_stage_args(Solver& S, StageArgs& a, Planes& qb, const Planes& q
     for (int v = 0; v < 8; ++v) a.acc_q[v] = S.acc_q[v];
     for (int v = 0; v < 11; ++v) a.acc_f[v] = S.acc_f[v];
     a.g = S.g; a.cd = S.cd; a.alpha_bot = S.alpha[S.nl - 1]; a.visc = S.visc;
-    a.botfr = S.botfr; a.has_visc = S.has_visc;
+    a.botfr = S.botfr; a.has_visc = S.has_visc; a.acc_graduvb = 1;
 }
 
 static int launch_stage(Solver& S, const StageArgs& a) {
