@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=128, help="edge (elements) of the CPU baseline sample brick")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library tuning option key=value (hnumo_set_option)")
     return ap.parse_args()
 
 
@@ -184,6 +185,9 @@ def main():
         ids = [hn.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         S.comm_init(ids[0])
+    for kv in args.opt:
+        k, v = kv.split("=")
+        S.set_option(k, float(v))
     S.upload_state(deck["q_df"], deck["qb_df"], deck["qprime_df"])
     stages_per_step = 2 * deck["N_btp"] * deck["kstages"]
     npoin_global = params["nelx"] * params["nely"] * deck["npts"]
@@ -279,7 +283,7 @@ def main():
                        "nelem": params["nelx"] * params["nely"], "npoin": npoin_global, "stages_per_step": stages_per_step,
                        "dt": params["dt"], "dt_btp": deck["dt_btp"], "partition": "row blocks, %d rank(s)" % world,
                        "l2_policy": "inputs larger than L2 (>= 60 GB of resident state per job vs 126 MB L2)",
-                       "stage_kernel_variant": args.variant},
+                       "stage_kernel_variant": args.variant, "options": args.opt},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_btp_stage (fused barotropic SSPRK stage)", "algorithmic_bytes_per_node_stage": bpn,
                          "stage_ms": stage_ms, "peak_source": peak_src, "per_gpu": True},

@@ -159,7 +159,7 @@ static void fill_stage_args(Solver& S, StageArgs& a, Planes& qb, const Planes& q
     for (int v = 0; v < 8; ++v) a.acc_q[v] = S.acc_q[v];
     for (int v = 0; v < 11; ++v) a.acc_f[v] = S.acc_f[v];
     a.g = S.g; a.cd = S.cd; a.alpha_bot = S.alpha[S.nl - 1]; a.visc = S.visc;
-    a.botfr = S.botfr; a.has_visc = S.has_visc; a.acc_graduvb = 1;
+    a.botfr = S.botfr; a.has_visc = S.has_visc; a.acc_graduvb = 1; a.pf_blocks = S.pf_blocks;
 }
 
 static int launch_stage(Solver& S, const StageArgs& a) {
@@ -774,6 +774,7 @@ int hnumo_set_option(hnumo_handle_t h, const char* key, double value) {
     Solver& S = h->S;
     if (!strcmp(key, "stage_kernel_variant")) { S.variant = (int)value; return 0; }
     if (!strcmp(key, "use_graph")) { S.use_graph = (int)value; return 0; }
+    if (!strcmp(key, "prefetch_blocks")) { S.pf_blocks = (int)value; return 0; }
     set_error("hnumo_set_option", "unknown key");
     return -2;
 }

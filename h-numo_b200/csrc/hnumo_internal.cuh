@@ -126,6 +126,7 @@ struct Solver {
     double ms_btp = 0, ms_step = 0, ms_btp_last = 0, ms_step_last = 0;
     long n_stages = 0, n_steps = 0, n_launches = 0;
     int use_graph = 0;
+    int pf_blocks = 100;  // L2 prefetch distance of the fused stage kernel, in thread blocks
     std::vector<void*> allocs;
 };
 

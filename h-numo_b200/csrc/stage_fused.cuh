@@ -111,6 +111,67 @@ __device__ __forceinline__ void ldg_gradient_lines(const double* nod, double* Lr
     }
 }
 
+
+// L2 prefetch of the chunk [first, first+n) doubles of a plane: one 128-byte line per lane (n*8 <= 32*128)
+__device__ __forceinline__ void pf_chunk(const double* base, size_t first, int n, int lane) {
+    if (base == nullptr) return;
+    const char* lo = (const char*)(base + first);
+    const char* hi = lo + (size_t)n * sizeof(double);
+    const char* p = (const char*)((uintptr_t)lo & ~(uintptr_t)127) + (size_t)lane * 128;
+    if (p < hi) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// Software prefetch into L2 of everything the block `pf_blocks` launches ahead will read (the kernel is otherwise
+// bound by the latency of its ~14 dependent DRAM round trips per element, see profiles/r1_fused_kernel_summary.md).
+template <int G, int Q>
+__device__ __forceinline__ void stage_prefetch(const StageArgs& a, int e0, int ne, int warp, int lane) {
+    constexpr int NP = G * G, NQ2 = Q * Q;
+    const size_t n0 = (size_t)e0 * NP, q0 = (size_t)e0 * NQ2, s0 = (size_t)e0 * 4 * Q, t0 = (size_t)e0 * 4 * G;
+    const int nn = ne * NP, nq = ne * NQ2, ns = ne * 4 * Q, nt = ne * 4 * G;
+    if (warp == 0) {
+#pragma unroll
+        for (int v = 0; v < 3; ++v) pf_chunk(a.qb[v], n0, nn, lane);
+        pf_chunk(a.pbprime_df, n0, nn, lane); pf_chunk(a.oop_df, n0, nn, lane); pf_chunk(a.massinv, n0, nn, lane);
+#pragma unroll
+        for (int v = 0; v < 6; ++v) pf_chunk(a.acc_n[v], n0, nn, lane);
+        if (a.botfr) { pf_chunk(a.qp_dp, n0, nn, lane); pf_chunk(a.qp_u, n0, nn, lane); pf_chunk(a.qp_v, n0, nn, lane); }
+        if (a.has_visc) {
+            pf_chunk(a.pbv, n0, nn, lane);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) pf_chunk(a.bdg[v], n0, nn, lane);
+            if (a.acc_graduvb) {
+#pragma unroll
+                for (int v = 6; v < 10; ++v) pf_chunk(a.acc_n[v], n0, nn, lane);
+            }
+        }
+        if (a.load_q0) {
+#pragma unroll
+            for (int v = 0; v < 3; ++v) pf_chunk(a.qb0[v], n0, nn, lane);
+        }
+        if (a.load_q2) {
+#pragma unroll
+            for (int v = 0; v < 3; ++v) pf_chunk(a.qb2[v], n0, nn, lane);
+        }
+    } else if (warp == 1) {
+        pf_chunk(a.coriolis_q, q0, nq, lane); pf_chunk(a.tauwx_q, q0, nq, lane); pf_chunk(a.tauwy_q, q0, nq, lane);
+        pf_chunk(a.gzx_q, q0, nq, lane); pf_chunk(a.gzy_q, q0, nq, lane); pf_chunk(a.oop_q, q0, nq, lane);
+        pf_chunk(a.Hbcl, q0, nq, lane); pf_chunk(a.Quu, q0, nq, lane); pf_chunk(a.Quv, q0, nq, lane); pf_chunk(a.Qvv, q0, nq, lane);
+    } else if (warp == 2) {
+#pragma unroll
+        for (int v = 0; v < 6; ++v) pf_chunk(a.acc_q[v], q0, nq, lane);
+        if (a.botfr == 2) { pf_chunk(a.acc_q[6], q0, nq, lane); pf_chunk(a.acc_q[7], q0, nq, lane); }
+        const int ntr = a.has_visc ? 7 : 3;
+        for (int v = 0; v < ntr; ++v) pf_chunk(a.tr_in + (size_t)v * a.trstride, t0, nt, lane);
+        pf_chunk(a.pbn, t0, nt, lane);
+    } else {
+        pf_chunk(a.cL, s0, ns, lane); pf_chunk(a.cR, s0, ns, lane); pf_chunk(a.cLR, s0, ns, lane); pf_chunk(a.lam, s0, ns, lane);
+        pf_chunk(a.oop_edge, s0, ns, lane); pf_chunk(a.Quu_e, s0, ns, lane); pf_chunk(a.Quv_e, s0, ns, lane);
+        pf_chunk(a.Qvv_e, s0, ns, lane); pf_chunk(a.Hbcl_e, s0, ns, lane); pf_chunk(a.pbl, s0, ns, lane); pf_chunk(a.pbr, s0, ns, lane);
+#pragma unroll
+        for (int v = 0; v < 11; ++v) pf_chunk(a.acc_f[v], s0, ns, lane);
+    }
+}
+
 template <int G, int Q>
 __global__ void __launch_bounds__(128) k_btp_stage_fused(StageArgs a) {
     using LAY = FusedLayout<G, Q>;
@@ -118,6 +179,11 @@ __global__ void __launch_bounds__(128) k_btp_stage_fused(StageArgs a) {
     extern __shared__ double sm_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int e = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (a.pf_blocks > 0 && !a.rhs_only) {
+        const int wpb = blockDim.x >> 5;
+        const long e0 = ((long)blockIdx.x + a.pf_blocks) * wpb;
+        if (e0 < a.M.nelem) stage_prefetch<G, Q>(a, (int)e0, min(wpb, a.M.nelem - (int)e0), warp, lane);
+    }
     if (e >= a.M.nelem) return;
     double* sm = sm_all + (size_t)warp * LAY::TOTAL;
     double* nod = sm + LAY::NOD;
@@ -140,9 +206,12 @@ __global__ void __launch_bounds__(128) k_btp_stage_fused(StageArgs a) {
         double u = mx * rpb, v = my * rpb;
         nod[7 * NP + I] = u; nod[8 * NP + I] = v;
         if (acc) {
+            // all accumulator loads are issued before the first store (the stores may alias for the compiler)
             double t = 1.0 + dpp * a.oop_df[nbase + I];
-            a.acc_n[0][nbase + I] += t * t; a.acc_n[1][nbase + I] += u; a.acc_n[2][nbase + I] += v;
-            a.acc_n[3][nbase + I] += dpp; a.acc_n[4][nbase + I] += mx; a.acc_n[5][nbase + I] += my;
+            double c0 = a.acc_n[0][nbase + I], c1 = a.acc_n[1][nbase + I], c2 = a.acc_n[2][nbase + I];
+            double c3 = a.acc_n[3][nbase + I], c4 = a.acc_n[4][nbase + I], c5 = a.acc_n[5][nbase + I];
+            a.acc_n[0][nbase + I] = c0 + t * t; a.acc_n[1][nbase + I] = c1 + u; a.acc_n[2][nbase + I] = c2 + v;
+            a.acc_n[3][nbase + I] = c3 + dpp; a.acc_n[4][nbase + I] = c4 + mx; a.acc_n[5][nbase + I] = c5 + my;
         }
     }
     __syncwarp();
@@ -175,12 +244,14 @@ __global__ void __launch_bounds__(128) k_btp_stage_fused(StageArgs a) {
             double dku = Lr[0 * NP + I], dkv = Lr[1 * NP + I], deu = Lr[2 * NP + I], dev = Lr[3 * NP + I];
             double g0 = ksx * dku + etx * deu, g1 = ksy * dku + ety * deu, g2 = ksx * dkv + etx * dev, g3 = ksy * dkv + ety * dev;
             Lr[4 * NP + I] = g0; Lr[5 * NP + I] = g1; Lr[6 * NP + I] = g2; Lr[7 * NP + I] = g3;
-            if (acc && a.acc_graduvb) {
-                a.acc_n[6][nbase + I] += g0; a.acc_n[7][nbase + I] += g1; a.acc_n[8][nbase + I] += g2; a.acc_n[9][nbase + I] += g3;
-            }
             double pv = a.pbv[nbase + I];
-            double q0 = pv * g0 + a.bdg[0][nbase + I], q1 = pv * g1 + a.bdg[1][nbase + I];
-            double q2 = pv * g2 + a.bdg[2][nbase + I], q3 = pv * g3 + a.bdg[3][nbase + I];
+            double b0 = a.bdg[0][nbase + I], b1 = a.bdg[1][nbase + I], b2 = a.bdg[2][nbase + I], b3 = a.bdg[3][nbase + I];
+            if (acc && a.acc_graduvb) {
+                double c0 = a.acc_n[6][nbase + I], c1 = a.acc_n[7][nbase + I], c2 = a.acc_n[8][nbase + I], c3 = a.acc_n[9][nbase + I];
+                a.acc_n[6][nbase + I] = c0 + g0; a.acc_n[7][nbase + I] = c1 + g1; a.acc_n[8][nbase + I] = c2 + g2; a.acc_n[9][nbase + I] = c3 + g3;
+            }
+            double q0 = pv * g0 + b0, q1 = pv * g1 + b1;
+            double q2 = pv * g2 + b2, q3 = pv * g3 + b3;
             double w = c_ops.wg[n] * c_ops.wg[m] * J;
             Lr[8 * NP + I] = w * (ksx * q0 + ksy * q1); Lr[9 * NP + I] = w * (ksx * q2 + ksy * q3);
             Lr[10 * NP + I] = w * (etx * q0 + ety * q1); Lr[11 * NP + I] = w * (etx * q2 + ety * q3);
@@ -203,18 +274,25 @@ __global__ void __launch_bounds__(128) k_btp_stage_fused(StageArgs a) {
             tb_u = spd * ubot; tb_v = spd * vbot;
         }
         double fcor = a.coriolis_q[Iq];
-        double sc_x = fcor * vdp + a.g * (a.tauwx_q[Iq] - tb_u) - a.g * dp * a.gzx_q[Iq];
-        double sc_y = -fcor * udp + a.g * (a.tauwy_q[Iq] - tb_v) - a.g * dp * a.gzy_q[Iq];
-        double ope = 1.0 + dpp * a.oop_q[Iq];
-        double ope2 = ope * ope;
-        double Hq = ope2 * a.Hbcl[Iq];
-        double qu = ub * udp + ope * a.Quu[Iq];
-        double quv = ub * vdp + ope * a.Quv[Iq];
-        double qv = vb * vdp + ope * a.Qvv[Iq];
+        double s_twx = a.tauwx_q[Iq], s_twy = a.tauwy_q[Iq], s_gzx = a.gzx_q[Iq], s_gzy = a.gzy_q[Iq], s_oop = a.oop_q[Iq];
+        double s_H = a.Hbcl[Iq], s_uu = a.Quu[Iq], s_uv = a.Quv[Iq], s_vv = a.Qvv[Iq];
+        double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
         if (acc) {
-            a.acc_q[0][Iq] += qu; a.acc_q[1][Iq] += qv; a.acc_q[2][Iq] += quv; a.acc_q[3][Iq] += ope2;
-            a.acc_q[4][Iq] += ub; a.acc_q[5][Iq] += vb;
-            if (a.botfr == 2) { a.acc_q[6][Iq] += tb_u; a.acc_q[7][Iq] += tb_v; }
+            c0 = a.acc_q[0][Iq]; c1 = a.acc_q[1][Iq]; c2 = a.acc_q[2][Iq]; c3 = a.acc_q[3][Iq]; c4 = a.acc_q[4][Iq]; c5 = a.acc_q[5][Iq];
+            if (a.botfr == 2) { c6 = a.acc_q[6][Iq]; c7 = a.acc_q[7][Iq]; }
+        }
+        double sc_x = fcor * vdp + a.g * (s_twx - tb_u) - a.g * dp * s_gzx;
+        double sc_y = -fcor * udp + a.g * (s_twy - tb_v) - a.g * dp * s_gzy;
+        double ope = 1.0 + dpp * s_oop;
+        double ope2 = ope * ope;
+        double Hq = ope2 * s_H;
+        double qu = ub * udp + ope * s_uu;
+        double quv = ub * vdp + ope * s_uv;
+        double qv = vb * vdp + ope * s_vv;
+        if (acc) {
+            a.acc_q[0][Iq] = c0 + qu; a.acc_q[1][Iq] = c1 + qv; a.acc_q[2][Iq] = c2 + quv; a.acc_q[3][Iq] = c3 + ope2;
+            a.acc_q[4][Iq] = c4 + ub; a.acc_q[5][Iq] = c5 + vb;
+            if (a.botfr == 2) { a.acc_q[6][Iq] = c6 + tb_u; a.acc_q[7][Iq] = c7 + tb_v; }
         }
         double Fx2 = Hq + qu, Fy3 = Hq + qv;
         X[0 * NQ2 + q] = wq * (ksx * udp + ksy * vdp);   // Fk1
@@ -379,25 +457,33 @@ __global__ void __launch_bounds__(128) k_btp_stage_fused(StageArgs a) {
             double pbR = R[0], ppR = R[Q], mxR = R[2 * Q], myR = R[3 * Q];
             size_t fo = (size_t)oslot * Q + iq;
             double cL = a.cL[fo], cR = a.cR[fo], cLR = a.cLR[fo], lam = a.lam[fo];
+            const double s_oope = a.oop_edge[fo], s_uue = a.Quu_e[fo], s_uve = a.Quv_e[fo], s_vve = a.Qvv_e[fo], s_He = a.Hbcl_e[fo];
+            const bool upd = acc && left;
+            double fa[11], s_pbl = 1.0, s_pbr = 1.0;
+            if (upd) {
+                s_pbl = a.pbl[fo]; s_pbr = a.pbr[fo];
+#pragma unroll
+                for (int v = 0; v < 11; ++v) fa[v] = a.acc_f[v][fo];
+            }
             double pU_L = nxl * mxL + nyl * myL;
             double pU_R = -nxl * mxR - nyl * myR;
             double pbpert_edge = cL * ppL + cR * ppR + cLR * (pU_L + pU_R);
-            double ope_e = 1.0 + pbpert_edge * a.oop_edge[fo];
+            double ope_e = 1.0 + pbpert_edge * s_oope;
             double fex = cR * mxL + cL * mxR + lam * (nxl * ppL - nxl * ppR);
             double fey = cR * myL + cL * myR + lam * (nyl * ppL - nyl * ppR);
             double rl = 1.0 / pbL, rr = 1.0 / pbR;
             double ul = mxL * rl, ur = mxR * rr, vl = myL * rl, vr = myR * rr;
-            double quu = 0.5 * (ul * mxL + ur * mxR) + ope_e * a.Quu_e[fo];
-            double quv = 0.5 * (vl * mxL + vr * mxR) + ope_e * a.Quv_e[fo];
-            double qvu = 0.5 * (ul * myL + ur * myR) + ope_e * a.Quv_e[fo];
-            double qvv = 0.5 * (vl * myL + vr * myR) + ope_e * a.Qvv_e[fo];
+            double quu = 0.5 * (ul * mxL + ur * mxR) + ope_e * s_uue;
+            double quv = 0.5 * (vl * mxL + vr * mxR) + ope_e * s_uve;
+            double qvu = 0.5 * (ul * myL + ur * myR) + ope_e * s_uve;
+            double qvv = 0.5 * (vl * myL + vr * myR) + ope_e * s_vve;
             double e2 = ope_e * ope_e;
-            double Hf = e2 * a.Hbcl_e[fo];
-            if (acc && left) {
-                double ol = 1.0 + (ppL / a.pbl[fo]), orr = 1.0 + (ppR / a.pbr[fo]);
-                a.acc_f[0][fo] += quu; a.acc_f[1][fo] += quv; a.acc_f[2][fo] += qvu; a.acc_f[3][fo] += qvv;
-                a.acc_f[4][fo] += ol * ol; a.acc_f[5][fo] += orr * orr; a.acc_f[6][fo] += e2;
-                a.acc_f[7][fo] += ul; a.acc_f[8][fo] += ur; a.acc_f[9][fo] += vl; a.acc_f[10][fo] += vr;
+            double Hf = e2 * s_He;
+            if (upd) {
+                double ol = 1.0 + (ppL / s_pbl), orr = 1.0 + (ppR / s_pbr);
+                a.acc_f[0][fo] = fa[0] + quu; a.acc_f[1][fo] = fa[1] + quv; a.acc_f[2][fo] = fa[2] + qvu; a.acc_f[3][fo] = fa[3] + qvv;
+                a.acc_f[4][fo] = fa[4] + ol * ol; a.acc_f[5][fo] = fa[5] + orr * orr; a.acc_f[6][fo] = fa[6] + e2;
+                a.acc_f[7][fo] = fa[7] + ul; a.acc_f[8][fo] = fa[8] + ur; a.acc_f[9][fo] = fa[9] + vl; a.acc_f[10][fo] = fa[10] + vr;
             }
             double wq = c_ops.wq[iq] * nlen;
             double dispu = 0.5 * lam * (mxR - mxL), dispv = 0.5 * lam * (myR - myL);
