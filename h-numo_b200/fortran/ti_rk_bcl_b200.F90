@@ -1,0 +1,115 @@
+! ti_rk_bcl_b200.F90 -- drop-in replacement of the reference's src/ti_rk_bcl.F90 (same external subroutine name and
+! dummy arguments, src/ti_rk_bcl.F90:9,32-34) that runs the step on the B200 through libhnumo_b200.so.
+!
+! Build: replace ti_rk_bcl.o by this file + hnumo_b200_iface.F90 in src/Makefile and add -lhnumo_b200 -lcudart to the
+! link line.  numo3d.in, the p4est mesh, the initial conditions and all output stay untouched.
+! NOT compiled in the build container (no Fortran compiler / MPI / p4est there) -- see INTEGRATION.md.
+!
+! Two modes:
+!   default      : upload -> one step -> download every call: bit-compatible drop-in (state lives on the host between
+!                  calls exactly as in the reference), costs 2 x 8 B x (6 nlayers + 4) npoin of PCIe traffic per step;
+!   HNUMO_RESIDENT (cpp macro): the state stays on the GPU; the caller (mod_time_loop.F90:219, before diagnostics /
+!                  restart output) calls hnumo_b200_sync_host(q_df, qb_df, qprime_df) when it needs host copies.
+module hnumo_b200_state
+    use iso_c_binding
+    use hnumo_b200_iface
+    implicit none
+    type(c_ptr), save :: handle = c_null_ptr
+    logical, save :: resident_valid = .false.
+    real(c_double), allocatable, target, save :: elem_metrics(:,:), face_geom(:,:), ssprk_a_c(:,:)
+    integer(c_int32_t), allocatable, target, save :: face_c(:,:), nbh_proc_c(:), num_send_recv_c(:), nbh_send_recv_c(:)
+contains
+
+    subroutine hnumo_b200_setup()
+        ! everything ti_rk_bcl reads through `use` (src/ti_rk_bcl.F90:19-28 and the modules below it)
+        use mod_grid, only: nelem, npoin, nface, face
+        use mod_basis, only: ngl, nq, psiq, dpsiq, wnq, wgl, dpsi
+        use mod_input, only: nlayers, kstages, dt, dt_btp, botfr, cd_mlswe, method_visc, visc_mlswe, ad_mlswe
+        use mod_constants, only: gravity
+        use mod_metrics, only: ksiq_x, ksiq_y, etaq_x, etaq_y, jacq, massinv
+        use mod_face, only: normal_vector_q, jac_faceq
+        use mod_initial, only: pbprime_df, coriolis_df, tau_wind_df, zbot_df, alpha_mlswe, ssprk_a, ssprk_beta, &
+                               N_btp
+        use mod_parallel, only: num_nbh, nbh_proc, num_send_recv, nbh_send_recv
+        use mod_mpi_utilities, only: irank, numproc
+        type(hnumo_desc_t) :: d
+        integer :: e, f, ierr, ntot
+        character(kind=c_char) :: id(128)
+        include 'mpif.h'
+
+        allocate(elem_metrics(5,nelem), face_geom(3,nface), face_c(8,nface), ssprk_a_c(kstages,3))
+        do e = 1, nelem      ! bricks are affine: one metric set per element (include/hnumo_b200.h, elem_metrics)
+            elem_metrics(1,e) = ksiq_x(1,1,1,e); elem_metrics(2,e) = ksiq_y(1,1,1,e)
+            elem_metrics(3,e) = etaq_x(1,1,1,e); elem_metrics(4,e) = etaq_y(1,1,1,e)
+            elem_metrics(5,e) = jacq(1,1,1,e) / (wnq(1)*wnq(1))
+        end do
+        do f = 1, nface
+            face_geom(1:2,f) = normal_vector_q(1:2,1,1,f)
+            face_geom(3,f)   = jac_faceq(1,1,f) / wnq(1)
+            face_c(:,f) = int(face(:,f), c_int32_t)
+        end do
+        ssprk_a_c = ssprk_a(1:kstages,1:3)
+
+        d%abi_version = HNUMO_ABI_VERSION
+        d%nelem = nelem; d%ngl = ngl; d%nq = nq; d%nlayers = nlayers; d%nface = nface
+        d%kstages = kstages; d%N_btp = N_btp; d%dt = dt; d%dt_btp = dt_btp
+        d%botfr = botfr; d%method_visc = method_visc
+        d%gravity = gravity; d%cd_mlswe = cd_mlswe; d%visc_mlswe = visc_mlswe; d%ad_mlswe = ad_mlswe
+        d%psiq = c_loc(psiq); d%dpsiq = c_loc(dpsiq); d%wnq = c_loc(wnq); d%wgl = c_loc(wgl); d%dpsi = c_loc(dpsi)
+        d%face = c_loc(face_c); d%elem_metrics = c_loc(elem_metrics); d%face_geom = c_loc(face_geom)
+        d%pbprime_df = c_loc(pbprime_df); d%massinv = c_loc(massinv); d%coriolis_df = c_loc(coriolis_df)
+        d%tau_wind_df = c_loc(tau_wind_df); d%zbot_df = c_loc(zbot_df); d%alpha_mlswe = c_loc(alpha_mlswe)
+        d%ssprk_a = c_loc(ssprk_a_c); d%ssprk_beta = c_loc(ssprk_beta)
+        d%rank = irank; d%nranks = numproc; d%num_nbh = num_nbh
+        d%nbh_proc = c_null_ptr; d%num_send_recv = c_null_ptr; d%nbh_send_recv = c_null_ptr
+        if (num_nbh > 0) then
+            ntot = sum(num_send_recv(1:num_nbh))
+            allocate(nbh_proc_c(num_nbh), num_send_recv_c(num_nbh), nbh_send_recv_c(ntot))
+            nbh_proc_c = nbh_proc(1:num_nbh); num_send_recv_c = num_send_recv(1:num_nbh)
+            nbh_send_recv_c = nbh_send_recv(1:ntot)
+            d%nbh_proc = c_loc(nbh_proc_c); d%num_send_recv = c_loc(num_send_recv_c); d%nbh_send_recv = c_loc(nbh_send_recv_c)
+        end if
+        d%device = mod(irank, 8) + 1      ! one MPI rank per GPU of the 8-GPU box
+        d%stage_kernel_variant = 0
+        if (hnumo_init(d, handle) /= 0) stop "hnumo_init failed"
+        if (numproc > 1) then               ! replaces mod_mpi_communicator_create: NCCL id broadcast over MPI
+            if (irank == 0) then
+                if (hnumo_comm_get_unique_id(id) /= 0) stop "hnumo_comm_get_unique_id failed"
+            end if
+            call mpi_bcast(id, 128, MPI_CHARACTER, 0, mpi_comm_world, ierr)
+            if (hnumo_comm_init(handle, id) /= 0) stop "hnumo_comm_init failed"
+        end if
+    end subroutine hnumo_b200_setup
+
+    subroutine hnumo_b200_sync_host(q_df, qb_df, qprime_df)
+        real(c_double), intent(inout) :: q_df(*), qb_df(*), qprime_df(*)
+        if (hnumo_download_state(handle, q_df, qb_df, qprime_df) /= 0) stop "hnumo_download_state failed"
+    end subroutine hnumo_b200_sync_host
+end module hnumo_b200_state
+
+subroutine ti_rk_bcl(q_df, qb_df, qprime_df)
+    use iso_c_binding
+    use hnumo_b200_iface
+    use hnumo_b200_state
+    use mod_grid, only: npoin
+    use mod_input, only: nlayers
+    implicit none
+    real, dimension(4,npoin), intent(inout) :: qb_df
+    real, dimension(3,npoin,nlayers), intent(inout) :: q_df
+    real, dimension(3,npoin,nlayers), intent(inout) :: qprime_df
+    integer(c_int) :: rc
+
+    if (.not. c_associated(handle)) call hnumo_b200_setup()
+#ifdef HNUMO_RESIDENT
+    if (.not. resident_valid) then
+        if (hnumo_upload_state(handle, q_df, qb_df, qprime_df) /= 0) stop "hnumo_upload_state failed"
+        resident_valid = .true.
+    end if
+    rc = hnumo_step(handle, 1_c_int32_t)
+#else
+    rc = hnumo_ti_rk_bcl(handle, q_df, qb_df, qprime_df)
+#endif
+    ! same failure behaviour as the reference (src/mod_splitting.F90:74-77,228-231)
+    if (rc == 1) stop "Negative mass in thickness at some points"
+    if (rc /= 0) stop "hnumo_b200: CUDA/NCCL error in ti_rk_bcl"
+end subroutine ti_rk_bcl

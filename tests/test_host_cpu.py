@@ -66,6 +66,35 @@ def test_library_exports_every_declared_symbol(hn_lib):
     assert declared == set(hn.EXPORTS)
 
 
+def test_fortran_interface_matches_header(hn_lib):
+    """h-numo_b200/fortran/hnumo_b200_iface.F90 (the reference-side ISO_C_BINDING layer) lists the
+    fields of hnumo_desc_t in the order of the C struct / ctypes mirror, and binds only exported symbols."""
+    src = open(os.path.join(ROOT, "h-numo_b200", "fortran", "hnumo_b200_iface.F90")).read()
+    body = src.split("type, bind(C) :: hnumo_desc_t")[1].split("end type")[0]
+    fields = []
+    for line in body.splitlines():
+        line = line.split("!")[0]
+        if "::" in line:
+            fields += [f.strip() for f in line.split("::")[1].split(",") if f.strip()]
+    assert fields == [f[0] for f in hn.Desc._fields_]
+    hdr = open(os.path.join(ROOT, "include", "hnumo_b200.h")).read()
+    struct = hdr.split("typedef struct hnumo_desc {")[1].split("} hnumo_desc_t;")[0]
+    struct = re.sub(r"/\*.*?\*/", "", struct, flags=re.S)
+    cfields = []
+    for stmt in struct.split(";"):
+        stmt = stmt.strip()
+        if not stmt:
+            continue
+        names = stmt.replace("const", "").replace("*", " ").split()[1:]
+        cfields += [n.strip(",") for n in " ".join(names).split(",")]
+    cfields = [c.strip() for c in cfields if c.strip()]
+    assert cfields == fields
+    for name in re.findall(r'bind\(C, name="(hnumo_[a-z_0-9]+)"\)', src):
+        assert hasattr(hn_lib, name), name
+    shim = open(os.path.join(ROOT, "h-numo_b200", "fortran", "ti_rk_bcl_b200.F90")).read()
+    assert re.search(r"subroutine ti_rk_bcl\(q_df, qb_df, qprime_df\)", shim)
+
+
 def test_no_cpu_fallback_without_gpu(hn_lib):
     """On a box without a CUDA device hnumo_init must fail loudly (no CPU path)."""
     import torch
