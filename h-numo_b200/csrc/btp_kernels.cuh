@@ -459,13 +459,17 @@ __global__ void k_btp_prime_traces(PrimeArgs a) {
 }
 
 // Reconstruct the full set of reference time averages (mod_rk_mlswe.F90:124-149) from the reduced sums.
+// The sums are addressed as  acc_n[v][e*en + node],  acc_q[v][e*eq + point],  acc_f[v][slot*ef + iq]  and the traces
+// of the nodal sums as  tr[v*tr_vs + rec*tr_rs + n]  so that both the plane layout (en = npts, eq = nq2, ef = nq,
+// tr_vs = plane stride, tr_rs = ngl) and the record layout of stage_tma.cuh can be read.
 struct FinalizeArgs {
     Mesh M;
     const double* acc_n[10];
     const double* acc_q[8];
     const double* acc_f[11];
-    const double* tr;  // traces of the nodal sums (mode-1 prime): 0 S_pbpert 1 S_mx 2 S_my (3..6 graduvb sums)
-    size_t trstride;
+    size_t en, eq, ef;
+    const double* tr;  // traces of the nodal sums: 0 S_pbpert 1 S_mx 2 S_my
+    size_t tr_vs, tr_rs;
     double* ave_q[12];
     double* ave_f[16];
     double* ave_n[7];
@@ -473,42 +477,56 @@ struct FinalizeArgs {
     const double *qp_dp, *qp_u, *qp_v;
     double S, N_inv, cd_over_g;
     int botfr;
+    int derive_graduvb;  // 1: graduvb_ave = grad(uvb_ave_df) (the gradient is linear); 0: acc_n[6..9] hold the per-stage sums
 };
 __global__ void k_btp_finalize(FinalizeArgs a) {
     extern __shared__ double sm[];
     const int ngl = a.M.ngl, nq = a.M.nq, npts = a.M.npts, nq2 = a.M.nq2, per = ngl * nq;
     const int e = blockIdx.x, tid = threadIdx.x;
     SOps o = load_sops(sm, ngl, nq);
-    double* nod = sm + sops_doubles(ngl, nq);  // 0 S_pbpert 1 S_mx 2 S_my 3 pp 4 up 5 vp
-    double* tmp = nod + 6 * npts;
+    double* nod = sm + sops_doubles(ngl, nq);  // 0 S_pbpert 1 S_mx 2 S_my 3 pp 4 up 5 vp 6 ub_ave 7 vb_ave
+    double* tmp = nod + 8 * npts;
     const size_t nbase = (size_t)e * npts, qbase = (size_t)e * nq2;
+    const size_t ab_n = (size_t)e * a.en, ab_q = (size_t)e * a.eq;
     if (tid < npts) {
-        nod[tid] = a.acc_n[3][nbase + tid]; nod[npts + tid] = a.acc_n[4][nbase + tid]; nod[2 * npts + tid] = a.acc_n[5][nbase + tid];
+        nod[tid] = a.acc_n[3][ab_n + tid]; nod[npts + tid] = a.acc_n[4][ab_n + tid]; nod[2 * npts + tid] = a.acc_n[5][ab_n + tid];
         if (a.botfr == 1) {
             nod[3 * npts + tid] = a.qp_dp[nbase + tid]; nod[4 * npts + tid] = a.qp_u[nbase + tid]; nod[5 * npts + tid] = a.qp_v[nbase + tid];
         }
-        a.ave_n[0][nbase + tid] = a.N_inv * a.acc_n[0][nbase + tid];
-        a.ave_n[1][nbase + tid] = a.N_inv * a.acc_n[1][nbase + tid];
-        a.ave_n[2][nbase + tid] = a.N_inv * a.acc_n[2][nbase + tid];
-        for (int v = 0; v < 4; ++v) a.ave_n[3 + v][nbase + tid] = a.N_inv * a.acc_n[6 + v][nbase + tid];
+        double ua = a.N_inv * a.acc_n[1][ab_n + tid], va = a.N_inv * a.acc_n[2][ab_n + tid];
+        nod[6 * npts + tid] = ua; nod[7 * npts + tid] = va;
+        a.ave_n[0][nbase + tid] = a.N_inv * a.acc_n[0][ab_n + tid];
+        a.ave_n[1][nbase + tid] = ua;
+        a.ave_n[2][nbase + tid] = va;
+        if (!a.derive_graduvb)
+            for (int v = 0; v < 4; ++v) a.ave_n[3 + v][nbase + tid] = a.N_inv * a.acc_n[6 + v][ab_n + tid];
     }
     __syncthreads();
+    if (a.derive_graduvb && tid < npts) {
+        const double ksx = a.M.em[e * 5 + 0], ksy = a.M.em[e * 5 + 1], etx = a.M.em[e * 5 + 2], ety = a.M.em[e * 5 + 3];
+        int m = tid / ngl, n = tid - m * ngl;
+        double dk, de;
+        nodal_grad(o, ngl, nod + 6 * npts, n, m, dk, de);
+        a.ave_n[3][nbase + tid] = ksx * dk + etx * de; a.ave_n[4][nbase + tid] = ksy * dk + ety * de;
+        nodal_grad(o, ngl, nod + 7 * npts, n, m, dk, de);
+        a.ave_n[5][nbase + tid] = ksx * dk + etx * de; a.ave_n[6][nbase + tid] = ksy * dk + ety * de;
+    }
     sf_pass1(o, ngl, nq, a.botfr == 1 ? 6 : 3, nod, npts, tmp, nullptr);
     __syncthreads();
     if (tid < nq2) {
         int j = tid / nq, i = tid - j * nq;
-        size_t Iq = qbase + tid;
+        size_t Iq = qbase + tid, Aq = ab_q + tid;
         double sp = sf_eval(o, ngl, nq, tmp, 0, i, j), smx = sf_eval(o, ngl, nq, tmp, 1, i, j), smy = sf_eval(o, ngl, nq, tmp, 2, i, j);
-        double ope2 = a.acc_q[3][Iq];
+        double ope2 = a.acc_q[3][Aq];
         a.ave_q[0][Iq] = a.N_inv * (a.S + sp * a.oop_q[Iq]);
         a.ave_q[1][Iq] = a.N_inv * (a.Hbcl[Iq] * ope2);
-        a.ave_q[2][Iq] = a.N_inv * a.acc_q[0][Iq];
-        a.ave_q[3][Iq] = a.N_inv * a.acc_q[1][Iq];
-        a.ave_q[4][Iq] = a.N_inv * a.acc_q[2][Iq];
+        a.ave_q[2][Iq] = a.N_inv * a.acc_q[0][Aq];
+        a.ave_q[3][Iq] = a.N_inv * a.acc_q[1][Aq];
+        a.ave_q[4][Iq] = a.N_inv * a.acc_q[2][Aq];
         a.ave_q[5][Iq] = a.N_inv * ope2;
         a.ave_q[6][Iq] = a.N_inv * smx;
         a.ave_q[7][Iq] = a.N_inv * smy;
-        double ubs = a.acc_q[4][Iq], vbs = a.acc_q[5][Iq];
+        double ubs = a.acc_q[4][Aq], vbs = a.acc_q[5][Aq];
         a.ave_q[8][Iq] = a.N_inv * ubs;
         a.ave_q[9][Iq] = a.N_inv * vbs;
         double tbx = 0.0, tby = 0.0;
@@ -516,7 +534,7 @@ __global__ void k_btp_finalize(FinalizeArgs a) {
             double pp = sf_eval(o, ngl, nq, tmp, 3, i, j), up = sf_eval(o, ngl, nq, tmp, 4, i, j), vp = sf_eval(o, ngl, nq, tmp, 5, i, j);
             double spd = a.cd_over_g * pp;
             tbx = spd * (a.S * up + ubs); tby = spd * (a.S * vp + vbs);
-        } else if (a.botfr == 2) { tbx = a.acc_q[6][Iq]; tby = a.acc_q[7][Iq]; }
+        } else if (a.botfr == 2) { tbx = a.acc_q[6][Aq]; tby = a.acc_q[7][Aq]; }
         a.ave_q[10][Iq] = a.N_inv * tbx;
         a.ave_q[11][Iq] = a.N_inv * tby;
     }
@@ -533,8 +551,8 @@ __global__ void k_btp_finalize(FinalizeArgs a) {
                 int I = face_node(s, n, ngl);
                 double ow[3] = {nod[I], nod[npts + I], nod[2 * npts + I]}, nv[3];
                 if (nb >= 0 || nb == NBR_HALO) {
-                    size_t base = (nb >= 0) ? ((size_t)nb * 4 + nbs) * ngl + n : ((size_t)a.M.nslots + nbs) * ngl + n;
-                    for (int v = 0; v < 3; ++v) nv[v] = a.tr[v * a.trstride + base];
+                    size_t rec = (nb >= 0) ? ((size_t)nb * 4 + nbs) : ((size_t)a.M.nslots + nbs);
+                    for (int v = 0; v < 3; ++v) nv[v] = a.tr[v * a.tr_vs + rec * a.tr_rs + n];
                 } else {
                     nv[0] = ow[0]; nv[1] = ow[1]; nv[2] = ow[2];
                     if (nb == NBR_FREESLIP) { double un = nxl * ow[1] + nyl * ow[2]; nv[1] = ow[1] - 2.0 * un * nxl; nv[2] = ow[2] - 2.0 * un * nyl; }
@@ -542,19 +560,19 @@ __global__ void k_btp_finalize(FinalizeArgs a) {
                 }
                 for (int v = 0; v < 3; ++v) { sl[v] += hi * ow[v]; sr[v] += hi * nv[v]; }
             }
-            size_t fo = (size_t)slot * nq + iq;
+            size_t fo = (size_t)slot * nq + iq, fa = (size_t)slot * a.ef + iq;
             double cL = a.cL[fo], cR = a.cR[fo], lam = a.lam[fo];
             a.ave_f[0][fo] = a.N_inv * (cR * sl[1] + cL * sr[1] + lam * (nxl * sl[0] - nxl * sr[0]));
             a.ave_f[1][fo] = a.N_inv * (cR * sl[2] + cL * sr[2] + lam * (nyl * sl[0] - nyl * sr[0]));
-            double e2 = a.acc_f[6][fo];
+            double e2 = a.acc_f[6][fa];
             a.ave_f[2][fo] = a.N_inv * (a.Hbcl_e[fo] * e2);
-            for (int v = 0; v < 4; ++v) a.ave_f[3 + v][fo] = a.N_inv * a.acc_f[v][fo];
+            for (int v = 0; v < 4; ++v) a.ave_f[3 + v][fo] = a.N_inv * a.acc_f[v][fa];
             a.ave_f[7][fo] = a.N_inv * (a.S + sl[0] / a.pbl[fo]);
             a.ave_f[8][fo] = a.N_inv * (a.S + sr[0] / a.pbr[fo]);
-            a.ave_f[9][fo] = a.N_inv * a.acc_f[4][fo];
-            a.ave_f[10][fo] = a.N_inv * a.acc_f[5][fo];
+            a.ave_f[9][fo] = a.N_inv * a.acc_f[4][fa];
+            a.ave_f[10][fo] = a.N_inv * a.acc_f[5][fa];
             a.ave_f[11][fo] = a.N_inv * e2;
-            for (int v = 0; v < 4; ++v) a.ave_f[12 + v][fo] = a.N_inv * a.acc_f[7 + v][fo];
+            for (int v = 0; v < 4; ++v) a.ave_f[12 + v][fo] = a.N_inv * a.acc_f[7 + v][fa];
         }
     }
 }

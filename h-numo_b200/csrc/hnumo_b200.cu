@@ -7,6 +7,7 @@
 #include "btp_kernels.cuh"
 #include "halo.cuh"
 #include "stage_fused.cuh"
+#include "stage_tma.cuh"
 
 namespace hn {
 
@@ -163,7 +164,7 @@ static void fill_stage_args(Solver& S, StageArgs& a, Planes& qb, const Planes& q
 }
 
 static int launch_stage(Solver& S, const StageArgs& a) {
-    if (S.variant == 0 && stage_fused_supported(S)) return launch_stage_fused(S, a);
+    if (S.variant != 1 && stage_fused_supported(S)) return launch_stage_fused(S, a);
     StageSmem L(S.ngl, S.nq);
     k_btp_stage_simple<<<S.nelem, threads_for(S), L.total * sizeof(double), S.stream>>>(a);
     S.n_launches++;
@@ -195,8 +196,10 @@ int rhs_btp_only(Solver& S, Planes& qb, const Planes& qprime, double* d_rhs_out)
     return 0;
 }
 
+static int btp_solve_rec(Solver& S, Planes& qb, const Planes& qprime);
 // ti_barotropic_ssprk_mlswe (mod_rk_mlswe.F90:19-151)
 int btp_solve(Solver& S, Planes& qb, const Planes& qprime) {
+    if (S.variant == 0 && stage_tma_supported(S)) return btp_solve_rec(S, qb, qprime);
     cudaMemsetAsync(S.acc_n.p, 0, S.acc_n.stride * S.acc_n.n * sizeof(double), S.stream);
     cudaMemsetAsync(S.acc_q.p, 0, S.acc_q.stride * S.acc_q.n * sizeof(double), S.stream);
     cudaMemsetAsync(S.acc_f.p, 0, S.acc_f.stride * S.acc_f.n * sizeof(double), S.stream);
@@ -240,7 +243,8 @@ int btp_solve(Solver& S, Planes& qb, const Planes& qprime) {
         for (int v = 0; v < 10; ++v) f.acc_n[v] = S.acc_n[v];
         for (int v = 0; v < 8; ++v) f.acc_q[v] = S.acc_q[v];
         for (int v = 0; v < 11; ++v) f.acc_f[v] = S.acc_f[v];
-        f.tr = S.trace[cur].p; f.trstride = S.trace[cur].stride;
+        f.tr = S.trace[cur].p; f.tr_vs = S.trace[cur].stride; f.tr_rs = S.ngl;
+        f.en = S.npts; f.eq = S.nq2; f.ef = S.nq; f.derive_graduvb = 0;
         for (int v = 0; v < 12; ++v) f.ave_q[v] = S.ave_q[v];
         for (int v = 0; v < 16; ++v) f.ave_f[v] = S.ave_f[v];
         for (int v = 0; v < 7; ++v) f.ave_n[v] = S.ave_n[v];
@@ -248,7 +252,7 @@ int btp_solve(Solver& S, Planes& qb, const Planes& qprime) {
         f.qp_dp = qprime[0 * S.nl + S.nl - 1]; f.qp_u = qprime[1 * S.nl + S.nl - 1]; f.qp_v = qprime[2 * S.nl + S.nl - 1];
         f.S = (double)(S.kstages * S.N_btp); f.N_inv = 1.0 / (double)(S.kstages * S.N_btp); f.cd_over_g = S.cd / S.g;
         f.botfr = S.botfr;
-        size_t sm = (sops_doubles_host(S.ngl, S.nq) + 6 * S.npts + 6 * S.ngl * S.nq) * sizeof(double);
+        size_t sm = (sops_doubles_host(S.ngl, S.nq) + 8 * S.npts + 6 * S.ngl * S.nq) * sizeof(double);
         k_btp_finalize<<<S.nelem, threads_for(S), sm, S.stream>>>(f);
         S.n_launches++;
         // halo copy of the averaged LDG gradient traces (graduvb_face_ave side 2 on processor boundaries)
@@ -261,6 +265,101 @@ int btp_solve(Solver& S, Planes& qb, const Planes& qprime) {
             S.n_launches++;
         }
     }
+    HN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// halo exchange of trace records: gather -> send/recv straight into the halo region of the trace buffer
+static int halo_exchange_trace_records(Solver& S, double* tr, int tside) {
+    if (S.nhalo == 0) return 0;
+    size_t tot = (size_t)S.nhalo * tside;
+    k_pack_trace_records<<<(tot + 255) / 256, 256, 0, S.stream>>>(tr, S.d_halo_slot, S.nhalo, tside, S.d_send);
+    S.n_launches++;
+    return halo_sendrecv(S, (size_t)tside, tr + (size_t)S.nslots * tside);
+}
+
+// ti_barotropic_ssprk_mlswe (mod_rk_mlswe.F90:19-151) on the record layout with the TMA stage kernel
+static int btp_solve_rec(Solver& S, Planes& qb, const Planes& qprime) {
+    const RecDims D = make_recdims(S.ngl, S.nq);
+    const size_t NE = (size_t)S.nelem;
+    const int naccq = (S.botfr == 2) ? 8 : 6;
+    cudaMemsetAsync(S.r_accn, 0, NE * D.ACCN * sizeof(double), S.stream);
+    cudaMemsetAsync(S.r_accq, 0, NE * D.ACCQ * sizeof(double), S.stream);
+    cudaMemsetAsync(S.r_accf, 0, NE * 4 * D.ASIDE * sizeof(double), S.stream);
+    cudaMemsetAsync(S.r_q2, 0, NE * D.QB * sizeof(double), S.stream);
+    int cur = 0;
+    {
+        RecPackArgs p; memset(&p, 0, sizeof(p));
+        p.M = S.mesh; p.D = D;
+        for (int v = 0; v < 3; ++v) p.qb[v] = qb[v];
+        const int bl = S.nl - 1;
+        const double* nstp[14] = {S.pbprime_df, S.massinv, qprime[0 * S.nl + bl], qprime[1 * S.nl + bl], qprime[2 * S.nl + bl], S.pbprime_visc,
+                                  S.btp_dpp_graduv[0], S.btp_dpp_graduv[1], S.btp_dpp_graduv[2], S.btp_dpp_graduv[3],
+                                  S.coriolis_df, S.tauw_df, S.tauw_df + S.npoin, S.zbot_df};
+        for (int v = 0; v < 14; ++v) p.nstp[v] = nstp[v];
+        const double* qstp[5] = {S.oop_q, S.Hbcl, S.Quu, S.Quv, S.Qvv};
+        for (int v = 0; v < 5; ++v) p.qstp[v] = qstp[v];
+        const double* fstp[11] = {S.cL, S.cR, S.cLR, S.lam, S.oop_edge, S.Quu_e, S.Quv_e, S.Qvv_e, S.Hbcl_e, S.pbl, S.pbr};
+        for (int v = 0; v < 11; ++v) p.fstp[v] = fstp[v];
+        for (int v = 0; v < 4; ++v) p.bdg[v] = S.btp_dpp_graduv[v];
+        p.pbv = S.pbprime_visc; p.pbn = S.pbn; p.hstat = S.h_stat.p; p.hstat_stride = S.h_stat.stride;
+        p.r_qb = S.r_qb; p.r_nst = S.r_nst; p.r_qst = S.r_qst; p.r_fst = S.r_fst; p.r_vst = S.r_vst; p.r_tr = S.r_tr[cur];
+        p.has_visc = S.has_visc;
+        k_rec_pack<<<S.nelem, 128, 2 * S.npts * sizeof(double), S.stream>>>(p);
+        S.n_launches++;
+        if (halo_exchange_trace_records(S, S.r_tr[cur], D.TSIDE)) return -1;
+    }
+    cudaEvent_t e_start, e_stop;
+    take_event_pair(S, 0, e_start, e_stop);
+    cudaEventRecord(e_start, S.stream);
+    TmaArgs a; memset(&a, 0, sizeof(a));
+    a.nelem = S.nelem; a.nslots = S.nslots;
+    a.geoc = S.r_geoc; a.nst = S.r_nst; a.qst = S.r_qst; a.fst = S.r_fst; a.vst = S.r_vst;
+    a.qb = S.r_qb; a.q0 = S.r_q0; a.q2 = S.r_q2; a.accn = S.r_accn; a.accq = S.r_accq; a.accf = S.r_accf;
+    a.nbx = (const int4*)S.d_nbx;
+    a.g = S.g; a.cd = S.cd; a.alpha_bot = S.alpha[S.nl - 1]; a.visc = S.visc; a.botfr = S.botfr; a.has_visc = S.has_visc;
+    for (int mstep = 1; mstep <= S.N_btp; ++mstep) {
+        for (int ik = 1; ik <= S.kstages; ++ik) {
+            a.a1 = S.ssprk_a[ik - 1][0]; a.a2 = S.ssprk_a[ik - 1][1]; a.a3 = S.ssprk_a[ik - 1][2];
+            a.dtt = S.dt_btp * S.ssprk_beta[ik - 1];
+            a.load_q0 = (ik > 1 && a.a1 != 0.0);
+            a.load_q2 = (a.a3 != 0.0);
+            a.store_q0 = (ik == 1 && S.kstages > 1);
+            a.store_q2 = (S.kstages == 5 && ik == 2);
+            a.tr_in = S.r_tr[cur]; a.tr_out = S.r_tr[cur ^ 1];
+            if (launch_stage_tma(S, a, naccq)) return -1;
+            cur ^= 1;
+            if (halo_exchange_trace_records(S, S.r_tr[cur], D.TSIDE)) return -1;
+        }
+    }
+    cudaEventRecord(e_stop, S.stream);
+    S.n_stages += (long)S.N_btp * S.kstages;
+    // state back to planes, time averages
+    k_rec_unpack_qb<<<nblk(S.npoin), 256, 0, S.stream>>>(S.nelem, D, S.r_qb, qb[0], qb[1], qb[2]);
+    k_rec_sum_traces<<<nblk((size_t)S.nslots * S.ngl), 256, 0, S.stream>>>(S.nelem, D, S.r_accn, S.r_tr[cur]);
+    S.n_launches += 2;
+    if (halo_exchange_trace_records(S, S.r_tr[cur], D.TSIDE)) return -1;
+    FinalizeArgs f; memset(&f, 0, sizeof(f));
+    f.M = S.mesh;
+    for (int v = 0; v < 6; ++v) f.acc_n[v] = S.r_accn + (size_t)v * D.NP;
+    for (int v = 6; v < 10; ++v) f.acc_n[v] = nullptr;
+    for (int v = 0; v < 8; ++v) f.acc_q[v] = S.r_accq + (size_t)v * D.NQ2;
+    for (int v = 0; v < 11; ++v) f.acc_f[v] = S.r_accf + (size_t)v * D.Q;
+    f.en = D.ACCN; f.eq = D.ACCQ; f.ef = D.ASIDE; f.derive_graduvb = 1;
+    f.tr = S.r_tr[cur]; f.tr_vs = D.G; f.tr_rs = D.TSIDE;
+    for (int v = 0; v < 12; ++v) f.ave_q[v] = S.ave_q[v];
+    for (int v = 0; v < 16; ++v) f.ave_f[v] = S.ave_f[v];
+    for (int v = 0; v < 7; ++v) f.ave_n[v] = S.ave_n[v];
+    f.oop_q = S.oop_q; f.Hbcl = S.Hbcl; f.Hbcl_e = S.Hbcl_e; f.cL = S.cL; f.cR = S.cR; f.lam = S.lam; f.pbl = S.pbl; f.pbr = S.pbr;
+    f.qp_dp = qprime[0 * S.nl + S.nl - 1]; f.qp_u = qprime[1 * S.nl + S.nl - 1]; f.qp_v = qprime[2 * S.nl + S.nl - 1];
+    f.S = (double)(S.kstages * S.N_btp); f.N_inv = 1.0 / (double)(S.kstages * S.N_btp); f.cd_over_g = S.cd / S.g;
+    f.botfr = S.botfr;
+    size_t sm = (sops_doubles_host(S.ngl, S.nq) + 8 * S.npts + 6 * S.ngl * S.nq) * sizeof(double);
+    k_btp_finalize<<<S.nelem, threads_for(S), sm, S.stream>>>(f);
+    S.n_launches++;
+    // graduvb_face_ave side 2 on processor boundaries = the neighbour's averaged gradient at the face nodes
+    if (S.has_visc && S.nhalo > 0)
+        if (halo_exchange_nodal(S, S.ave_n[3], 4, S.ave_n.stride, S.h_gub)) return -1;
     HN_CUDA(cudaGetLastError());
     return 0;
 }
@@ -562,7 +661,21 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     size_t hs = (size_t)std::max(S.nhalo, 1) * S.ngl;
     S.h_q = palloc(S, 3 * nl, hs); S.h_dp = palloc(S, nl, hs); S.h_dpv = palloc(S, nl, hs); S.h_dpg = palloc(S, 4 * nl, hs);
     S.h_gub = palloc(S, 4, hs); S.h_stat = palloc(S, 5, hs);
-    S.halo_capacity = (size_t)std::max(7, 4 * nl) * hs;
+    S.halo_capacity = (size_t)std::max(8, 4 * nl) * hs;
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, S.device) == cudaSuccess) S.num_sms = prop.multiProcessorCount;
+    }
+    if (stage_tma_supported(S)) {
+        const RecDims D = make_recdims(S.ngl, S.nq);
+        const size_t NE = (size_t)S.nelem;
+        S.r_geoc = dalloc(S, NE * D.GEOC); S.r_qb = dalloc(S, NE * D.QB); S.r_q0 = dalloc(S, NE * D.QB); S.r_q2 = dalloc(S, NE * D.QB);
+        S.r_nst = dalloc(S, NE * D.NST); S.r_accn = dalloc(S, NE * D.ACCN); S.r_qst = dalloc(S, NE * D.QST); S.r_accq = dalloc(S, NE * D.ACCQ);
+        S.r_fst = dalloc(S, NE * 4 * D.FSIDE); S.r_accf = dalloc(S, NE * 4 * D.ASIDE); S.r_vst = dalloc(S, NE * 4 * D.VSIDE);
+        S.r_tr[0] = dalloc(S, (size_t)(S.nslots + S.nhalo) * D.TSIDE); S.r_tr[1] = dalloc(S, (size_t)(S.nslots + S.nhalo) * D.TSIDE);
+        HN_CUDA(cudaMalloc(&S.d_nbx, NE * sizeof(int4)));
+        if (S.r_geoc && S.d_nbx) k_rec_static<<<nblk(NE), 256, 0, S.stream>>>(M, D, S.r_geoc, (int4*)S.d_nbx);
+    }
     S.d_send = dalloc(S, S.halo_capacity); S.d_recv = dalloc(S, S.halo_capacity);
     HN_CUDA(cudaMalloc(&S.d_flag, sizeof(int)));
     cudaMemsetAsync(S.d_flag, 0, sizeof(int), S.stream);
@@ -580,6 +693,7 @@ int hnumo_finalize(hnumo_handle_t h) {
     cudaStreamSynchronize(S.stream);
     halo_comm_destroy(S);
     for (void* p : S.allocs) cudaFree(p);
+    if (S.d_nbx) cudaFree(S.d_nbx);
     cudaFree(S.d_nbr); cudaFree(S.d_nbslot); cudaFree(S.d_flag); if (S.d_halo_slot) cudaFree(S.d_halo_slot);
     cudaEventDestroy(S.ev0); cudaEventDestroy(S.ev1); cudaEventDestroy(S.ev2); cudaEventDestroy(S.ev3);
     cudaStreamDestroy(S.stream); cudaStreamDestroy(S.comm_stream);
@@ -775,6 +889,7 @@ int hnumo_set_option(hnumo_handle_t h, const char* key, double value) {
     if (!strcmp(key, "stage_kernel_variant")) { S.variant = (int)value; return 0; }
     if (!strcmp(key, "use_graph")) { S.use_graph = (int)value; return 0; }
     if (!strcmp(key, "prefetch_blocks")) { S.pf_blocks = (int)value; return 0; }
+    if (!strcmp(key, "tma_blocks_per_sm")) { S.tma_blocks_per_sm = (int)value; return 0; }
     set_error("hnumo_set_option", "unknown key");
     return -2;
 }

@@ -125,6 +125,11 @@ struct Solver {
     size_t ev_used = 0;
     double ms_btp = 0, ms_step = 0, ms_btp_last = 0, ms_step_last = 0;
     long n_stages = 0, n_steps = 0, n_launches = 0;
+    // record layout of the TMA stage kernel (stage_tma.cuh)
+    double *r_geoc = nullptr, *r_qb = nullptr, *r_q0 = nullptr, *r_q2 = nullptr, *r_nst = nullptr, *r_accn = nullptr,
+           *r_qst = nullptr, *r_accq = nullptr, *r_fst = nullptr, *r_accf = nullptr, *r_vst = nullptr, *r_tr[2] = {nullptr, nullptr};
+    void* d_nbx = nullptr;
+    int num_sms = 148, tma_blocks_per_sm = 0;
     int use_graph = 0;
     int pf_blocks = 100;  // L2 prefetch distance of the fused stage kernel, in thread blocks
     std::vector<void*> allocs;
