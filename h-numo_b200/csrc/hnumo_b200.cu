@@ -8,6 +8,7 @@
 #include "halo.cuh"
 #include "stage_fused.cuh"
 #include "stage_tma.cuh"
+#include "stage_rec.cuh"
 
 namespace hn {
 
@@ -199,7 +200,7 @@ int rhs_btp_only(Solver& S, Planes& qb, const Planes& qprime, double* d_rhs_out)
 static int btp_solve_rec(Solver& S, Planes& qb, const Planes& qprime);
 // ti_barotropic_ssprk_mlswe (mod_rk_mlswe.F90:19-151)
 int btp_solve(Solver& S, Planes& qb, const Planes& qprime) {
-    if (S.variant == 0 && stage_tma_supported(S)) return btp_solve_rec(S, qb, qprime);
+    if ((S.variant == 0 || S.variant == 3) && stage_tma_supported(S)) return btp_solve_rec(S, qb, qprime);
     cudaMemsetAsync(S.acc_n.p, 0, S.acc_n.stride * S.acc_n.n * sizeof(double), S.stream);
     cudaMemsetAsync(S.acc_q.p, 0, S.acc_q.stride * S.acc_q.n * sizeof(double), S.stream);
     cudaMemsetAsync(S.acc_f.p, 0, S.acc_f.stride * S.acc_f.n * sizeof(double), S.stream);
@@ -327,7 +328,7 @@ static int btp_solve_rec(Solver& S, Planes& qb, const Planes& qprime) {
             a.store_q0 = (ik == 1 && S.kstages > 1);
             a.store_q2 = (S.kstages == 5 && ik == 2);
             a.tr_in = S.r_tr[cur]; a.tr_out = S.r_tr[cur ^ 1];
-            if (launch_stage_tma(S, a, naccq)) return -1;
+            if ((S.variant == 3 ? launch_stage_tma(S, a, naccq) : launch_stage_rec(S, a, naccq))) return -1;
             cur ^= 1;
             if (halo_exchange_trace_records(S, S.r_tr[cur], D.TSIDE)) return -1;
         }

@@ -229,7 +229,8 @@ __global__ void __launch_bounds__(128, 5) k_btp_stage_tma(const TmaArgs a, const
             const long en = (long)e + gridDim.x;
             if (en < a.nelem) nbx_cur = a.nbx[en];  // connectivity of the next element, one iteration ahead
         }
-        mbar_wait(bar, parity);
+        if (warp == 0) mbar_wait(bar, parity);   // one polling warp; the others sleep in the hardware barrier
+        __syncthreads();
 
         const double ksx = geo[0], ksy = geo[1], etx = geo[2], ety = geo[3], J = geo[4];
         const double* fg = geo + 6;

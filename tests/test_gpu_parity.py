@@ -24,7 +24,7 @@ DECKS = {
     "noslip_rk3": lambda: dict(hn.decks.SHIPPED["double_gyre"], nelx=6, nely=5, x_boundary=(2, 2), kstages=3, botfr=2, cd_mlswe=1e-3),
     "nop3_5layers": lambda: dict(hn.decks.synthetic_double_gyre(5, 5, nop=3, nlayers=5)),
 }
-VARIANTS = [0, 1, 2]  # 0: TMA record kernel, 1: simple reference-form kernel, 2: warp-per-element fused kernel
+VARIANTS = [0, 1, 2, 3]  # 0: record kernel (output per thread), 1: simple reference-form kernel, 2: warp-per-element fused kernel, 3: record kernel (line per lane)
 
 
 def natural_errors(S, O, deck):
@@ -147,7 +147,7 @@ def test_variants_agree_bitwise_on_mass():
         S.step(3)
         outs.append(S.download_state())
         S.close()
-    for k in (0, 2):
+    for k in (0, 2, 3):
         assert rel_l2(outs[k][1][:, 0], outs[1][1][:, 0]) < 1e-13
         assert rel_l2(outs[k][0][:, :, 0], outs[1][0][:, :, 0]) < 1e-12
 
