@@ -161,7 +161,7 @@ static void fill_stage_args(Solver& S, StageArgs& a, Planes& qb, const Planes& q
     for (int v = 0; v < 8; ++v) a.acc_q[v] = S.acc_q[v];
     for (int v = 0; v < 11; ++v) a.acc_f[v] = S.acc_f[v];
     a.g = S.g; a.cd = S.cd; a.alpha_bot = S.alpha[S.nl - 1]; a.visc = S.visc;
-    a.botfr = S.botfr; a.has_visc = S.has_visc; a.acc_graduvb = 1; a.pf_blocks = S.pf_blocks;
+    a.botfr = S.botfr; a.has_visc = S.has_visc; a.acc_graduvb = (S.variant == 1); a.pf_blocks = S.pf_blocks;
 }
 
 static int launch_stage(Solver& S, const StageArgs& a) {
@@ -245,7 +245,7 @@ int btp_solve(Solver& S, Planes& qb, const Planes& qprime) {
         for (int v = 0; v < 8; ++v) f.acc_q[v] = S.acc_q[v];
         for (int v = 0; v < 11; ++v) f.acc_f[v] = S.acc_f[v];
         f.tr = S.trace[cur].p; f.tr_vs = S.trace[cur].stride; f.tr_rs = S.ngl;
-        f.en = S.npts; f.eq = S.nq2; f.ef = S.nq; f.derive_graduvb = 0;
+        f.en = S.npts; f.eq = S.nq2; f.ef = S.nq; f.derive_graduvb = (S.variant != 1);
         for (int v = 0; v < 12; ++v) f.ave_q[v] = S.ave_q[v];
         for (int v = 0; v < 16; ++v) f.ave_f[v] = S.ave_f[v];
         for (int v = 0; v < 7; ++v) f.ave_n[v] = S.ave_n[v];
@@ -257,7 +257,9 @@ int btp_solve(Solver& S, Planes& qb, const Planes& qprime) {
         k_btp_finalize<<<S.nelem, threads_for(S), sm, S.stream>>>(f);
         S.n_launches++;
         // halo copy of the averaged LDG gradient traces (graduvb_face_ave side 2 on processor boundaries)
-        if (S.nhalo > 0) {
+        if (S.has_visc && S.nhalo > 0 && f.derive_graduvb) {
+            if (halo_exchange_nodal(S, S.ave_n[3], 4, S.ave_n.stride, S.h_gub)) return -1;
+        } else if (S.nhalo > 0) {
             size_t hs = S.h_gub.stride;
             for (int v = 0; v < 4; ++v)
                 cudaMemcpyAsync(S.h_gub[v], S.trace[cur].p + (size_t)(3 + v) * S.trace[cur].stride + (size_t)S.nslots * S.ngl,

@@ -131,7 +131,7 @@ struct Solver {
     void* d_nbx = nullptr;
     int num_sms = 148, tma_blocks_per_sm = 0;
     int use_graph = 0;
-    int pf_blocks = 100;  // L2 prefetch distance of the fused stage kernel, in thread blocks
+    int pf_blocks = -1;   // L2 prefetch distance of the fused stage kernel, in thread blocks
     std::vector<void*> allocs;
 };
 

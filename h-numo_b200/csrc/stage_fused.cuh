@@ -179,9 +179,9 @@ __global__ void __launch_bounds__(128) k_btp_stage_fused(StageArgs a) {
     extern __shared__ double sm_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int e = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (a.pf_blocks > 0 && !a.rhs_only) {
+    if (a.pf_blocks != 0 && !a.rhs_only) {   // > 0: blocks ahead;  < 0: this block's own later-phase data
         const int wpb = blockDim.x >> 5;
-        const long e0 = ((long)blockIdx.x + a.pf_blocks) * wpb;
+        const long e0 = ((long)blockIdx.x + (a.pf_blocks > 0 ? a.pf_blocks : 0)) * wpb;
         if (e0 < a.M.nelem) stage_prefetch<G, Q>(a, (int)e0, min(wpb, a.M.nelem - (int)e0), warp, lane);
     }
     if (e >= a.M.nelem) return;
