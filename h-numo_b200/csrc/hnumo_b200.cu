@@ -161,7 +161,7 @@ static void fill_stage_args(Solver& S, StageArgs& a, Planes& qb, const Planes& q
     for (int v = 0; v < 8; ++v) a.acc_q[v] = S.acc_q[v];
     for (int v = 0; v < 11; ++v) a.acc_f[v] = S.acc_f[v];
     a.g = S.g; a.cd = S.cd; a.alpha_bot = S.alpha[S.nl - 1]; a.visc = S.visc;
-    a.botfr = S.botfr; a.has_visc = S.has_visc; a.acc_graduvb = (S.variant == 1); a.pf_blocks = S.pf_blocks;
+    a.botfr = S.botfr; a.has_visc = S.has_visc; a.acc_graduvb = (S.variant == 1 || !stage_fused_supported(S)); a.pf_blocks = S.pf_blocks;
 }
 
 static int launch_stage(Solver& S, const StageArgs& a) {
@@ -200,7 +200,7 @@ int rhs_btp_only(Solver& S, Planes& qb, const Planes& qprime, double* d_rhs_out)
 static int btp_solve_rec(Solver& S, Planes& qb, const Planes& qprime);
 // ti_barotropic_ssprk_mlswe (mod_rk_mlswe.F90:19-151)
 int btp_solve(Solver& S, Planes& qb, const Planes& qprime) {
-    if ((S.variant == 0 || S.variant == 3) && stage_tma_supported(S)) return btp_solve_rec(S, qb, qprime);
+    if ((S.variant == 2 || S.variant == 3) && stage_tma_supported(S)) return btp_solve_rec(S, qb, qprime);
     cudaMemsetAsync(S.acc_n.p, 0, S.acc_n.stride * S.acc_n.n * sizeof(double), S.stream);
     cudaMemsetAsync(S.acc_q.p, 0, S.acc_q.stride * S.acc_q.n * sizeof(double), S.stream);
     cudaMemsetAsync(S.acc_f.p, 0, S.acc_f.stride * S.acc_f.n * sizeof(double), S.stream);
@@ -245,7 +245,7 @@ int btp_solve(Solver& S, Planes& qb, const Planes& qprime) {
         for (int v = 0; v < 8; ++v) f.acc_q[v] = S.acc_q[v];
         for (int v = 0; v < 11; ++v) f.acc_f[v] = S.acc_f[v];
         f.tr = S.trace[cur].p; f.tr_vs = S.trace[cur].stride; f.tr_rs = S.ngl;
-        f.en = S.npts; f.eq = S.nq2; f.ef = S.nq; f.derive_graduvb = (S.variant != 1);
+        f.en = S.npts; f.eq = S.nq2; f.ef = S.nq; f.derive_graduvb = !(S.variant == 1 || !stage_fused_supported(S));
         for (int v = 0; v < 12; ++v) f.ave_q[v] = S.ave_q[v];
         for (int v = 0; v < 16; ++v) f.ave_f[v] = S.ave_f[v];
         for (int v = 0; v < 7; ++v) f.ave_n[v] = S.ave_n[v];

@@ -26,19 +26,18 @@ struct FusedLayout {
     static constexpr int X_RHS = 0;                       // 6*NP   rhsP[3], rhsR[3]
     static constexpr int X_OWN = 6 * NP;                  // 4*8*G  own traces   [s][v][n], v: 0 dpp 1 mx 2 my 3..6 G 7 pb
     static constexpr int X_NBT = X_OWN + 32 * G;          // 4*8*G  neighbour traces
-    static constexpr int X_OWNV = X_NBT + 32 * G;         // 4*5*G  own viscosity statics
-    static constexpr int X_NBV = X_OWNV + 20 * G;         // 4*5*G  neighbour viscosity statics
+    static constexpr int X_NBV = X_NBT + 32 * G;          // 4*5*G  neighbour viscosity statics (own ones are re-read from L1)
     static constexpr int X_LF = X_NBV + 20 * G;           // 4*2*G  LDG face flux
     static constexpr int X_SZ = cmax(8 * NQ2, X_LF + 8 * G);
     // T: pass-1 intermediates, later face quadrature data
     static constexpr int T = X + X_SZ;
     static constexpr int T_FQV = 0;                       // 4*2*4*Q interpolated traces [s][side][var][iq]
     static constexpr int T_FF = 32 * Q;                   // 4*3*Q   face fluxes
-    static constexpr int T_PROJ = T_FF + 12 * Q;          // 4*3*G   projected face fluxes
-    static constexpr int T_SZ = cmax(8 * PER, T_PROJ + 12 * G);
-    // L: LDG work: 0..3 dxi(u),dxi(v),det(u),det(v) | 4..7 G | 8..11 Zxi(2),Zeta(2) | 12..15 lapX(2),lapE(2)
+    static constexpr int T_PROJ = T_FQV;                  // 4*3*G   projected face fluxes (the interpolated traces are dead by then)
+    static constexpr int T_SZ = cmax(8 * PER, T_FF + 12 * Q);
+    // L: LDG work: 0..3 dxi(u),dxi(v),det(u),det(v), later lapX(2),lapE(2) | 4..7 G | 8..11 Zxi(2),Zeta(2)
     static constexpr int L = T + T_SZ;
-    static constexpr int L_SZ = 16 * NP;
+    static constexpr int L_SZ = 12 * NP;
     static constexpr int TOTAL = L + L_SZ;
 };
 
@@ -124,11 +123,12 @@ __device__ __forceinline__ void pf_chunk(const double* base, size_t first, int n
 // Software prefetch into L2 of everything the block `pf_blocks` launches ahead will read (the kernel is otherwise
 // bound by the latency of its ~14 dependent DRAM round trips per element, see profiles/r1_fused_kernel_summary.md).
 template <int G, int Q>
-__device__ __forceinline__ void stage_prefetch(const StageArgs& a, int e0, int ne, int warp, int lane) {
+__device__ __forceinline__ void stage_prefetch(const StageArgs& a, int e0, int ne, int warp, int nwarps, int lane) {
     constexpr int NP = G * G, NQ2 = Q * Q;
     const size_t n0 = (size_t)e0 * NP, q0 = (size_t)e0 * NQ2, s0 = (size_t)e0 * 4 * Q, t0 = (size_t)e0 * 4 * G;
     const int nn = ne * NP, nq = ne * NQ2, ns = ne * 4 * Q, nt = ne * 4 * G;
-    if (warp == 0) {
+    for (int set = warp; set < 4; set += nwarps) {
+    if (set == 0) {
 #pragma unroll
         for (int v = 0; v < 3; ++v) pf_chunk(a.qb[v], n0, nn, lane);
         pf_chunk(a.pbprime_df, n0, nn, lane); pf_chunk(a.oop_df, n0, nn, lane); pf_chunk(a.massinv, n0, nn, lane);
@@ -152,11 +152,11 @@ __device__ __forceinline__ void stage_prefetch(const StageArgs& a, int e0, int n
 #pragma unroll
             for (int v = 0; v < 3; ++v) pf_chunk(a.qb2[v], n0, nn, lane);
         }
-    } else if (warp == 1) {
+    } else if (set == 1) {
         pf_chunk(a.coriolis_q, q0, nq, lane); pf_chunk(a.tauwx_q, q0, nq, lane); pf_chunk(a.tauwy_q, q0, nq, lane);
         pf_chunk(a.gzx_q, q0, nq, lane); pf_chunk(a.gzy_q, q0, nq, lane); pf_chunk(a.oop_q, q0, nq, lane);
         pf_chunk(a.Hbcl, q0, nq, lane); pf_chunk(a.Quu, q0, nq, lane); pf_chunk(a.Quv, q0, nq, lane); pf_chunk(a.Qvv, q0, nq, lane);
-    } else if (warp == 2) {
+    } else if (set == 2) {
 #pragma unroll
         for (int v = 0; v < 6; ++v) pf_chunk(a.acc_q[v], q0, nq, lane);
         if (a.botfr == 2) { pf_chunk(a.acc_q[6], q0, nq, lane); pf_chunk(a.acc_q[7], q0, nq, lane); }
@@ -170,10 +170,11 @@ __device__ __forceinline__ void stage_prefetch(const StageArgs& a, int e0, int n
 #pragma unroll
         for (int v = 0; v < 11; ++v) pf_chunk(a.acc_f[v], s0, ns, lane);
     }
+    }
 }
 
 template <int G, int Q>
-__global__ void __launch_bounds__(128) k_btp_stage_fused(StageArgs a) {
+__global__ void __maxnreg__(112) k_btp_stage_fused(StageArgs a) {
     using LAY = FusedLayout<G, Q>;
     constexpr int NP = LAY::NP, NQ2 = LAY::NQ2, PER = LAY::PER;
     extern __shared__ double sm_all[];
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(128) k_btp_stage_fused(StageArgs a) {
     if (a.pf_blocks != 0 && !a.rhs_only) {   // > 0: blocks ahead;  < 0: this block's own later-phase data
         const int wpb = blockDim.x >> 5;
         const long e0 = ((long)blockIdx.x + (a.pf_blocks > 0 ? a.pf_blocks : 0)) * wpb;
-        if (e0 < a.M.nelem) stage_prefetch<G, Q>(a, (int)e0, min(wpb, a.M.nelem - (int)e0), warp, lane);
+        if (e0 < a.M.nelem) stage_prefetch<G, Q>(a, (int)e0, min(wpb, a.M.nelem - (int)e0), warp, wpb, lane);
     }
     if (e >= a.M.nelem) return;
     double* sm = sm_all + (size_t)warp * LAY::TOTAL;
@@ -366,19 +367,19 @@ __global__ void __launch_bounds__(128) k_btp_stage_fused(StageArgs a) {
                 for (int n = 0; n < G; ++n) in[n] = Lr[(8 + c) * NP + l * G + n];
                 line_gradT<G>(in, out);
 #pragma unroll
-                for (int n = 0; n < G; ++n) Lr[(12 + c) * NP + l * G + n] = out[n];
+                for (int n = 0; n < G; ++n) Lr[(0 + c) * NP + l * G + n] = out[n];
             } else {
 #pragma unroll
                 for (int m = 0; m < G; ++m) in[m] = Lr[(10 + c) * NP + m * G + l];
                 line_gradT<G>(in, out);
 #pragma unroll
-                for (int m = 0; m < G; ++m) Lr[(14 + c) * NP + m * G + l] = out[m];
+                for (int m = 0; m < G; ++m) Lr[(2 + c) * NP + m * G + l] = out[m];
             }
         }
     }
     // ---- 7a. face traces: own and neighbour (btp_extract_df), LDG gradient traces, viscosity statics
     {
-        double* own = X + LAY::X_OWN; double* nbt = X + LAY::X_NBT; double* ownv = X + LAY::X_OWNV; double* nbv = X + LAY::X_NBV;
+        double* own = X + LAY::X_OWN; double* nbt = X + LAY::X_NBT; double* nbv = X + LAY::X_NBV;
         for (int it = lane; it < 4 * G; it += 32) {
             int s = it / G, n = it - s * G;
             int slot = e * 4 + s, nb = a.M.nbr[slot], nbs = a.M.nbslot[slot];
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(128) k_btp_stage_fused(StageArgs a) {
 #pragma unroll
                 for (int v = 0; v < 4; ++v) { po[(3 + v) * G] = go[v]; pn[(3 + v) * G] = gn[v]; }
 #pragma unroll
-                for (int v = 0; v < 5; ++v) { ownv[(s * 5 + v) * G + n] = so[v]; nbv[(s * 5 + v) * G + n] = sn[v]; }
+                for (int v = 0; v < 5; ++v) nbv[(s * 5 + v) * G + n] = sn[v];
             }
         }
     }
@@ -497,20 +498,23 @@ __global__ void __launch_bounds__(128) k_btp_stage_fused(StageArgs a) {
         }
         // ---- 7e. LDG face flux at the face nodes, as written (mod_laplacian_quad.F90:427-519)
         if (visc) {
-            const double* own = X + LAY::X_OWN; const double* nbt = X + LAY::X_NBT; const double* ownv = X + LAY::X_OWNV; const double* nbv = X + LAY::X_NBV;
+            const double* own = X + LAY::X_OWN; const double* nbt = X + LAY::X_NBT; const double* nbv = X + LAY::X_NBV;
             double* lf = X + LAY::X_LF;
             for (int it = lane; it < 4 * G; it += 32) {
                 int s = it / G, n = it - s * G;
                 int slot = e * 4 + s, nb = a.M.nbr[slot];
                 bool left = (nb < 0) || (e < nb);
                 double nx = a.M.fgeom[slot * 3 + 0], ny = a.M.fgeom[slot * 3 + 1], nlen = a.M.fgeom[slot * 3 + 2];
-                const double* gl = (left ? own : nbt) + (s * 8 + 3) * G + n;
-                const double* gr = (left ? nbt : own) + (s * 8 + 3) * G + n;
-                const double* sl = (left ? ownv : nbv) + s * 5 * G + n;
-                const double* sr = (left ? nbv : ownv) + s * 5 * G + n;
-                double fl[4], fr[4];
+                const double* go = own + (s * 8 + 3) * G + n;
+                const double* gn = nbt + (s * 8 + 3) * G + n;
+                const double* sn = nbv + s * 5 * G + n;
+                const int I = face_node(s, n, G);
+                const double pvo = a.pbv[nbase + I];
+                double fo_[4], fn_[4];
 #pragma unroll
-                for (int v = 0; v < 4; ++v) { fl[v] = sl[4 * G] * gl[v * G] + sl[v * G]; fr[v] = sr[4 * G] * gr[v * G] + sr[v * G]; }
+                for (int v = 0; v < 4; ++v) { fo_[v] = pvo * go[v * G] + a.bdg[v][nbase + I]; fn_[v] = sn[4 * G] * gn[v * G] + sn[v * G]; }
+                const double* fl = left ? fo_ : fn_;
+                const double* fr = left ? fn_ : fo_;
                 double qu0 = 0.5 * fl[0] + 0.5 * fr[0], qu1 = 0.5 * fl[1] + 0.5 * fr[1];
                 double qv0 = 0.5 * fl[2] + 0.5 * fr[2], qv1 = 0.5 * fl[3] + 0.5 * fr[3];
                 double wq = c_ops.wg[n] * nlen;
@@ -546,7 +550,7 @@ __global__ void __launch_bounds__(128) k_btp_stage_fused(StageArgs a) {
             int m = I / G, n = I - m * G;
             double r0 = R[0 * NP + I] + R[3 * NP + I], r1 = R[1 * NP + I] + R[4 * NP + I], r2 = R[2 * NP + I] + R[5 * NP + I];
             double l0 = 0.0, l1 = 0.0;
-            if (visc) { l0 = -(Lr[12 * NP + I] + Lr[14 * NP + I]); l1 = -(Lr[13 * NP + I] + Lr[15 * NP + I]); }
+            if (visc) { l0 = -(Lr[0 * NP + I] + Lr[2 * NP + I]); l1 = -(Lr[1 * NP + I] + Lr[3 * NP + I]); }
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 bool on = (s == 0) ? (m == 0) : (s == 1) ? (m == G - 1) : (s == 2) ? (n == 0) : (n == G - 1);
@@ -626,7 +630,7 @@ inline bool stage_fused_supported(const Solver& S) { return (S.ngl == 5 && S.nq 
 template <int G, int Q>
 static int launch_fused_t(Solver& S, const StageArgs& a) {
     using LAY = FusedLayout<G, Q>;
-    const int warps = 4;
+    const int warps = 3;   // 6 blocks of 3 warps per SM (shared memory bound)
     size_t smem = (size_t)warps * LAY::TOTAL * sizeof(double);
     static bool configured = false;
     if (!configured) {

@@ -87,7 +87,8 @@ typedef struct hnumo_desc {
     const int32_t* nbh_send_recv;
     /* 0 = use the current CUDA device */
     int32_t device;
-    /* tuning: 0 = default fused stage kernel, 1 = simple reference-form kernel (bisecting aid) */
+    /* tuning: 0 = default (warp-per-element fused stage kernel), 1 = simple reference-form kernel (bisecting aid),
+     * 2 = record layout + TMA staging, one output per thread, 3 = record layout + TMA staging, one line per lane */
     int32_t stage_kernel_variant;
 } hnumo_desc_t;
 

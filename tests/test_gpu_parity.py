@@ -24,7 +24,7 @@ DECKS = {
     "noslip_rk3": lambda: dict(hn.decks.SHIPPED["double_gyre"], nelx=6, nely=5, x_boundary=(2, 2), kstages=3, botfr=2, cd_mlswe=1e-3),
     "nop3_5layers": lambda: dict(hn.decks.synthetic_double_gyre(5, 5, nop=3, nlayers=5)),
 }
-VARIANTS = [0, 1, 2, 3]  # 0: record kernel (output per thread), 1: simple reference-form kernel, 2: warp-per-element fused kernel, 3: record kernel (line per lane)
+VARIANTS = [0, 1, 2, 3]  # 0: warp-per-element fused kernel (default), 1: simple reference-form kernel, 2/3: record-layout TMA kernels
 
 
 def natural_errors(S, O, deck):
