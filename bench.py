@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--nely", type=int, default=1000)
     ap.add_argument("--nop", type=int, default=4)
     ap.add_argument("--layers", type=int, default=3)
-    ap.add_argument("--variant", type=int, default=0, help="0 = fused stage kernel (default), 1 = simple kernel, 2/3 = record-layout TMA kernels")
+    ap.add_argument("--variant", type=int, default=0, help="0 = fused stage kernel, 1 = simple kernel, 2/3 = record-layout TMA kernels, 4 = element-pair kernel")
     ap.add_argument("--cpu-sample", type=int, default=128, help="edge (elements) of the CPU baseline sample brick")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

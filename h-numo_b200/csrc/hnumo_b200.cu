@@ -9,6 +9,7 @@
 #include "stage_fused.cuh"
 #include "stage_tma.cuh"
 #include "stage_rec.cuh"
+#include "stage_pair.cuh"
 
 namespace hn {
 
@@ -198,9 +199,11 @@ int rhs_btp_only(Solver& S, Planes& qb, const Planes& qprime, double* d_rhs_out)
 }
 
 static int btp_solve_rec(Solver& S, Planes& qb, const Planes& qprime);
+static int btp_solve_pair(Solver& S, Planes& qb, const Planes& qprime);
 // ti_barotropic_ssprk_mlswe (mod_rk_mlswe.F90:19-151)
 int btp_solve(Solver& S, Planes& qb, const Planes& qprime) {
-    if ((S.variant == 2 || S.variant == 3) && stage_tma_supported(S)) return btp_solve_rec(S, qb, qprime);
+    if (S.variant == 4 && S.p_rec) return btp_solve_pair(S, qb, qprime);
+    if ((S.variant == 2 || S.variant == 3) && S.r_geoc) return btp_solve_rec(S, qb, qprime);
     cudaMemsetAsync(S.acc_n.p, 0, S.acc_n.stride * S.acc_n.n * sizeof(double), S.stream);
     cudaMemsetAsync(S.acc_q.p, 0, S.acc_q.stride * S.acc_q.n * sizeof(double), S.stream);
     cudaMemsetAsync(S.acc_f.p, 0, S.acc_f.stride * S.acc_f.n * sizeof(double), S.stream);
@@ -361,6 +364,86 @@ static int btp_solve_rec(Solver& S, Planes& qb, const Planes& qprime) {
     k_btp_finalize<<<S.nelem, threads_for(S), sm, S.stream>>>(f);
     S.n_launches++;
     // graduvb_face_ave side 2 on processor boundaries = the neighbour's averaged gradient at the face nodes
+    if (S.has_visc && S.nhalo > 0)
+        if (halo_exchange_nodal(S, S.ave_n[3], 4, S.ave_n.stride, S.h_gub)) return -1;
+    HN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ti_barotropic_ssprk_mlswe (mod_rk_mlswe.F90:19-151) on per-element records with the element-pair stage kernel
+static int btp_solve_pair(Solver& S, Planes& qb, const Planes& qprime) {
+    const PairDims D = make_pairdims(S.ngl, S.nq);
+    const size_t NE = (size_t)S.nelem;
+    cudaMemsetAsync(S.p_accf, 0, NE * 4 * D.ASIDE * sizeof(double), S.stream);
+    int cur = 0;
+    {
+        PairPackArgs p; memset(&p, 0, sizeof(p));
+        p.M = S.mesh; p.D = D;
+        for (int v = 0; v < 3; ++v) p.qb[v] = qb[v];
+        const int bl = S.nl - 1;
+        const double* nstp[11] = {S.pbprime_df, S.oop_df, S.massinv, qprime[0 * S.nl + bl], qprime[1 * S.nl + bl], qprime[2 * S.nl + bl],
+                                  S.pbprime_visc, S.btp_dpp_graduv[0], S.btp_dpp_graduv[1], S.btp_dpp_graduv[2], S.btp_dpp_graduv[3]};
+        for (int v = 0; v < 11; ++v) p.nstp[v] = nstp[v];
+        const double* qstp[10] = {S.oop_q, S.Hbcl, S.Quu, S.Quv, S.Qvv, S.coriolis_q, S.tauw_q, S.tauw_q + S.npoin_q, S.gradzb_q, S.gradzb_q + S.npoin_q};
+        for (int v = 0; v < 10; ++v) p.qstp[v] = qstp[v];
+        const double* fstp[11] = {S.cL, S.cR, S.cLR, S.lam, S.oop_edge, S.Quu_e, S.Quv_e, S.Qvv_e, S.Hbcl_e, S.pbl, S.pbr};
+        for (int v = 0; v < 11; ++v) p.fstp[v] = fstp[v];
+        for (int v = 0; v < 4; ++v) p.bdg[v] = S.btp_dpp_graduv[v];
+        p.pbv = S.pbprime_visc; p.pbn = S.pbn; p.hstat = S.h_stat.p; p.hstat_stride = S.h_stat.stride;
+        p.rec = S.p_rec; p.tr = S.p_tr[cur];
+        p.has_visc = S.has_visc;
+        k_pair_pack<<<S.nelem, 128, 2 * S.npts * sizeof(double), S.stream>>>(p);
+        S.n_launches++;
+        if (halo_exchange_trace_records(S, S.p_tr[cur], D.TSIDE)) return -1;
+    }
+    cudaEvent_t e_start, e_stop;
+    take_event_pair(S, 0, e_start, e_stop);
+    cudaEventRecord(e_start, S.stream);
+    PairArgs a; memset(&a, 0, sizeof(a));
+    a.nelem = S.nelem; a.nslots = S.nslots;
+    a.rec = S.p_rec; a.accf = S.p_accf;
+    a.g = S.g; a.cd_g = S.cd / S.g; a.cd_alpha = S.cd / S.alpha[S.nl - 1]; a.visc = S.visc; a.botfr = S.botfr;
+    a.prefetch = S.pair_prefetch; a.pf_dist = S.pair_pf_dist;
+    for (int mstep = 1; mstep <= S.N_btp; ++mstep) {
+        for (int ik = 1; ik <= S.kstages; ++ik) {
+            a.a1 = S.ssprk_a[ik - 1][0]; a.a2 = S.ssprk_a[ik - 1][1]; a.a3 = S.ssprk_a[ik - 1][2];
+            a.dtt = S.dt_btp * S.ssprk_beta[ik - 1];
+            a.load_q0 = (ik > 1 && a.a1 != 0.0);
+            a.load_q2 = (a.a3 != 0.0);
+            a.store_q0 = (ik == 1 && S.kstages > 1);
+            a.store_q2 = (S.kstages == 5 && ik == 2);
+            a.tr_in = S.p_tr[cur]; a.tr_out = S.p_tr[cur ^ 1];
+            if (launch_stage_pair(S, a)) return -1;
+            cur ^= 1;
+            if (halo_exchange_trace_records(S, S.p_tr[cur], D.TSIDE)) return -1;
+        }
+    }
+    cudaEventRecord(e_stop, S.stream);
+    S.n_stages += (long)S.N_btp * S.kstages;
+    // state back to planes, time averages
+    k_pair_unpack_qb<<<nblk(S.npoin), 256, 0, S.stream>>>(S.nelem, D, S.p_rec, qb[0], qb[1], qb[2]);
+    k_pair_sum_traces<<<nblk((size_t)S.nslots * S.ngl), 256, 0, S.stream>>>(S.nelem, D, S.p_rec, S.p_tr[cur]);
+    S.n_launches += 2;
+    if (halo_exchange_trace_records(S, S.p_tr[cur], D.TSIDE)) return -1;
+    FinalizeArgs f; memset(&f, 0, sizeof(f));
+    f.M = S.mesh;
+    for (int v = 0; v < 6; ++v) f.acc_n[v] = S.p_rec + D.O_ACCN + (size_t)v * D.NP;
+    for (int v = 6; v < 10; ++v) f.acc_n[v] = nullptr;
+    for (int v = 0; v < 6; ++v) f.acc_q[v] = S.p_rec + D.O_ACCQ + (size_t)v * D.NQ2;
+    for (int v = 6; v < 8; ++v) f.acc_q[v] = S.p_rec + D.O_ACCQR + (size_t)(v - 6) * D.NQ2;
+    for (int v = 0; v < 11; ++v) f.acc_f[v] = S.p_accf + (size_t)v * D.Q;
+    f.en = D.REC; f.eq = D.REC; f.ef = D.ASIDE; f.derive_graduvb = 1;
+    f.tr = S.p_tr[cur]; f.tr_vs = D.G; f.tr_rs = D.TSIDE;
+    for (int v = 0; v < 12; ++v) f.ave_q[v] = S.ave_q[v];
+    for (int v = 0; v < 16; ++v) f.ave_f[v] = S.ave_f[v];
+    for (int v = 0; v < 7; ++v) f.ave_n[v] = S.ave_n[v];
+    f.oop_q = S.oop_q; f.Hbcl = S.Hbcl; f.Hbcl_e = S.Hbcl_e; f.cL = S.cL; f.cR = S.cR; f.lam = S.lam; f.pbl = S.pbl; f.pbr = S.pbr;
+    f.qp_dp = qprime[0 * S.nl + S.nl - 1]; f.qp_u = qprime[1 * S.nl + S.nl - 1]; f.qp_v = qprime[2 * S.nl + S.nl - 1];
+    f.S = (double)(S.kstages * S.N_btp); f.N_inv = 1.0 / (double)(S.kstages * S.N_btp); f.cd_over_g = S.cd / S.g;
+    f.botfr = S.botfr;
+    size_t sm = (sops_doubles_host(S.ngl, S.nq) + 8 * S.npts + 6 * S.ngl * S.nq) * sizeof(double);
+    k_btp_finalize<<<S.nelem, threads_for(S), sm, S.stream>>>(f);
+    S.n_launches++;
     if (S.has_visc && S.nhalo > 0)
         if (halo_exchange_nodal(S, S.ave_n[3], 4, S.ave_n.stride, S.h_gub)) return -1;
     HN_CUDA(cudaGetLastError());
@@ -669,7 +752,16 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, S.device) == cudaSuccess) S.num_sms = prop.multiProcessorCount;
     }
-    if (stage_tma_supported(S)) {
+    if (const char* ev = getenv("HNUMO_PAIR_NE")) S.pair_ne = atoi(ev);          // tuning overrides (tests, sweeps)
+    if (const char* ev = getenv("HNUMO_PAIR_WARPS")) S.pair_warps = atoi(ev);
+    if (const char* ev = getenv("HNUMO_PAIR_PREFETCH")) S.pair_prefetch = atoi(ev);
+    if (S.variant == 4 && stage_pair_supported(S)) {
+        const PairDims D = make_pairdims(S.ngl, S.nq);
+        const size_t NE = (size_t)S.nelem;
+        S.p_rec = dalloc(S, NE * D.REC); S.p_accf = dalloc(S, NE * 4 * D.ASIDE);
+        S.p_tr[0] = dalloc(S, (size_t)(S.nslots + S.nhalo) * D.TSIDE); S.p_tr[1] = dalloc(S, (size_t)(S.nslots + S.nhalo) * D.TSIDE);
+    }
+    if ((S.variant == 2 || S.variant == 3) && stage_tma_supported(S)) {
         const RecDims D = make_recdims(S.ngl, S.nq);
         const size_t NE = (size_t)S.nelem;
         S.r_geoc = dalloc(S, NE * D.GEOC); S.r_qb = dalloc(S, NE * D.QB); S.r_q0 = dalloc(S, NE * D.QB); S.r_q2 = dalloc(S, NE * D.QB);
@@ -893,6 +985,10 @@ int hnumo_set_option(hnumo_handle_t h, const char* key, double value) {
     if (!strcmp(key, "use_graph")) { S.use_graph = (int)value; return 0; }
     if (!strcmp(key, "prefetch_blocks")) { S.pf_blocks = (int)value; return 0; }
     if (!strcmp(key, "tma_blocks_per_sm")) { S.tma_blocks_per_sm = (int)value; return 0; }
+    if (!strcmp(key, "pair_ne")) { S.pair_ne = (int)value; return 0; }
+    if (!strcmp(key, "pair_warps")) { S.pair_warps = (int)value; return 0; }
+    if (!strcmp(key, "pair_prefetch")) { S.pair_prefetch = (int)value; return 0; }
+    if (!strcmp(key, "pair_pf_dist")) { S.pair_pf_dist = (int)value; return 0; }
     set_error("hnumo_set_option", "unknown key");
     return -2;
 }

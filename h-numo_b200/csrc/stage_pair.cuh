@@ -1,0 +1,903 @@
+// stage_pair.cuh -- barotropic SSPRK stage kernel, "element pair per warp" (default variant).
+//
+// Same operator as k_btp_stage_simple / k_btp_stage_fused (reference src/mod_rhs_btp.F90:28-370,
+// src/mod_barotropic_terms.F90:25-97,165-217, src/mod_laplacian_quad.F90:32-121,357-519, src/mod_rk_mlswe.F90:87-114).
+//
+// Why this shape (profiles/r1_fused_kernel_summary.md): the warp-per-element kernel issues 4 360 warp instructions per
+// element of which only 27 % are FP64 math; 46 % are integer/address/control work and the issue slots are 43 % busy at
+// 0.41 of the HBM roofline -- the kernel is bound by instruction issue (and by board power), not by DRAM.  Here
+//   * one warp advances NE = 2 elements at once: every shared-memory word is a double2 {element A, element B}
+//     (LDS.128 / STS.128), every lane works on the same line / point of both elements, so loop control, index
+//     arithmetic, the uniform-register loads of the operator entries (LDCU) and the shared-memory traffic are paid
+//     once per pair, and each lane carries two independent dependency chains;
+//   * everything an element needs for a stage lives in ONE contiguous record (state, statics, accumulators, face
+//     coefficients): one base pointer per element, compile-time offsets, no per-plane address arithmetic; the record
+//     is pulled into L2 by a single bulk prefetch instruction (cp.async.bulk.prefetch.L2) when the warp starts;
+//   * only 9 warps are resident per SM (shared memory), so each thread may use 224 registers: the global loads of a
+//     phase are issued one phase ahead and held in registers, which hides the L2 latency behind FP64 work;
+//   * the LDG face flux is evaluated by the lane that gathers the traces (no staging of gradient traces), and the two
+//     scatter passes are one iteration each (27 and 15 lanes) with the psiq/dpsiq parts chained in registers.
+// The kernel is bandwidth bound by design (1.3 flop/B); tensor cores do not apply (FP64, 5x9 operators).
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+
+#include "btp_kernels.cuh"
+
+namespace hn {
+
+__host__ __device__ constexpr int pr_pad2(int n) { return (n + 1) & ~1; }
+
+// forcing-sparsity flags of an element (header word 22): a zero field is not read
+enum { PF_GZ = 1, PF_TWX = 2, PF_TWY = 4, PF_COR = 8 };
+
+template <int G, int Q>
+struct PairRec {
+    static constexpr int NP = G * G, NQ2 = Q * Q, PER = G * Q;
+    // header (doubles): 0 ksx 1 ksy 2 etx 3 ety 4 J 5 - | 6..17 fgeom[4][3] | 18,19 int nbr[4] | 20,21 int trec[4] |
+    //                   22 int flags, int - | 23 -
+    static constexpr int HDR = 24;
+    static constexpr int QBSZ = pr_pad2(3 * NP);
+    static constexpr int O_QB = HDR;
+    // nodal statics: 0 pbprime 1 1/pbprime 2 massinv 3 qp_dp 4 qp_u 5 qp_v 6 pbprime_visc 7..10 btp_dpp_graduv
+    static constexpr int NST_NF = 11;
+    static constexpr int O_NST = O_QB + QBSZ;
+    static constexpr int O_ACCN = O_NST + pr_pad2(NST_NF * NP);   // 0 ope2_df 1 ub 2 vb 3 S_pbpert 4 S_mx 5 S_my
+    // quadrature statics: 0 1/pbprime 1 H_bcl 2 Quu 3 Quv 4 Qvv 5 coriolis 6 tau_x 7 tau_y 8 dzb/dx 9 dzb/dy
+    // (7 tau_y, 8 dzb/dx, 9 dzb/dy live in the rarely-read tail of the record)
+    static constexpr int QST_NF = 7, QST_RARE = 3;
+    static constexpr int O_QST = O_ACCN + pr_pad2(6 * NP);
+    static constexpr int O_ACCQ = O_QST + pr_pad2(QST_NF * NQ2);  // 0 Qu 1 Qv 2 Quv 3 ope2 4 ub 5 vb (tail: 6,7 tau_bot, botfr==2)
+    // face statics per side: cL cR cLR lam oop_edge Quu_e Quv_e Qvv_e Hbcl_e 1/pbl 1/pbr (copy of the owner's values)
+    static constexpr int FSIDE = pr_pad2(11 * Q);
+    static constexpr int O_FST = O_ACCQ + pr_pad2(6 * NQ2);
+    // neighbour's viscosity statics at the face nodes (ghosts resolved): bdg0..3, pbv, and the neighbour's pbprime
+    static constexpr int VSIDE = pr_pad2(6 * G);
+    static constexpr int O_VST = O_FST + 4 * FSIDE;
+    static constexpr int O_Q0 = O_VST + 4 * VSIDE, O_Q2 = O_Q0 + QBSZ;         // SSPRK work states
+    static constexpr int O_QSTR = O_Q2 + QBSZ;                                   // rare quadrature statics 7..9
+    static constexpr int O_ACCQR = O_QSTR + pr_pad2(QST_RARE * NQ2);             // rare quadrature sums 6,7
+    static constexpr int REC = O_ACCQR + pr_pad2(2 * NQ2);
+    static constexpr int ASIDE = pr_pad2(11 * Q);   // face sums, separate array [slot][ASIDE]
+    static constexpr int TSIDE = pr_pad2(7 * G);    // trace record [slot][7][G]: pbpert mx my G0..G3
+    // shared memory per warp, in units of NE doubles
+    static constexpr int S_NOD = 0;                 // 0 dpp 1 mx 2 my 3 pb 4 pp 5 up 6 vp 7 u 8 v ; later 4..7 = LDG flux variable
+    static constexpr int S_X = S_NOD + 9 * NP;      // 8 quadrature-point arrays; later rhs, face traces, face fluxes
+    static constexpr int X_RHS = 0, X_FL = 3 * NP, X_FR = X_FL + 16 * G, X_LF = X_FR + 16 * G, X_FF = X_LF + 8 * G;
+    static constexpr int S_T = S_X + 8 * NQ2;       // pass-1 results; later interpolated traces, projected face fluxes
+    static constexpr int T_SZ = 8 * PER;
+    static constexpr int S_L = S_T + T_SZ;          // LDG: 0..3 gradient lines / laplacian lines, 4..7 G, 8..11 Z
+    static constexpr int S_TOTAL = S_L + 12 * NP;
+    static_assert(X_FF + 12 * Q <= 8 * NQ2, "face work does not fit in X");
+    static_assert(32 * Q <= T_SZ && 7 * PER <= T_SZ, "T too small");
+    static size_t smem_bytes(int ne, int warps) { return (size_t)warps * ((size_t)S_TOTAL * ne + (size_t)HDR * ne) * sizeof(double); }
+};
+
+struct PairArgs {
+    int nelem, nslots;
+    double* rec;
+    double* accf;
+    const double* tr_in;
+    double* tr_out;
+    double a1, a2, a3, dtt, g, cd_g, cd_alpha, visc;   // cd_g = cd/g (botfr 1), cd_alpha = cd/alpha_bottom (botfr 2)
+    int botfr, load_q0, load_q2, store_q0, store_q2;
+    int prefetch, pf_dist;   // bit 0: own record tail -> L2 at start; bit 1: head of the record pf_dist units ahead
+};
+
+// shared-memory vector of NE doubles
+template <int NE> struct PV;
+template <> struct PV<1> {
+    typedef double T;
+    static __device__ __forceinline__ void ld(const T* p, double (&o)[1]) { o[0] = *p; }
+    static __device__ __forceinline__ void st(T* p, const double (&i)[1]) { *p = i[0]; }
+};
+template <> struct PV<2> {
+    typedef double2 T;
+    static __device__ __forceinline__ void ld(const T* p, double (&o)[2]) { double2 t = *p; o[0] = t.x; o[1] = t.y; }
+    static __device__ __forceinline__ void st(T* p, const double (&i)[2]) { *p = make_double2(i[0], i[1]); }
+};
+
+#define PR_FORC _Pragma("unroll") for (int c = 0; c < NE; ++c)
+
+// reciprocal: hardware seed + two Newton steps (<= 1 ulp); the IEEE division sequence costs ~20 issue slots and a
+// slow-path branch per use, and there are 14 of them per element and stage
+__device__ __forceinline__ double pr_rcp(double a) {
+#ifdef HN_EXACT_DIV
+    return 1.0 / a;
+#else
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    double e = fma(-a, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-a, x, 1.0);
+    x = fma(x, e, x);
+    return x;
+#endif
+}
+
+__device__ __forceinline__ void pr_prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// ---- line contractions on NE elements at once; the operator entry is a uniform-register operand shared by the NE FMAs
+// out[i] = sum_n M(n,i) in[n], nodes -> quadrature points
+template <int NE, int G, int Q, bool DERIV, int SS, int DS>
+__device__ __forceinline__ void pl_n2q(const typename PV<NE>::T* src, typename PV<NE>::T* dst) {
+    double in[G][NE];
+#pragma unroll
+    for (int n = 0; n < G; ++n) PV<NE>::ld(src + n * SS, in[n]);
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        double s[NE];
+        PR_FORC s[c] = 0.0;
+#pragma unroll
+        for (int n = 0; n < G; ++n) {
+            const double mv = DERIV ? c_ops.B[n + G * i] : c_ops.A[n + G * i];
+            PR_FORC s[c] = fma(mv, in[n][c], s[c]);
+        }
+        PV<NE>::st(dst + i * DS, s);
+    }
+}
+// acc[n] (+)= sum_i M(n,i) in[i], quadrature points -> nodes (weak-form transpose)
+template <int NE, int G, int Q, bool DERIV, int SS>
+__device__ __forceinline__ void pl_q2n_acc(const typename PV<NE>::T* src, double (&acc)[G][NE]) {
+    double in[Q][NE];
+#pragma unroll
+    for (int i = 0; i < Q; ++i) PV<NE>::ld(src + i * SS, in[i]);
+#pragma unroll
+    for (int n = 0; n < G; ++n) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            const double mv = DERIV ? c_ops.B[n + G * i] : c_ops.A[n + G * i];
+            PR_FORC acc[n][c] = fma(mv, in[i][c], acc[n][c]);
+        }
+    }
+}
+// collocation derivative along a nodal line (runtime stride): out[n] = sum_k D(k,n) in[k]  or transposed D(n,k)
+template <int NE, int G, bool TRANSP>
+__device__ __forceinline__ void pl_grad(const typename PV<NE>::T* src, typename PV<NE>::T* dst, int stride) {
+    double in[G][NE];
+#pragma unroll
+    for (int k = 0; k < G; ++k) PV<NE>::ld(src + k * stride, in[k]);
+#pragma unroll
+    for (int n = 0; n < G; ++n) {
+        double s[NE];
+        PR_FORC s[c] = 0.0;
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            const double mv = TRANSP ? c_ops.D[n + G * k] : c_ops.D[k + G * n];
+            PR_FORC s[c] = fma(mv, in[k][c], s[c]);
+        }
+        PV<NE>::st(dst + n * stride, s);
+    }
+}
+
+template <int G>
+__device__ __forceinline__ int pr_face_node(int s, int n) {
+    return s == 0 ? n : s == 1 ? (G - 1) * G + n : s == 2 ? n * G : n * G + G - 1;
+}
+
+template <int G, int Q, int NE, int W, bool VISC>
+__global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 168) : 128) k_btp_stage_pair(const PairArgs a) {
+    using R = PairRec<G, Q>;
+    using V = PV<NE>;
+    typedef typename V::T VT;
+    constexpr int NP = R::NP, NQ2 = R::NQ2, PER = R::PER;
+    constexpr int NQIT = (NQ2 + 31) / 32, NFIT = (4 * Q + 31) / 32;
+    static_assert(NP <= 32 && 4 * G <= 32 && 3 * Q <= 32 && 12 <= 32, "polynomial order too high for this lane mapping");
+    extern __shared__ __align__(16) double sm_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int unit = blockIdx.x * W + warp;
+    if (unit * NE >= a.nelem) return;
+    double* smw = sm_all + (size_t)warp * ((size_t)R::S_TOTAL * NE + (size_t)R::HDR * NE);
+    double* hdr = smw;                                   // [NE][HDR], plain doubles
+    VT* sv = reinterpret_cast<VT*>(smw + R::HDR * NE);
+    VT* nod = sv + R::S_NOD;
+    VT* X = sv + R::S_X;
+    VT* T = sv + R::S_T;
+    VT* Lr = sv + R::S_L;
+
+    int e[NE];
+    bool ok[NE];
+    double* rec[NE];
+    PR_FORC {
+        e[c] = unit * NE + c;
+        ok[c] = e[c] < a.nelem;
+        if (!ok[c]) e[c] = a.nelem - 1;
+        rec[c] = a.rec + (size_t)e[c] * R::REC;
+    }
+    // ---- 0. header -> shared memory; pull the rest of the record into L2 (one instruction per element)
+    if (lane < R::HDR) { PR_FORC hdr[c * R::HDR + lane] = rec[c][lane]; }
+    if (a.prefetch && lane < NE) {
+        const double* p = (lane == 0) ? rec[0] : rec[NE - 1];
+        if (a.prefetch & 1) {
+            pr_prefetch_l2(p + R::O_QST, (uint32_t)((R::O_Q0 - R::O_QST) * sizeof(double)));
+            if (a.load_q0) pr_prefetch_l2(p + R::O_Q0, (uint32_t)(R::QBSZ * sizeof(double)));
+            if (a.load_q2) pr_prefetch_l2(p + R::O_Q2, (uint32_t)(R::QBSZ * sizeof(double)));
+        }
+        // the head of the record (header, state, nodal statics and sums) of the unit that follows one wave later
+        if ((a.prefetch & 2) && (long)(unit + a.pf_dist) * NE + lane < a.nelem)
+            pr_prefetch_l2(p + (size_t)a.pf_dist * NE * R::REC, (uint32_t)(R::O_QST * sizeof(double)));
+    }
+    const bool botfr = a.botfr != 0;
+
+    // ---- 1. nodal loads + nodal sums (mod_rk_mlswe.F90:90-92)
+    double pbp[NE], pv[NE], bd[4][NE];   // kept by lane I < NP for the LDG flux variable and the update
+    if (lane < NP) {
+        const int I = lane;
+        double dpp[NE], mx[NE], my[NE], oop[NE], c0[NE], c1[NE], c2[NE], c3[NE], c4[NE], c5[NE];
+        double pp[NE], up[NE], vp[NE];
+        PR_FORC {
+            const double* r = rec[c];
+            dpp[c] = r[R::O_QB + I]; mx[c] = r[R::O_QB + NP + I]; my[c] = r[R::O_QB + 2 * NP + I];
+            pbp[c] = r[R::O_NST + I]; oop[c] = r[R::O_NST + NP + I];
+            c0[c] = r[R::O_ACCN + I]; c1[c] = r[R::O_ACCN + NP + I]; c2[c] = r[R::O_ACCN + 2 * NP + I];
+            c3[c] = r[R::O_ACCN + 3 * NP + I]; c4[c] = r[R::O_ACCN + 4 * NP + I]; c5[c] = r[R::O_ACCN + 5 * NP + I];
+            if (botfr) { pp[c] = r[R::O_NST + 3 * NP + I]; up[c] = r[R::O_NST + 4 * NP + I]; vp[c] = r[R::O_NST + 5 * NP + I]; }
+            if (VISC) {
+                pv[c] = r[R::O_NST + 6 * NP + I];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) bd[k][c] = r[R::O_NST + (7 + k) * NP + I];
+            }
+        }
+        double pb[NE], u[NE], v[NE];
+        PR_FORC {
+            pb[c] = dpp[c] + pbp[c];
+            const double rpb = pr_rcp(pb[c]);
+            u[c] = mx[c] * rpb; v[c] = my[c] * rpb;
+            const double t = 1.0 + dpp[c] * oop[c];
+            if (ok[c]) {
+                double* r = rec[c];
+                r[R::O_ACCN + I] = c0[c] + t * t; r[R::O_ACCN + NP + I] = c1[c] + u[c]; r[R::O_ACCN + 2 * NP + I] = c2[c] + v[c];
+                r[R::O_ACCN + 3 * NP + I] = c3[c] + dpp[c]; r[R::O_ACCN + 4 * NP + I] = c4[c] + mx[c]; r[R::O_ACCN + 5 * NP + I] = c5[c] + my[c];
+            }
+        }
+        V::st(nod + 0 * NP + I, dpp); V::st(nod + 1 * NP + I, mx); V::st(nod + 2 * NP + I, my); V::st(nod + 3 * NP + I, pb);
+        if (botfr) { V::st(nod + 4 * NP + I, pp); V::st(nod + 5 * NP + I, up); V::st(nod + 6 * NP + I, vp); }
+        V::st(nod + 7 * NP + I, u); V::st(nod + 8 * NP + I, v);
+    }
+    __syncwarp();
+    // per-element geometry and flags (registers)
+    double ksx[NE], ksy[NE], etx[NE], ety[NE], J[NE];
+    int flags[NE];
+    PR_FORC {
+        const double* h = hdr + c * R::HDR;
+        ksx[c] = h[0]; ksy[c] = h[1]; etx[c] = h[2]; ety[c] = h[3]; J[c] = h[4];
+        flags[c] = reinterpret_cast<const int*>(h + 22)[0];
+    }
+    // neighbour traces and owned face sums -> L2 (the header has just told us where they are)
+    if ((a.prefetch & 1) && lane < 4 * NE) {
+        const int c = lane >> 2, s = lane & 3;
+        const int* hi = reinterpret_cast<const int*>(hdr + c * R::HDR + 18);
+        const int nb = hi[s], tr = hi[4 + s];
+        if (tr >= 0) pr_prefetch_l2(a.tr_in + (size_t)tr * R::TSIDE, R::TSIDE * 8u);
+        if (nb < 0 || e[c] < nb) pr_prefetch_l2(a.accf + ((size_t)e[c] * 4 + s) * R::ASIDE, R::ASIDE * 8u);
+    }
+    // ---- 2. sum factorisation, pass 1: one nodal row per lane -> T[f][m][i]; LDG gradient lines -> Lr[0..3]
+    {
+        if (lane < 4 * G) {
+            const int f = lane / G, m = lane - f * G;
+            pl_n2q<NE, G, Q, false, 1, 1>(nod + f * NP + m * G, T + f * PER + m * Q);
+        }
+        if (botfr && lane < 3 * G) {
+            const int f = 4 + lane / G, m = lane % G;
+            pl_n2q<NE, G, Q, false, 1, 1>(nod + f * NP + m * G, T + f * PER + m * Q);
+        }
+        if (VISC && lane < 4 * G) {
+            const int kind = lane / (2 * G), r = lane - kind * 2 * G, f = r / G, l = r - f * G;
+            const int stride = kind ? G : 1, off = kind ? l : l * G;
+            pl_grad<NE, G, false>(nod + (7 + f) * NP + off, Lr + (2 * kind + f) * NP + off, stride);
+        }
+    }
+    // quadrature-point operands of a block of 32 points: 7 statics + 6 running sums per element, loaded one block ahead
+    struct QL { double s[7][NE]; double acc[6][NE]; };
+    auto qload = [&](int it, QL& L) {
+        const int q = it * 32 + lane;
+        if (q < NQ2) {
+            PR_FORC {
+                const double* rs = rec[c] + R::O_QST + q;
+                const double* ra = rec[c] + R::O_ACCQ + q;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) L.s[k][c] = rs[k * NQ2];
+                L.s[5][c] = (flags[c] & PF_COR) ? rs[5 * NQ2] : 0.0;
+                L.s[6][c] = (flags[c] & PF_TWX) ? rs[6 * NQ2] : 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) L.acc[k][c] = ra[k * NQ2];
+            }
+        }
+    };
+    QL qbuf[2];
+    qload(0, qbuf[0]);
+    __syncwarp();
+    // ---- 3. pass 2: one quadrature column per lane -> X[f][j][i]; LDG: G = grad(ub,vb), flux variable, weighted metric terms
+    {
+        const int nlines = (botfr ? 7 : 4) * Q;
+#pragma unroll 1
+        for (int it = lane; it < nlines; it += 32) {
+            const int f = it / Q, i = it - f * Q;
+            pl_n2q<NE, G, Q, false, Q, Q>(T + f * PER + i, X + f * NQ2 + i);
+        }
+        if (VISC && lane < NP) {
+            const int I = lane, m = I / G, n = I - m * G;
+            double dku[NE], dkv[NE], deu[NE], dev[NE];
+            V::ld(Lr + 0 * NP + I, dku); V::ld(Lr + 1 * NP + I, dkv); V::ld(Lr + 2 * NP + I, deu); V::ld(Lr + 3 * NP + I, dev);
+            const double w0 = c_ops.wg[n] * c_ops.wg[m];
+            double g0[NE], g1[NE], g2[NE], g3[NE], q0[NE], q1[NE], q2[NE], q3[NE], z0[NE], z1[NE], z2[NE], z3[NE];
+            PR_FORC {
+                g0[c] = ksx[c] * dku[c] + etx[c] * deu[c]; g1[c] = ksy[c] * dku[c] + ety[c] * deu[c];
+                g2[c] = ksx[c] * dkv[c] + etx[c] * dev[c]; g3[c] = ksy[c] * dkv[c] + ety[c] * dev[c];
+                q0[c] = pv[c] * g0[c] + bd[0][c]; q1[c] = pv[c] * g1[c] + bd[1][c];
+                q2[c] = pv[c] * g2[c] + bd[2][c]; q3[c] = pv[c] * g3[c] + bd[3][c];
+                const double w = w0 * J[c];
+                z0[c] = w * (ksx[c] * q0[c] + ksy[c] * q1[c]); z1[c] = w * (ksx[c] * q2[c] + ksy[c] * q3[c]);
+                z2[c] = w * (etx[c] * q0[c] + ety[c] * q1[c]); z3[c] = w * (etx[c] * q2[c] + ety[c] * q3[c]);
+            }
+            V::st(Lr + 4 * NP + I, g0); V::st(Lr + 5 * NP + I, g1); V::st(Lr + 6 * NP + I, g2); V::st(Lr + 7 * NP + I, g3);
+            V::st(nod + 4 * NP + I, q0); V::st(nod + 5 * NP + I, q1); V::st(nod + 6 * NP + I, q2); V::st(nod + 7 * NP + I, q3);
+            V::st(Lr + 8 * NP + I, z0); V::st(Lr + 9 * NP + I, z1); V::st(Lr + 10 * NP + I, z2); V::st(Lr + 11 * NP + I, z3);
+        }
+    }
+    __syncwarp();
+    // ---- 4. pointwise physics at the quadrature points (mod_rhs_btp.F90:136-192); the fluxes overwrite X in place
+#pragma unroll
+    for (int it = 0; it < NQIT; ++it) {
+        QL& qcur = qbuf[it & 1];
+        if (it + 1 < NQIT) qload(it + 1, qbuf[(it + 1) & 1]);
+        const int q = it * 32 + lane;
+        if (q < NQ2) {
+            const int j = q / Q, i = q - j * Q;
+            const double w0 = c_ops.wq[i] * c_ops.wq[j];
+            double dpp[NE], udp[NE], vdp[NE], dp[NE], pp[NE], up[NE], vp[NE];
+            V::ld(X + 0 * NQ2 + q, dpp); V::ld(X + 1 * NQ2 + q, udp); V::ld(X + 2 * NQ2 + q, vdp); V::ld(X + 3 * NQ2 + q, dp);
+            if (botfr) { V::ld(X + 4 * NQ2 + q, pp); V::ld(X + 5 * NQ2 + q, up); V::ld(X + 6 * NQ2 + q, vp); }
+            double o0[NE], o1[NE], o2[NE], o3[NE], o4[NE], o5[NE], o6[NE], o7[NE];
+            PR_FORC {
+                const double wq = w0 * J[c];
+                const double rdp = pr_rcp(dp[c]);
+                const double ub = udp[c] * rdp, vb = vdp[c] * rdp;
+                double tb_u = 0.0, tb_v = 0.0;
+                if (botfr) {
+                    const double ubot = up[c] + ub, vbot = vp[c] + vb;
+                    const double spd = (a.botfr == 1) ? a.cd_g * pp[c] : a.cd_alpha * sqrt(ubot * ubot + vbot * vbot);
+                    tb_u = spd * ubot; tb_v = spd * vbot;
+                }
+                const double s_oop = qcur.s[0][c], s_H = qcur.s[1][c], s_uu = qcur.s[2][c], s_uv = qcur.s[3][c], s_vv = qcur.s[4][c];
+                const double fcor = qcur.s[5][c], s_twx = qcur.s[6][c];
+                double s_twy = 0.0, s_gzx = 0.0, s_gzy = 0.0;
+                if (flags[c] & (PF_TWY | PF_GZ)) {   // rare forcing fields are read on demand
+                    const double* rs = rec[c] + R::O_QSTR + q;
+                    if (flags[c] & PF_TWY) s_twy = rs[0];
+                    if (flags[c] & PF_GZ) { s_gzx = rs[NQ2]; s_gzy = rs[2 * NQ2]; }
+                }
+                const double sc_x = fcor * vdp[c] + a.g * (s_twx - tb_u) - a.g * dp[c] * s_gzx;
+                const double sc_y = -fcor * udp[c] + a.g * (s_twy - tb_v) - a.g * dp[c] * s_gzy;
+                const double ope = 1.0 + dpp[c] * s_oop;
+                const double ope2 = ope * ope;
+                const double Hq = ope2 * s_H;
+                const double qu = ub * udp[c] + ope * s_uu;
+                const double quv = ub * vdp[c] + ope * s_uv;
+                const double qv = vb * vdp[c] + ope * s_vv;
+                if (ok[c]) {
+                    double* ra = rec[c] + R::O_ACCQ + q;
+                    ra[0] = qcur.acc[0][c] + qu; ra[NQ2] = qcur.acc[1][c] + qv; ra[2 * NQ2] = qcur.acc[2][c] + quv;
+                    ra[3 * NQ2] = qcur.acc[3][c] + ope2; ra[4 * NQ2] = qcur.acc[4][c] + ub; ra[5 * NQ2] = qcur.acc[5][c] + vb;
+                    if (a.botfr == 2) { double* rr_ = rec[c] + R::O_ACCQR + q; rr_[0] += tb_u; rr_[NQ2] += tb_v; }
+                }
+                const double Fx2 = Hq + qu, Fy3 = Hq + qv;
+                o0[c] = wq * (ksx[c] * udp[c] + ksy[c] * vdp[c]);   // Fk1
+                o1[c] = wq * (etx[c] * udp[c] + ety[c] * vdp[c]);   // Fe1
+                o2[c] = wq * sc_x;                                  // S2
+                o3[c] = wq * (ksx[c] * Fx2 + ksy[c] * quv);         // Fk2
+                o4[c] = wq * (etx[c] * Fx2 + ety[c] * quv);         // Fe2
+                o5[c] = wq * sc_y;                                  // S3
+                o6[c] = wq * (ksx[c] * quv + ksy[c] * Fy3);         // Fk3
+                o7[c] = wq * (etx[c] * quv + ety[c] * Fy3);         // Fe3
+            }
+            V::st(X + 0 * NQ2 + q, o0); V::st(X + 1 * NQ2 + q, o1); V::st(X + 2 * NQ2 + q, o2); V::st(X + 3 * NQ2 + q, o3);
+            V::st(X + 4 * NQ2 + q, o4); V::st(X + 5 * NQ2 + q, o5); V::st(X + 6 * NQ2 + q, o6); V::st(X + 7 * NQ2 + q, o7);
+        }
+    }
+    // neighbour traces and the neighbour's viscosity statics of face node (s,n), issued one phase ahead
+    double tn[7][NE], vs[6][NE];
+    const int fs = lane / G, fn = lane - fs * G;   // face node owned by this lane (lane < 4G)
+    if (lane < 4 * G) {
+        PR_FORC {
+            const int tr = reinterpret_cast<const int*>(hdr + c * R::HDR + 18)[4 + fs];
+            if (tr >= 0) {
+                const double* t = a.tr_in + (size_t)tr * R::TSIDE + fn;
+#pragma unroll
+                for (int k = 0; k < (VISC ? 7 : 3); ++k) tn[k][c] = t[k * G];
+            }
+            const double* vp_ = rec[c] + R::O_VST + fs * R::VSIDE + fn;
+            vs[5][c] = vp_[5 * G];
+            if (VISC) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) vs[k][c] = vp_[k * G];
+            }
+        }
+    }
+    __syncwarp();
+    // ---- 5. scatter pass 1 (contraction over j): lane (f,i) -> TB_f = A.Fk_f, TA_f = B.Fe_f + A.S_f, as T[f][m][i], T[3+f][m][i]
+    if (lane < 3 * Q) {
+        const int f = lane / Q, i = lane - f * Q;
+        double tb[G][NE], ta[G][NE];
+#pragma unroll
+        for (int m = 0; m < G; ++m) { PR_FORC { tb[m][c] = 0.0; ta[m][c] = 0.0; } }
+        pl_q2n_acc<NE, G, Q, false, Q>(X + (3 * f) * NQ2 + i, tb);
+        pl_q2n_acc<NE, G, Q, true, Q>(X + (3 * f + 1) * NQ2 + i, ta);
+        if (f > 0) pl_q2n_acc<NE, G, Q, false, Q>(X + (3 * f - 1) * NQ2 + i, ta);
+#pragma unroll
+        for (int m = 0; m < G; ++m) { V::st(T + f * PER + m * Q + i, tb[m]); V::st(T + (3 + f) * PER + m * Q + i, ta[m]); }
+    }
+    __syncwarp();
+    // ---- 6. scatter pass 2 (contraction over i): lane (f,m) -> rhs[f][m][n] = B.TB_f + A.TA_f
+    if (lane < 3 * G) {
+        const int f = lane / G, m = lane - f * G;
+        double r[G][NE];
+#pragma unroll
+        for (int n = 0; n < G; ++n) { PR_FORC r[n][c] = 0.0; }
+        pl_q2n_acc<NE, G, Q, true, 1>(T + f * PER + m * Q, r);
+        pl_q2n_acc<NE, G, Q, false, 1>(T + (3 + f) * PER + m * Q, r);
+#pragma unroll
+        for (int n = 0; n < G; ++n) V::st(X + R::X_RHS + f * NP + m * G + n, r[n]);
+    }
+    // LDG volume lines (btp_compute_laplacian): lapX[c][m'][n'] = sum_n D(n',n) Zxi_c[m'][n]; lapE[c][m'][n'] = sum_m D(m',m) Zeta_c[m][n']
+    if (VISC && lane < 4 * G) {
+        const int kind = lane / (2 * G), r = lane - kind * 2 * G, cc = r / G, l = r - cc * G;
+        const int stride = kind ? G : 1, off = kind ? l : l * G;
+        pl_grad<NE, G, true>(Lr + (8 + 2 * kind + cc) * NP + off, Lr + (2 * kind + cc) * NP + off, stride);
+    }
+    // ---- 7a. face traces: own and neighbour state in canonical (left, right) order; LDG face flux at the face nodes,
+    //          as written (btp_extract_df; mod_laplacian_quad.F90:85-98,427-519)
+    if (lane < 4 * G) {
+        const int s = fs, n = fn, I = pr_face_node<G>(s, n);
+        double ow0[NE], ow1[NE], ow2[NE], pbo[NE];
+        V::ld(nod + 0 * NP + I, ow0); V::ld(nod + 1 * NP + I, ow1); V::ld(nod + 2 * NP + I, ow2); V::ld(nod + 3 * NP + I, pbo);
+        double go[4][NE], qo[4][NE];
+        if (VISC) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { V::ld(Lr + (4 + k) * NP + I, go[k]); V::ld(nod + (4 + k) * NP + I, qo[k]); }
+        }
+        double L0[NE], L1[NE], L2[NE], L3[NE], R0[NE], R1[NE], R2[NE], R3[NE], lfu[NE], lfv[NE];
+        const double wgn = c_ops.wg[n];
+        PR_FORC {
+            const double* h = hdr + c * R::HDR;
+            const int* hi = reinterpret_cast<const int*>(h + 18);
+            const int nb = hi[s], tr = hi[4 + s];
+            const double nx = h[6 + s * 3 + 0], ny = h[6 + s * 3 + 1], nlen = h[6 + s * 3 + 2];
+            const bool left = (nb < 0) || (e[c] < nb);
+            double n0, n1, n2;
+            if (tr >= 0) { n0 = tn[0][c]; n1 = tn[1][c]; n2 = tn[2][c]; }
+            else {
+                n0 = ow0[c]; n1 = ow1[c]; n2 = ow2[c];
+                if (nb == NBR_FREESLIP) { const double un = nx * ow1[c] + ny * ow2[c]; n1 = ow1[c] - 2.0 * un * nx; n2 = ow2[c] - 2.0 * un * ny; }
+                else if (nb == NBR_NOSLIP) { n1 = -ow1[c]; n2 = -ow2[c]; }
+            }
+            const double pbn = n0 + vs[5][c];
+            L0[c] = left ? pbo[c] : pbn; R0[c] = left ? pbn : pbo[c];
+            L1[c] = left ? ow0[c] : n0;  R1[c] = left ? n0 : ow0[c];
+            L2[c] = left ? ow1[c] : n1;  R2[c] = left ? n1 : ow1[c];
+            L3[c] = left ? ow2[c] : n2;  R3[c] = left ? n2 : ow2[c];
+            if (VISC) {
+                double gn[4];
+                if (tr >= 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) gn[k] = tn[3 + k][c];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) gn[k] = go[k][c];
+                    if (nb == NBR_FREESLIP) {
+                        double un = go[0][c] * nx + go[1][c] * ny;
+                        gn[0] = go[0][c] - 2.0 * un * nx; gn[1] = go[1][c] - 2.0 * un * ny;
+                        un = go[2][c] * nx + go[3][c] * ny;
+                        gn[2] = go[2][c] - 2.0 * un * nx; gn[3] = go[3][c] - 2.0 * un * ny;
+                    }
+                }
+                double fo_[4], fn_[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { fo_[k] = qo[k][c]; fn_[k] = vs[4][c] * gn[k] + vs[k][c]; }
+                double fl[4], fr[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { fl[k] = left ? fo_[k] : fn_[k]; fr[k] = left ? fn_[k] : fo_[k]; }
+                const double qu0 = 0.5 * fl[0] + 0.5 * fr[0], qu1 = 0.5 * fl[1] + 0.5 * fr[1];
+                const double qv0 = 0.5 * fl[2] + 0.5 * fr[2], qv1 = 0.5 * fl[3] + 0.5 * fr[3];
+                const double wq = wgn * nlen;
+                const double flux_qu = (qu0 - fl[0] * nx) + (qu1 - fl[1] * ny);
+                const double flux_qv = (qv0 - fl[2] * nx) + (qv1 - fl[3] * ny);
+                const double sgn = left ? wq : -wq;
+                lfu[c] = sgn * flux_qu; lfv[c] = sgn * flux_qv;
+            }
+        }
+        VT* FL = X + R::X_FL + (s * 4) * G + n;
+        VT* FR = X + R::X_FR + (s * 4) * G + n;
+        V::st(FL, L0); V::st(FL + G, L1); V::st(FL + 2 * G, L2); V::st(FL + 3 * G, L3);
+        V::st(FR, R0); V::st(FR + G, R1); V::st(FR + 2 * G, R2); V::st(FR + 3 * G, R3);
+        if (VISC) { V::st(X + R::X_LF + (s * 2 + 0) * G + n, lfu); V::st(X + R::X_LF + (s * 2 + 1) * G + n, lfv); }
+    }
+    // face coefficients and (owner only) running sums of the face quadrature points, first block, one phase ahead
+    struct FLd { double cf[11][NE]; double acc[11][NE]; };
+    auto fload = [&](int it, FLd& F) {
+        const int p = it * 32 + lane;
+        if (p < 4 * Q) {
+            const int s = p / Q, iq = p - s * Q;
+            PR_FORC {
+                const int nb = reinterpret_cast<const int*>(hdr + c * R::HDR + 18)[s];
+                const double* cf = rec[c] + R::O_FST + s * R::FSIDE + iq;
+#pragma unroll
+                for (int k = 0; k < 11; ++k) F.cf[k][c] = cf[k * Q];
+                if (nb < 0 || e[c] < nb) {
+                    const double* af = a.accf + ((size_t)e[c] * 4 + s) * R::ASIDE + iq;
+#pragma unroll
+                    for (int k = 0; k < 11; ++k) F.acc[k][c] = af[k * Q];
+                }
+            }
+        }
+    };
+    FLd fbuf[2];
+    fload(0, fbuf[0]);
+    __syncwarp();
+    // ---- 7b. interpolate the traces to the face quadrature points: one (side, L/R, variable) line per lane
+    {
+        const int s = lane >> 3, side = (lane >> 2) & 1, var = lane & 3;   // var: 0 pb 1 pbpert 2 mx 3 my
+        pl_n2q<NE, G, Q, false, 1, 1>(X + R::X_FL + side * 16 * G + (s * 4 + var) * G, T + lane * Q);
+    }
+    // update operands of node I, one phase ahead
+    double mi[NE], q0v[3][NE], q2v[3][NE];
+    if (lane < NP) {
+        PR_FORC {
+            const double* r = rec[c];
+            mi[c] = r[R::O_NST + 2 * NP + lane];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                q0v[k][c] = a.load_q0 ? r[R::O_Q0 + k * NP + lane] : 0.0;
+                q2v[k][c] = a.load_q2 ? r[R::O_Q2 + k * NP + lane] : 0.0;
+            }
+        }
+    }
+    __syncwarp();
+    // ---- 7c. face fluxes, canonical left perspective (mod_rhs_btp.F90:237-330)
+#pragma unroll
+    for (int it = 0; it < NFIT; ++it) {
+        FLd& fcur = fbuf[it & 1];
+        if (it + 1 < NFIT) fload(it + 1, fbuf[(it + 1) & 1]);
+        const int p = it * 32 + lane;
+        if (p < 4 * Q) {
+            const int s = p / Q, iq = p - s * Q;
+            const VT* Lp = T + (s * 8) * Q + iq;
+            const VT* Rp = T + (s * 8 + 4) * Q + iq;
+            double pbL[NE], ppL[NE], mxL[NE], myL[NE], pbR[NE], ppR[NE], mxR[NE], myR[NE];
+            V::ld(Lp, pbL); V::ld(Lp + Q, ppL); V::ld(Lp + 2 * Q, mxL); V::ld(Lp + 3 * Q, myL);
+            V::ld(Rp, pbR); V::ld(Rp + Q, ppR); V::ld(Rp + 2 * Q, mxR); V::ld(Rp + 3 * Q, myR);
+            const double wq0 = c_ops.wq[iq];
+            double f0[NE], f1[NE], f2[NE];
+            PR_FORC {
+                const double* h = hdr + c * R::HDR;
+                const int nb = reinterpret_cast<const int*>(h + 18)[s];
+                const bool left = (nb < 0) || (e[c] < nb);
+                const double nxl = h[6 + s * 3 + 0], nyl = h[6 + s * 3 + 1], nlen = h[6 + s * 3 + 2];
+                const double cL = fcur.cf[0][c], cR = fcur.cf[1][c], cLR = fcur.cf[2][c], lam = fcur.cf[3][c];
+                const double s_oope = fcur.cf[4][c], s_uue = fcur.cf[5][c], s_uve = fcur.cf[6][c], s_vve = fcur.cf[7][c], s_He = fcur.cf[8][c];
+                const double pU_L = nxl * mxL[c] + nyl * myL[c];
+                const double pU_R = -nxl * mxR[c] - nyl * myR[c];
+                const double pbpert_edge = cL * ppL[c] + cR * ppR[c] + cLR * (pU_L + pU_R);
+                const double ope_e = 1.0 + pbpert_edge * s_oope;
+                const double fex = cR * mxL[c] + cL * mxR[c] + lam * (nxl * ppL[c] - nxl * ppR[c]);
+                const double fey = cR * myL[c] + cL * myR[c] + lam * (nyl * ppL[c] - nyl * ppR[c]);
+                const double rl = pr_rcp(pbL[c]), rr = pr_rcp(pbR[c]);
+                const double ul = mxL[c] * rl, ur = mxR[c] * rr, vl = myL[c] * rl, vr = myR[c] * rr;
+                const double quu = 0.5 * (ul * mxL[c] + ur * mxR[c]) + ope_e * s_uue;
+                const double quv = 0.5 * (vl * mxL[c] + vr * mxR[c]) + ope_e * s_uve;
+                const double qvu = 0.5 * (ul * myL[c] + ur * myR[c]) + ope_e * s_uve;
+                const double qvv = 0.5 * (vl * myL[c] + vr * myR[c]) + ope_e * s_vve;
+                const double e2 = ope_e * ope_e;
+                const double Hf = e2 * s_He;
+                if (left && ok[c]) {
+                    const double ol = 1.0 + ppL[c] * fcur.cf[9][c], orr = 1.0 + ppR[c] * fcur.cf[10][c];
+                    double* af = a.accf + ((size_t)e[c] * 4 + s) * R::ASIDE + iq;
+                    af[0] = fcur.acc[0][c] + quu; af[Q] = fcur.acc[1][c] + quv; af[2 * Q] = fcur.acc[2][c] + qvu; af[3 * Q] = fcur.acc[3][c] + qvv;
+                    af[4 * Q] = fcur.acc[4][c] + ol * ol; af[5 * Q] = fcur.acc[5][c] + orr * orr; af[6 * Q] = fcur.acc[6][c] + e2;
+                    af[7 * Q] = fcur.acc[7][c] + ul; af[8 * Q] = fcur.acc[8][c] + ur; af[9 * Q] = fcur.acc[9][c] + vl; af[10 * Q] = fcur.acc[10][c] + vr;
+                }
+                const double wq = wq0 * nlen;
+                const double dispu = 0.5 * lam * (mxR[c] - mxL[c]), dispv = 0.5 * lam * (myR[c] - myL[c]);
+                const double flux_x = nxl * quu + nyl * quv - dispu;
+                const double flux_y = nxl * qvu + nyl * qvv - dispv;
+                const double flux = nxl * fex + nyl * fey;
+                const double sgn = left ? -wq : wq;
+                f0[c] = sgn * flux; f1[c] = sgn * (nxl * Hf + flux_x); f2[c] = sgn * (nyl * Hf + flux_y);
+            }
+            VT* ff = X + R::X_FF + (s * 3) * Q + iq;
+            V::st(ff, f0); V::st(ff + Q, f1); V::st(ff + 2 * Q, f2);
+        }
+    }
+    __syncwarp();
+    // ---- 7d. project the face fluxes onto the face nodes: one (side, field) line per lane -> T[0 .. 12G)
+    if (lane < 12) {
+        double pr[G][NE];
+#pragma unroll
+        for (int n = 0; n < G; ++n) { PR_FORC pr[n][c] = 0.0; }
+        pl_q2n_acc<NE, G, Q, false, 1>(X + R::X_FF + lane * Q, pr);
+#pragma unroll
+        for (int n = 0; n < G; ++n) V::st(T + lane * G + n, pr[n]);
+    }
+    __syncwarp();
+    // ---- 8. gather per node, mass matrix, viscosity, SSPRK update, wall projection (mod_rk_mlswe.F90:97-108)
+    if (lane < NP) {
+        const int I = lane, m = I / G, n = I - m * G;
+        double r0[NE], r1[NE], r2[NE], l0[NE], l1[NE];
+        V::ld(X + R::X_RHS + 0 * NP + I, r0); V::ld(X + R::X_RHS + 1 * NP + I, r1); V::ld(X + R::X_RHS + 2 * NP + I, r2);
+        if (VISC) {
+            double t0[NE], t1[NE], t2[NE], t3[NE];
+            V::ld(Lr + 0 * NP + I, t0); V::ld(Lr + 1 * NP + I, t1); V::ld(Lr + 2 * NP + I, t2); V::ld(Lr + 3 * NP + I, t3);
+            PR_FORC { l0[c] = -(t0[c] + t2[c]); l1[c] = -(t1[c] + t3[c]); }
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const bool on = (s == 0) ? (m == 0) : (s == 1) ? (m == G - 1) : (s == 2) ? (n == 0) : (n == G - 1);
+            if (!on) continue;
+            const int nf = (s < 2) ? n : m;
+            double p0[NE], p1[NE], p2[NE];
+            V::ld(T + (s * 3 + 0) * G + nf, p0); V::ld(T + (s * 3 + 1) * G + nf, p1); V::ld(T + (s * 3 + 2) * G + nf, p2);
+            PR_FORC { r0[c] += p0[c]; r1[c] += p1[c]; r2[c] += p2[c]; }
+            if (VISC) {
+                double a0[NE], a1[NE];
+                V::ld(X + R::X_LF + (s * 2 + 0) * G + nf, a0); V::ld(X + R::X_LF + (s * 2 + 1) * G + nf, a1);
+                PR_FORC { l0[c] += a0[c]; l1[c] += a1[c]; }
+            }
+        }
+        double q1a[NE], q1b[NE], q1c[NE];
+        V::ld(nod + 0 * NP + I, q1a); V::ld(nod + 1 * NP + I, q1b); V::ld(nod + 2 * NP + I, q1c);
+        double nw0[NE], nw1[NE], nw2[NE], un_[NE], vn_[NE];
+        PR_FORC {
+            double rr[3] = {mi[c] * r0[c], mi[c] * r1[c], mi[c] * r2[c]};
+            if (VISC) { rr[1] = rr[1] + a.visc * mi[c] * l0[c]; rr[2] = rr[2] + a.visc * mi[c] * l1[c]; }
+            const double q1[3] = {q1a[c], q1b[c], q1c[c]};
+            double qn[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double q0 = a.load_q0 ? q0v[k][c] : q1[k];
+                qn[k] = a.a1 * q0 + a.a2 * q1[k] + a.a3 * q2v[k][c] + a.dtt * rr[k];
+            }
+            const double* h = hdr + c * R::HDR;
+            const int* hi = reinterpret_cast<const int*>(h + 18);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const bool on = (s == 0) ? (m == 0) : (s == 1) ? (m == G - 1) : (s == 2) ? (n == 0) : (n == G - 1);
+                if (!on) continue;
+                const int nb = hi[s];
+                if (nb == NBR_FREESLIP) {
+                    const double nx = h[6 + s * 3 + 0], ny = h[6 + s * 3 + 1];
+                    const double unl = qn[1] * nx + qn[2] * ny;
+                    qn[1] = qn[1] - unl * nx; qn[2] = qn[2] - unl * ny;
+                } else if (nb == NBR_NOSLIP) { qn[1] = 0.0; qn[2] = 0.0; }
+            }
+            if (ok[c]) {
+                double* r = rec[c];
+                if (a.store_q0) { r[R::O_Q0 + I] = q1[0]; r[R::O_Q0 + NP + I] = q1[1]; r[R::O_Q0 + 2 * NP + I] = q1[2]; }
+                r[R::O_QB + I] = qn[0]; r[R::O_QB + NP + I] = qn[1]; r[R::O_QB + 2 * NP + I] = qn[2];
+                if (a.store_q2) { r[R::O_Q2 + I] = qn[0]; r[R::O_Q2 + NP + I] = qn[1]; r[R::O_Q2 + 2 * NP + I] = qn[2]; }
+            }
+            const double rpb = pr_rcp(qn[0] + pbp[c]);
+            nw0[c] = qn[0]; nw1[c] = qn[1]; nw2[c] = qn[2];
+            un_[c] = qn[1] * rpb; vn_[c] = qn[2] * rpb;
+        }
+        V::st(nod + 0 * NP + I, nw0); V::st(nod + 1 * NP + I, nw1); V::st(nod + 2 * NP + I, nw2);
+        V::st(nod + 7 * NP + I, un_); V::st(nod + 8 * NP + I, vn_);
+    }
+    __syncwarp();
+    // ---- 9. traces of the new state (+ LDG gradient) for the next stage
+    if (VISC) {
+        if (lane < 4 * G) {
+            const int kind = lane / (2 * G), r = lane - kind * 2 * G, f = r / G, l = r - f * G;
+            const int stride = kind ? G : 1, off = kind ? l : l * G;
+            pl_grad<NE, G, false>(nod + (7 + f) * NP + off, Lr + (2 * kind + f) * NP + off, stride);
+        }
+        __syncwarp();
+    }
+    if (lane < 4 * G) {
+        const int s = fs, n = fn, I = pr_face_node<G>(s, n);
+        double t0[NE], t1[NE], t2[NE], dku[NE], dkv[NE], deu[NE], dev[NE];
+        V::ld(nod + 0 * NP + I, t0); V::ld(nod + 1 * NP + I, t1); V::ld(nod + 2 * NP + I, t2);
+        if (VISC) { V::ld(Lr + 0 * NP + I, dku); V::ld(Lr + 1 * NP + I, dkv); V::ld(Lr + 2 * NP + I, deu); V::ld(Lr + 3 * NP + I, dev); }
+        PR_FORC {
+            if (ok[c]) {
+                double* to = a.tr_out + ((size_t)e[c] * 4 + s) * R::TSIDE + n;
+                to[0] = t0[c]; to[G] = t1[c]; to[2 * G] = t2[c];
+                if (VISC) {
+                    to[3 * G] = ksx[c] * dku[c] + etx[c] * deu[c];
+                    to[4 * G] = ksy[c] * dku[c] + ety[c] * deu[c];
+                    to[5 * G] = ksx[c] * dkv[c] + etx[c] * dev[c];
+                    to[6 * G] = ksy[c] * dkv[c] + ety[c] * dev[c];
+                }
+            }
+        }
+    }
+}
+
+// ---- runtime view of the record layout (pack kernels, host) ------------------------------------------------------
+struct PairDims {
+    int G, Q, NP, NQ2, HDR, O_QB, O_Q0, O_Q2, O_NST, O_ACCN, O_QST, O_ACCQ, O_FST, O_VST, O_QSTR, O_ACCQR, REC, FSIDE, VSIDE, ASIDE, TSIDE;
+};
+template <int G, int Q>
+inline PairDims make_pairdims_t() {
+    using R = PairRec<G, Q>;
+    PairDims d;
+    d.G = G; d.Q = Q; d.NP = R::NP; d.NQ2 = R::NQ2; d.HDR = R::HDR; d.O_QB = R::O_QB; d.O_Q0 = R::O_Q0; d.O_Q2 = R::O_Q2; d.O_NST = R::O_NST;
+    d.O_ACCN = R::O_ACCN; d.O_QST = R::O_QST; d.O_ACCQ = R::O_ACCQ; d.O_FST = R::O_FST; d.O_VST = R::O_VST; d.REC = R::REC;
+    d.O_QSTR = R::O_QSTR; d.O_ACCQR = R::O_ACCQR;
+    d.FSIDE = R::FSIDE; d.VSIDE = R::VSIDE; d.ASIDE = R::ASIDE; d.TSIDE = R::TSIDE;
+    return d;
+}
+inline bool stage_pair_supported(const Solver& S) { return (S.ngl == 5 && S.nq == 9) || (S.ngl == 4 && S.nq == 7); }
+inline PairDims make_pairdims(int G, int Q) { return (G == 5) ? make_pairdims_t<5, 9>() : make_pairdims_t<4, 7>(); }
+
+struct PairPackArgs {
+    Mesh M;
+    PairDims D;
+    const double* qb[3];
+    const double* nstp[11];
+    const double* qstp[10];
+    const double* fstp[11];   // the last two (pbl, pbr) are stored as reciprocals
+    const double* bdg[4];
+    const double* pbv;
+    const double* pbn;
+    const double* hstat;      // halo copies of (bdg0..3, pbv) traces
+    size_t hstat_stride;
+    double *rec, *tr;
+    int has_visc;
+};
+// planes -> records, once per substep loop (block per element): header, state, statics, initial traces.
+// The running sums (ACCN, ACCQ, face sums) and the SSPRK work states are zeroed.
+__global__ void k_pair_pack(PairPackArgs a) {
+    extern __shared__ double sm[];
+    __shared__ int s_flags;
+    const PairDims& D = a.D;
+    const int G = D.G, Q = D.Q, NP = D.NP, NQ2 = D.NQ2;
+    const int e = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const size_t nbase = (size_t)e * NP, qbase = (size_t)e * NQ2;
+    double* r = a.rec + (size_t)e * D.REC;
+    double* u = sm;
+    double* v = sm + NP;
+    if (tid == 0) s_flags = 0;
+    __syncthreads();
+    // header
+    if (tid < 5) r[tid] = a.M.em[e * 5 + tid];
+    if (tid == 5 || tid == 23) r[tid] = 0.0;
+    if (tid >= 6 && tid < 18) r[tid] = a.M.fgeom[(size_t)e * 12 + (tid - 6)];
+    if (tid < 4) {
+        const int nb = a.M.nbr[e * 4 + tid], nbs = a.M.nbslot[e * 4 + tid];
+        int* hi = reinterpret_cast<int*>(r + 18);
+        hi[tid] = nb;
+        hi[4 + tid] = (nb >= 0) ? nb * 4 + nbs : (nb == NBR_HALO) ? a.M.nslots + nbs : -1;
+    }
+    // state, work states, nodal statics, nodal sums
+    for (int t = tid; t < 3 * NP; t += nt) { r[D.O_QB + t] = a.qb[t / NP][nbase + t % NP]; r[D.O_Q0 + t] = 0.0; r[D.O_Q2 + t] = 0.0; }
+    for (int t = tid; t < 11 * NP; t += nt) {
+        const double* p = a.nstp[t / NP];
+        r[D.O_NST + t] = p ? p[nbase + t % NP] : 0.0;
+    }
+    for (int t = tid; t < 6 * NP; t += nt) r[D.O_ACCN + t] = 0.0;
+    // quadrature statics (+ forcing sparsity flags), quadrature sums
+    int fl = 0;
+    for (int t = tid; t < 10 * NQ2; t += nt) {
+        const int f = t / NQ2;
+        const double x = a.qstp[f][qbase + t % NQ2];
+        r[(f < 7 ? D.O_QST : D.O_QSTR - 7 * NQ2) + t] = x;
+        if (x != 0.0) fl |= (f == 5) ? PF_COR : (f == 6) ? PF_TWX : (f == 7) ? PF_TWY : (f >= 8) ? PF_GZ : 0;
+    }
+    if (fl) atomicOr(&s_flags, fl);
+    for (int t = tid; t < 6 * NQ2; t += nt) r[D.O_ACCQ + t] = 0.0;
+    for (int t = tid; t < 2 * NQ2; t += nt) r[D.O_ACCQR + t] = 0.0;
+    // face statics: a copy of the owner's coefficients for every side
+    for (int t = tid; t < 4 * 11 * Q; t += nt) {
+        int s = t / (11 * Q), rr = t - s * 11 * Q, f = rr / Q, iq = rr - f * Q;
+        int slot = e * 4 + s, nb = a.M.nbr[slot], nbs = a.M.nbslot[slot];
+        bool left = (nb < 0) || (e < nb);
+        int oslot = left ? slot : nb * 4 + nbs;
+        double x = a.fstp[f][(size_t)oslot * Q + iq];
+        if (f >= 9) x = 1.0 / x;
+        r[D.O_FST + s * D.FSIDE + rr] = x;
+    }
+    for (int t = tid; t < NP; t += nt) {
+        double pb = a.qb[0][nbase + t] + a.nstp[0][nbase + t];
+        u[t] = a.qb[1][nbase + t] / pb; v[t] = a.qb[2][nbase + t] / pb;
+    }
+    __syncthreads();
+    if (tid == 0) { int* hi = reinterpret_cast<int*>(r + 22); hi[0] = s_flags; hi[1] = 0; }
+    for (int t = tid; t < 4 * G; t += nt) {
+        int s = t / G, n = t - s * G, slot = e * 4 + s, nb = a.M.nbr[slot], nbs = a.M.nbslot[slot];
+        int I = face_node(s, n, G);
+        double nx = a.M.fgeom[slot * 3 + 0], ny = a.M.fgeom[slot * 3 + 1];
+        double* vs = r + D.O_VST + s * D.VSIDE + n;
+        double so[5] = {0, 0, 0, 0, 0}, sn[5] = {0, 0, 0, 0, 0};
+        if (a.has_visc) {
+            for (int k = 0; k < 4; ++k) so[k] = a.bdg[k][nbase + I];
+            so[4] = a.pbv[nbase + I];
+            if (nb >= 0) {
+                size_t In = (size_t)nb * NP + face_node(nbs, n, G);
+                for (int k = 0; k < 4; ++k) sn[k] = a.bdg[k][In];
+                sn[4] = a.pbv[In];
+            } else if (nb == NBR_HALO) {
+                for (int k = 0; k < 5; ++k) sn[k] = a.hstat[k * a.hstat_stride + (size_t)nbs * G + n];
+            } else {
+                for (int k = 0; k < 5; ++k) sn[k] = so[k];
+                if (nb == NBR_FREESLIP) reflect4(so, nx, ny, sn);
+            }
+        }
+        for (int k = 0; k < 5; ++k) vs[k * G] = sn[k];
+        vs[5 * G] = a.pbn[(size_t)slot * G + n];
+        // traces of the initial state of the loop (the stage kernel publishes the later ones)
+        double* tr = a.tr + ((size_t)e * 4 + s) * D.TSIDE + n;
+        for (int k = 0; k < 3; ++k) tr[k * G] = a.qb[k][nbase + I];
+        double g4[4] = {0, 0, 0, 0};
+        if (a.has_visc) {
+            const double ksx = a.M.em[e * 5 + 0], ksy = a.M.em[e * 5 + 1], etx = a.M.em[e * 5 + 2], ety = a.M.em[e * 5 + 3];
+            int m = I / G, nn = I - m * G;
+            double dku = 0, deu = 0, dkv = 0, dev = 0;
+            for (int k = 0; k < G; ++k) {
+                dku += c_ops.D[k + G * nn] * u[m * G + k]; deu += c_ops.D[k + G * m] * u[k * G + nn];
+                dkv += c_ops.D[k + G * nn] * v[m * G + k]; dev += c_ops.D[k + G * m] * v[k * G + nn];
+            }
+            g4[0] = ksx * dku + etx * deu; g4[1] = ksy * dku + ety * deu; g4[2] = ksx * dkv + etx * dev; g4[3] = ksy * dkv + ety * dev;
+        }
+        for (int k = 0; k < 4; ++k) tr[(3 + k) * G] = g4[k];
+    }
+}
+// state records -> planes after the loop
+__global__ void k_pair_unpack_qb(int nelem, PairDims D, const double* rec, double* q0, double* q1, double* q2) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nelem * D.NP) return;
+    size_t e = t / D.NP; int I = (int)(t - e * D.NP);
+    const double* r = rec + e * D.REC + D.O_QB;
+    q0[t] = r[I]; q1[t] = r[D.NP + I]; q2[t] = r[2 * D.NP + I];
+}
+// traces of the nodal sums S_pbpert, S_mx, S_my (ACCN fields 3..5) for k_btp_finalize
+__global__ void k_pair_sum_traces(int nelem, PairDims D, const double* rec, double* tr) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nelem * 4 * D.G) return;
+    size_t e = t / (4 * D.G); int r = (int)(t - e * 4 * D.G), s = r / D.G, n = r - s * D.G;
+    int I = face_node(s, n, D.G);
+    double* to = tr + (e * 4 + s) * D.TSIDE + n;
+    for (int k = 0; k < 3; ++k) to[k * D.G] = rec[e * D.REC + D.O_ACCN + (3 + k) * D.NP + I];
+}
+
+template <int G, int Q, int NE, int W>
+static int launch_pair_w(Solver& S, const PairArgs& a) {
+    using R = PairRec<G, Q>;
+    const size_t smem = R::smem_bytes(NE, W);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e1 = cudaFuncSetAttribute(k_btp_stage_pair<G, Q, NE, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e2 = cudaFuncSetAttribute(k_btp_stage_pair<G, Q, NE, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("cudaFuncSetAttribute", "shared memory opt-in failed"); return -1; }
+        cudaFuncSetAttribute(k_btp_stage_pair<G, Q, NE, W, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_btp_stage_pair<G, Q, NE, W, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        configured = true;
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_btp_stage_pair<G, Q, NE, W, true>, 32 * W, smem);
+        S.pair_units_per_wave = nb * W * S.num_sms;
+        if (getenv("HNUMO_DEBUG"))
+            fprintf(stderr, "[hnumo] pair stage kernel NE=%d W=%d: %zu B smem/block, %d blocks/SM (%d warps)\n", NE, W, smem, nb, nb * W);
+    }
+    PairArgs b = a;
+    if (b.pf_dist <= 0) b.pf_dist = S.pair_units_per_wave;
+    const int units = (S.nelem + NE - 1) / NE;
+    const int blocks = (units + W - 1) / W;
+    if (S.has_visc) k_btp_stage_pair<G, Q, NE, W, true><<<blocks, 32 * W, smem, S.stream>>>(b);
+    else k_btp_stage_pair<G, Q, NE, W, false><<<blocks, 32 * W, smem, S.stream>>>(b);
+    S.n_launches++;
+    return 0;
+}
+template <int G, int Q>
+static int launch_pair_t(Solver& S, const PairArgs& a) {
+    if (S.pair_ne == 1) return launch_pair_w<G, Q, 1, 4>(S, a);
+    if (S.pair_warps == 3) return launch_pair_w<G, Q, 2, 3>(S, a);
+    return launch_pair_w<G, Q, 2, 4>(S, a);
+}
+inline int launch_stage_pair(Solver& S, const PairArgs& a) {
+    if (S.ngl == 5 && S.nq == 9) return launch_pair_t<5, 9>(S, a);
+    if (S.ngl == 4 && S.nq == 7) return launch_pair_t<4, 7>(S, a);
+    return -1;
+}
+
+}  // namespace hn

@@ -24,7 +24,7 @@ DECKS = {
     "noslip_rk3": lambda: dict(hn.decks.SHIPPED["double_gyre"], nelx=6, nely=5, x_boundary=(2, 2), kstages=3, botfr=2, cd_mlswe=1e-3),
     "nop3_5layers": lambda: dict(hn.decks.synthetic_double_gyre(5, 5, nop=3, nlayers=5)),
 }
-VARIANTS = [0, 1, 2, 3]  # 0: warp-per-element fused kernel (default), 1: simple reference-form kernel, 2/3: record-layout TMA kernels
+VARIANTS = [0, 1, 2, 3, 4]  # 0: warp-per-element fused kernel, 1: simple reference-form kernel, 2/3: record-layout TMA kernels, 4: element-pair kernel
 
 
 def natural_errors(S, O, deck):
@@ -147,14 +147,14 @@ def test_variants_agree_bitwise_on_mass():
         S.step(3)
         outs.append(S.download_state())
         S.close()
-    for k in (0, 2, 3):
+    for k in (0, 2, 3, 4):
         assert rel_l2(outs[k][1][:, 0], outs[1][1][:, 0]) < 1e-13
         assert rel_l2(outs[k][0][:, :, 0], outs[1][0][:, :, 0]) < 1e-12
 
 
-def _run_partitioned(params, nranks, nsteps, gid):
+def _run_partitioned(params, nranks, nsteps, gid, variant=0):
     decks = [hn.decks.build_deck(params, r, nranks) for r in range(nranks)]
-    solvers = [hn.Solver(d) for d in decks]
+    solvers = [hn.Solver(d, variant=variant) for d in decks]
     for S, d in zip(solvers, decks):
         S.comm_init(hn.local_group_id(gid))
         S.upload_state(d["q_df"], d["qb_df"], d["qprime_df"])
@@ -172,9 +172,10 @@ def _run_partitioned(params, nranks, nsteps, gid):
     return decks, outs
 
 
+@pytest.mark.parametrize("variant", [0, 4])
 @pytest.mark.parametrize("visc", [0.0, 50.0])
 @pytest.mark.parametrize("nranks", [2, 4])
-def test_partitioned_equals_single(nranks, visc):
+def test_partitioned_equals_single(nranks, visc, variant):
     """k-way element partition with face-halo exchange == 1-way; in-process back end on one GPU.
 
     With visc_mlswe == 0 every face term is antisymmetric under (L<->R, n->-n) and the two runs agree to round-off.
@@ -184,12 +185,12 @@ def test_partitioned_equals_single(nranks, visc):
     params = dict(hn.decks.SHIPPED["double_gyre"], nelx=6, nely=8, visc_mlswe=visc)
     tol = 1e-13 if visc == 0.0 else 1e-10
     single = hn.decks.build_deck(params)
-    S = hn.Solver(single)
+    S = hn.Solver(single, variant=variant)
     S.upload_state(single["q_df"], single["qb_df"], single["qprime_df"])
     assert S.step(3) == 0
     q1, qb1, qp1 = S.download_state()
     S.close()
-    decks, outs = _run_partitioned(params, nranks, 3, gid=100 + nranks + (10 if visc else 0))
+    decks, outs = _run_partitioned(params, nranks, 3, gid=100 + nranks + (10 if visc else 0) + 20 * variant, variant=variant)
     npts = single["npts"]
     c = np.sqrt(single["gravity"] * 9928.0)
     for d, (q, qb, qp) in zip(decks, outs):
