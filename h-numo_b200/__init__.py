@@ -19,7 +19,7 @@ from . import decks  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libhnumo_b200.so")
+LIB_PATH = os.environ.get("HNUMO_LIB_PATH", os.path.join(_HERE, "libhnumo_b200.so"))  # override: instrumented debug builds
 _LIB = None
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

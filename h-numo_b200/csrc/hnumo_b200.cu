@@ -29,6 +29,11 @@ Planes palloc(Solver& S, int nplanes, size_t stride) {
 }
 void upload_ops(const Ops& ops) { cudaMemcpyToSymbol(c_ops, &ops, sizeof(Ops)); }
 
+// stage kernel variants: 0 element-record kernel (default; falls back to 1 for orders without an instantiation),
+// 1 simple reference-form kernel, 2/3 record-layout TMA kernels, 5 warp-per-element kernel on the plane layout
+static bool use_fused(const Solver& S) { return S.variant == 5 && stage_fused_supported(S); }
+static bool use_pair(const Solver& S) { return (S.variant == 0 || S.variant == 4) && S.p_rec != nullptr; }
+
 static int threads_for(const Solver& S) {
     int t = S.nq2;
     if (t < 4 * S.nq + 4 * S.ngl) t = 4 * S.nq + 4 * S.ngl;
@@ -162,11 +167,11 @@ static void fill_stage_args(Solver& S, StageArgs& a, Planes& qb, const Planes& q
     for (int v = 0; v < 8; ++v) a.acc_q[v] = S.acc_q[v];
     for (int v = 0; v < 11; ++v) a.acc_f[v] = S.acc_f[v];
     a.g = S.g; a.cd = S.cd; a.alpha_bot = S.alpha[S.nl - 1]; a.visc = S.visc;
-    a.botfr = S.botfr; a.has_visc = S.has_visc; a.acc_graduvb = (S.variant == 1 || !stage_fused_supported(S)); a.pf_blocks = S.pf_blocks;
+    a.botfr = S.botfr; a.has_visc = S.has_visc; a.acc_graduvb = !use_fused(S); a.pf_blocks = S.pf_blocks;
 }
 
 static int launch_stage(Solver& S, const StageArgs& a) {
-    if (S.variant != 1 && stage_fused_supported(S)) return launch_stage_fused(S, a);
+    if (use_fused(S)) return launch_stage_fused(S, a);
     StageSmem L(S.ngl, S.nq);
     k_btp_stage_simple<<<S.nelem, threads_for(S), L.total * sizeof(double), S.stream>>>(a);
     S.n_launches++;
@@ -202,7 +207,7 @@ static int btp_solve_rec(Solver& S, Planes& qb, const Planes& qprime);
 static int btp_solve_pair(Solver& S, Planes& qb, const Planes& qprime);
 // ti_barotropic_ssprk_mlswe (mod_rk_mlswe.F90:19-151)
 int btp_solve(Solver& S, Planes& qb, const Planes& qprime) {
-    if (S.variant == 4 && S.p_rec) return btp_solve_pair(S, qb, qprime);
+    if (use_pair(S)) return btp_solve_pair(S, qb, qprime);
     if ((S.variant == 2 || S.variant == 3) && S.r_geoc) return btp_solve_rec(S, qb, qprime);
     cudaMemsetAsync(S.acc_n.p, 0, S.acc_n.stride * S.acc_n.n * sizeof(double), S.stream);
     cudaMemsetAsync(S.acc_q.p, 0, S.acc_q.stride * S.acc_q.n * sizeof(double), S.stream);
@@ -248,7 +253,7 @@ int btp_solve(Solver& S, Planes& qb, const Planes& qprime) {
         for (int v = 0; v < 8; ++v) f.acc_q[v] = S.acc_q[v];
         for (int v = 0; v < 11; ++v) f.acc_f[v] = S.acc_f[v];
         f.tr = S.trace[cur].p; f.tr_vs = S.trace[cur].stride; f.tr_rs = S.ngl;
-        f.en = S.npts; f.eq = S.nq2; f.ef = S.nq; f.derive_graduvb = !(S.variant == 1 || !stage_fused_supported(S));
+        f.en = S.npts; f.eq = S.nq2; f.ef = S.nq; f.derive_graduvb = use_fused(S);
         for (int v = 0; v < 12; ++v) f.ave_q[v] = S.ave_q[v];
         for (int v = 0; v < 16; ++v) f.ave_f[v] = S.ave_f[v];
         for (int v = 0; v < 7; ++v) f.ave_n[v] = S.ave_n[v];
@@ -633,6 +638,10 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     for (int i = 0; i < S.ngl * S.ngl; ++i) S.ops.D[i] = d->dpsi[i];
     for (int i = 0; i < S.nq; ++i) S.ops.wq[i] = d->wnq[i];
     for (int i = 0; i < S.ngl; ++i) S.ops.wg[i] = d->wgl[i];
+    for (int n = 0; n < S.ngl; ++n)
+        for (int i = 0; i < S.nq; ++i) { S.ops.AT[i + S.nq * n] = S.ops.A[n + S.ngl * i]; S.ops.BT[i + S.nq * n] = S.ops.B[n + S.ngl * i]; }
+    for (int n = 0; n < S.ngl; ++n)
+        for (int k = 0; k < S.ngl; ++k) S.ops.DT[n + S.ngl * k] = S.ops.D[k + S.ngl * n];
     upload_ops(S.ops);
     upload_fused_ops(S.ops, S.ngl, S.nq);
     // connectivity from face(8,nface)
@@ -755,7 +764,7 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     if (const char* ev = getenv("HNUMO_PAIR_NE")) S.pair_ne = atoi(ev);          // tuning overrides (tests, sweeps)
     if (const char* ev = getenv("HNUMO_PAIR_WARPS")) S.pair_warps = atoi(ev);
     if (const char* ev = getenv("HNUMO_PAIR_PREFETCH")) S.pair_prefetch = atoi(ev);
-    if (S.variant == 4 && stage_pair_supported(S)) {
+    if ((S.variant == 0 || S.variant == 4) && stage_pair_supported(S)) {
         const PairDims D = make_pairdims(S.ngl, S.nq);
         const size_t NE = (size_t)S.nelem;
         S.p_rec = dalloc(S, NE * D.REC); S.p_accf = dalloc(S, NE * 4 * D.ASIDE);
@@ -961,6 +970,16 @@ int64_t hnumo_get_array(hnumo_handle_t h, const char* name, double* out, int64_t
     if (nm == "zbot_face") return copy_face({S.zbf_l, S.zbf_r}, false);
     if (nm == "a_bcl") return copy_planes({S.a_bcl}, NP);
     if (nm == "b_bcl") return copy_planes({S.b_bcl}, NP);
+#ifdef HN_PAIR_TIMING
+    if (nm == "pair_timing") {
+        const int64_t n = (int64_t)HN_PT_UNITS * HN_PT_SLOTS;
+        if (n > capacity) return -4;
+        std::vector<long long> tmp(n);
+        cudaMemcpyFromSymbol(tmp.data(), g_pair_timing, n * sizeof(long long));
+        for (int64_t i = 0; i < n; ++i) out[i] = (double)tmp[i];
+        return n;
+    }
+#endif
     set_error("hnumo_get_array", "unknown array name");
     return -5;
 }

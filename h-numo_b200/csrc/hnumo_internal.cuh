@@ -38,12 +38,17 @@ struct Mesh {
 };
 
 // 1-D operator tables (constant memory copies are in hnumo_ops.cu)
-struct Ops {
+struct alignas(16) Ops {
     double A[HN_MAXNGL * HN_MAXNQ];   // psiq(n,i)   -> A[n + ngl*i]
     double B[HN_MAXNGL * HN_MAXNQ];   // dpsiq(n,i)
     double D[HN_MAXNGL * HN_MAXNGL];  // dpsi(k,n) = l_k'(x_n) -> D[k + ngl*n]
     double wq[HN_MAXNQ];
     double wg[HN_MAXNGL];
+    // transposed copies (output index fastest) for the line contractions of stage_pair.cuh: consecutive entries feed
+    // independent accumulators, and one 128-bit uniform load brings two of them
+    alignas(16) double AT[HN_MAXNGL * HN_MAXNQ];   // AT[i + nq*n] = A[n + ngl*i]
+    alignas(16) double BT[HN_MAXNGL * HN_MAXNQ];
+    alignas(16) double DT[HN_MAXNGL * HN_MAXNGL];  // DT[n + ngl*k] = D[k + ngl*n]
 };
 
 struct Planes {  // convenience: contiguous set of planes
@@ -131,7 +136,7 @@ struct Solver {
     void* d_nbx = nullptr;
     // record layout of the element-pair stage kernel (stage_pair.cuh): one record per element, face sums, traces
     double *p_rec = nullptr, *p_accf = nullptr, *p_tr[2] = {nullptr, nullptr};
-    int pair_ne = 2, pair_warps = 4, pair_prefetch = 3, pair_pf_dist = 0, pair_units_per_wave = 0;
+    int pair_ne = 1, pair_warps = 4, pair_prefetch = 1, pair_pf_dist = 0, pair_units_per_wave = 0;
     int num_sms = 148, tma_blocks_per_sm = 0;
     int use_graph = 0;
     int pf_blocks = -1;   // L2 prefetch distance of the fused stage kernel, in thread blocks

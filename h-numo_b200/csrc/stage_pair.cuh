@@ -60,16 +60,22 @@ struct PairRec {
     static constexpr int REC = O_ACCQR + pr_pad2(2 * NQ2);
     static constexpr int ASIDE = pr_pad2(11 * Q);   // face sums, separate array [slot][ASIDE]
     static constexpr int TSIDE = pr_pad2(7 * G);    // trace record [slot][7][G]: pbpert mx my G0..G3
-    // shared memory per warp, in units of NE doubles
+    // shared memory per warp, in units of NE doubles.  The strides SX, ST, TM are padded so that in the line phases
+    // (lane = Q*f + i, or lane = G*f + m) the word index is congruent to the lane number modulo 16: no bank conflicts
+    // (profiles/smem_conflicts.py).
+    static constexpr int pick(int lo, int mod) { return lo + ((mod - lo) % 16 + 16) % 16; }
+    static constexpr int SX = pick(NQ2, Q);         // stride of the quadrature-point arrays
+    static constexpr int TM = 11;                   // row stride of the pass-1 arrays T[f][m][i]
+    static constexpr int ST = pick((G - 1) * TM + Q, Q);
     static constexpr int S_NOD = 0;                 // 0 dpp 1 mx 2 my 3 pb 4 pp 5 up 6 vp 7 u 8 v ; later 4..7 = LDG flux variable
     static constexpr int S_X = S_NOD + 9 * NP;      // 8 quadrature-point arrays; later rhs, face traces, face fluxes
     static constexpr int X_RHS = 0, X_FL = 3 * NP, X_FR = X_FL + 16 * G, X_LF = X_FR + 16 * G, X_FF = X_LF + 8 * G;
-    static constexpr int S_T = S_X + 8 * NQ2;       // pass-1 results; later interpolated traces, projected face fluxes
-    static constexpr int T_SZ = 8 * PER;
+    static constexpr int S_T = S_X + 8 * SX;        // pass-1 results; later interpolated traces, projected face fluxes
+    static constexpr int T_SZ = 8 * ST;
     static constexpr int S_L = S_T + T_SZ;          // LDG: 0..3 gradient lines / laplacian lines, 4..7 G, 8..11 Z
     static constexpr int S_TOTAL = S_L + 12 * NP;
-    static_assert(X_FF + 12 * Q <= 8 * NQ2, "face work does not fit in X");
-    static_assert(32 * Q <= T_SZ && 7 * PER <= T_SZ, "T too small");
+    static_assert(X_FF + 12 * Q <= 8 * SX, "face work does not fit in X");
+    static_assert(32 * Q <= T_SZ && 7 * ST <= T_SZ, "T too small");
     static size_t smem_bytes(int ne, int warps) { return (size_t)warps * ((size_t)S_TOTAL * ne + (size_t)HDR * ne) * sizeof(double); }
 };
 
@@ -99,6 +105,16 @@ template <> struct PV<2> {
 
 #define PR_FORC _Pragma("unroll") for (int c = 0; c < NE; ++c)
 
+// phase time stamps of a sample of warps (debug builds only: -DHN_PAIR_TIMING)
+#ifdef HN_PAIR_TIMING
+#define HN_PT_SLOTS 16
+#define HN_PT_UNITS 4096
+__device__ long long g_pair_timing[HN_PT_UNITS * HN_PT_SLOTS];
+#define PR_STAMP(k) do { if (lane == 0 && (unit % 61) == 0 && unit / 61 < HN_PT_UNITS) g_pair_timing[(unit / 61) * HN_PT_SLOTS + (k)] = clock64(); } while (0)
+#else
+#define PR_STAMP(k) do { } while (0)
+#endif
+
 // reciprocal: hardware seed + two Newton steps (<= 1 ulp); the IEEE division sequence costs ~20 issue slots and a
 // slow-path branch per use, and there are 14 of them per element and stage
 __device__ __forceinline__ double pr_rcp(double a) {
@@ -115,61 +131,75 @@ __device__ __forceinline__ double pr_rcp(double a) {
 #endif
 }
 
+// running sums: fire-and-forget FP64 reduction at the L2 (RED.E.ADD.F64).  Every address receives exactly one add per
+// launch, so the result is bitwise the one of load-add-store; no register is tied up by the old value and no load
+// has to be waited for.
+#if defined(HN_PAIR_DIAG) && HN_PAIR_DIAG == 1
+__device__ __forceinline__ void pr_red(double* p, double v) { *p = v; }          // timing diagnostics only (wrong sums)
+#elif defined(HN_PAIR_DIAG) && HN_PAIR_DIAG == 2
+__device__ __forceinline__ void pr_red(double* p, double v) { }
+#else
+__device__ __forceinline__ void pr_red(double* p, double v) { atomicAdd(p, v); }
+#endif
+
 __device__ __forceinline__ void pr_prefetch_l2(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-// ---- line contractions on NE elements at once; the operator entry is a uniform-register operand shared by the NE FMAs
+// ---- line contractions on NE elements at once.  The operator entry is a uniform-register operand shared by the NE
+// FMAs.  Loop order: contraction index outside, OUTPUT index inside -- consecutive FMAs belong to independent
+// accumulators (an FP64 FMA has ~8 cycles of dependent-issue latency; the chain-serial order costs 4x the pipe time).
 // out[i] = sum_n M(n,i) in[n], nodes -> quadrature points
 template <int NE, int G, int Q, bool DERIV, int SS, int DS>
 __device__ __forceinline__ void pl_n2q(const typename PV<NE>::T* src, typename PV<NE>::T* dst) {
-    double in[G][NE];
+    double in[G][NE], s[Q][NE];
 #pragma unroll
     for (int n = 0; n < G; ++n) PV<NE>::ld(src + n * SS, in[n]);
 #pragma unroll
-    for (int i = 0; i < Q; ++i) {
-        double s[NE];
-        PR_FORC s[c] = 0.0;
+    for (int n = 0; n < G; ++n) {
 #pragma unroll
-        for (int n = 0; n < G; ++n) {
-            const double mv = DERIV ? c_ops.B[n + G * i] : c_ops.A[n + G * i];
-            PR_FORC s[c] = fma(mv, in[n][c], s[c]);
+        for (int i = 0; i < Q; ++i) {
+            const double mv = DERIV ? c_ops.BT[i + Q * n] : c_ops.AT[i + Q * n];
+            if (n == 0) { PR_FORC s[i][c] = mv * in[0][c]; }
+            else { PR_FORC s[i][c] = fma(mv, in[n][c], s[i][c]); }
         }
-        PV<NE>::st(dst + i * DS, s);
     }
+#pragma unroll
+    for (int i = 0; i < Q; ++i) PV<NE>::st(dst + i * DS, s[i]);
 }
 // acc[n] (+)= sum_i M(n,i) in[i], quadrature points -> nodes (weak-form transpose)
-template <int NE, int G, int Q, bool DERIV, int SS>
+template <int NE, int G, int Q, bool DERIV, int SS, bool FIRST>
 __device__ __forceinline__ void pl_q2n_acc(const typename PV<NE>::T* src, double (&acc)[G][NE]) {
     double in[Q][NE];
 #pragma unroll
     for (int i = 0; i < Q; ++i) PV<NE>::ld(src + i * SS, in[i]);
 #pragma unroll
-    for (int n = 0; n < G; ++n) {
+    for (int i = 0; i < Q; ++i) {
 #pragma unroll
-        for (int i = 0; i < Q; ++i) {
+        for (int n = 0; n < G; ++n) {
             const double mv = DERIV ? c_ops.B[n + G * i] : c_ops.A[n + G * i];
-            PR_FORC acc[n][c] = fma(mv, in[i][c], acc[n][c]);
+            if (FIRST && i == 0) { PR_FORC acc[n][c] = mv * in[0][c]; }
+            else { PR_FORC acc[n][c] = fma(mv, in[i][c], acc[n][c]); }
         }
     }
 }
 // collocation derivative along a nodal line (runtime stride): out[n] = sum_k D(k,n) in[k]  or transposed D(n,k)
 template <int NE, int G, bool TRANSP>
 __device__ __forceinline__ void pl_grad(const typename PV<NE>::T* src, typename PV<NE>::T* dst, int stride) {
-    double in[G][NE];
+    double in[G][NE], s[G][NE];
 #pragma unroll
     for (int k = 0; k < G; ++k) PV<NE>::ld(src + k * stride, in[k]);
 #pragma unroll
-    for (int n = 0; n < G; ++n) {
-        double s[NE];
-        PR_FORC s[c] = 0.0;
+    for (int k = 0; k < G; ++k) {
 #pragma unroll
-        for (int k = 0; k < G; ++k) {
-            const double mv = TRANSP ? c_ops.D[n + G * k] : c_ops.D[k + G * n];
-            PR_FORC s[c] = fma(mv, in[k][c], s[c]);
+        for (int n = 0; n < G; ++n) {
+            const double mv = TRANSP ? c_ops.D[n + G * k] : c_ops.DT[n + G * k];
+            if (k == 0) { PR_FORC s[n][c] = mv * in[0][c]; }
+            else { PR_FORC s[n][c] = fma(mv, in[k][c], s[n][c]); }
         }
-        PV<NE>::st(dst + n * stride, s);
     }
+#pragma unroll
+    for (int n = 0; n < G; ++n) PV<NE>::st(dst + n * stride, s[n]);
 }
 
 template <int G>
@@ -177,18 +207,21 @@ __device__ __forceinline__ int pr_face_node(int s, int n) {
     return s == 0 ? n : s == 1 ? (G - 1) * G + n : s == 2 ? n * G : n * G + G - 1;
 }
 
-template <int G, int Q, int NE, int W, bool VISC>
+// BOTFR: 0 none, 1 linear bottom drag, 2 quadratic bottom drag (mod_rhs_btp.F90:149-169) -- compile time, so that the
+// pointwise phases are single basic blocks the scheduler can interleave
+template <int G, int Q, int NE, int W, bool VISC, int BOTFR>
 __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 168) : 128) k_btp_stage_pair(const PairArgs a) {
     using R = PairRec<G, Q>;
     using V = PV<NE>;
     typedef typename V::T VT;
-    constexpr int NP = R::NP, NQ2 = R::NQ2, PER = R::PER;
+    constexpr int NP = R::NP, NQ2 = R::NQ2, SX = R::SX, ST = R::ST, TM = R::TM;
     constexpr int NQIT = (NQ2 + 31) / 32, NFIT = (4 * Q + 31) / 32;
     static_assert(NP <= 32 && 4 * G <= 32 && 3 * Q <= 32 && 12 <= 32, "polynomial order too high for this lane mapping");
     extern __shared__ __align__(16) double sm_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int unit = blockIdx.x * W + warp;
     if (unit * NE >= a.nelem) return;
+    PR_STAMP(0);
     double* smw = sm_all + (size_t)warp * ((size_t)R::S_TOTAL * NE + (size_t)R::HDR * NE);
     double* hdr = smw;                                   // [NE][HDR], plain doubles
     VT* sv = reinterpret_cast<VT*>(smw + R::HDR * NE);
@@ -206,33 +239,17 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
         if (!ok[c]) e[c] = a.nelem - 1;
         rec[c] = a.rec + (size_t)e[c] * R::REC;
     }
-    // ---- 0. header -> shared memory; pull the rest of the record into L2 (one instruction per element)
-    if (lane < R::HDR) { PR_FORC hdr[c * R::HDR + lane] = rec[c][lane]; }
-    if (a.prefetch && lane < NE) {
-        const double* p = (lane == 0) ? rec[0] : rec[NE - 1];
-        if (a.prefetch & 1) {
-            pr_prefetch_l2(p + R::O_QST, (uint32_t)((R::O_Q0 - R::O_QST) * sizeof(double)));
-            if (a.load_q0) pr_prefetch_l2(p + R::O_Q0, (uint32_t)(R::QBSZ * sizeof(double)));
-            if (a.load_q2) pr_prefetch_l2(p + R::O_Q2, (uint32_t)(R::QBSZ * sizeof(double)));
-        }
-        // the head of the record (header, state, nodal statics and sums) of the unit that follows one wave later
-        if ((a.prefetch & 2) && (long)(unit + a.pf_dist) * NE + lane < a.nelem)
-            pr_prefetch_l2(p + (size_t)a.pf_dist * NE * R::REC, (uint32_t)(R::O_QST * sizeof(double)));
-    }
-    const bool botfr = a.botfr != 0;
+    constexpr bool botfr = BOTFR != 0;
 
     // ---- 1. nodal loads + nodal sums (mod_rk_mlswe.F90:90-92)
     double pbp[NE], pv[NE], bd[4][NE];   // kept by lane I < NP for the LDG flux variable and the update
+    double dpp[NE], mx[NE], my[NE], oop[NE], pp[NE], up[NE], vp[NE];
     if (lane < NP) {
         const int I = lane;
-        double dpp[NE], mx[NE], my[NE], oop[NE], c0[NE], c1[NE], c2[NE], c3[NE], c4[NE], c5[NE];
-        double pp[NE], up[NE], vp[NE];
         PR_FORC {
             const double* r = rec[c];
             dpp[c] = r[R::O_QB + I]; mx[c] = r[R::O_QB + NP + I]; my[c] = r[R::O_QB + 2 * NP + I];
             pbp[c] = r[R::O_NST + I]; oop[c] = r[R::O_NST + NP + I];
-            c0[c] = r[R::O_ACCN + I]; c1[c] = r[R::O_ACCN + NP + I]; c2[c] = r[R::O_ACCN + 2 * NP + I];
-            c3[c] = r[R::O_ACCN + 3 * NP + I]; c4[c] = r[R::O_ACCN + 4 * NP + I]; c5[c] = r[R::O_ACCN + 5 * NP + I];
             if (botfr) { pp[c] = r[R::O_NST + 3 * NP + I]; up[c] = r[R::O_NST + 4 * NP + I]; vp[c] = r[R::O_NST + 5 * NP + I]; }
             if (VISC) {
                 pv[c] = r[R::O_NST + 6 * NP + I];
@@ -240,6 +257,39 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
                 for (int k = 0; k < 4; ++k) bd[k][c] = r[R::O_NST + (7 + k) * NP + I];
             }
         }
+    }
+    // quadrature-point statics of all blocks of 32 points (7 per point and element): issued with the first loads, they
+    // are consumed three phases later.  Lanes past the last point re-read it (branch-free phases; they never store sums).
+    double qs[NQIT][7][NE];
+#pragma unroll
+    for (int it = 0; it < NQIT; ++it) {
+        const int q = min(it * 32 + lane, NQ2 - 1);
+        PR_FORC {
+            const double* rs = rec[c] + R::O_QST + q;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) qs[it][k][c] = rs[k * NQ2];
+        }
+    }
+    // ---- 0. header -> shared memory (issued after the nodal loads so that the two round trips overlap); the tail of
+    //          the record -> L2 with one bulk prefetch per element
+    {
+        double hv[NE];
+        if (lane < R::HDR) { PR_FORC hv[c] = rec[c][lane]; }
+        if (a.prefetch && lane < NE) {
+            const double* p = (lane == 0) ? rec[0] : rec[NE - 1];
+            if (a.prefetch & 1) {
+                pr_prefetch_l2(p + R::O_QST, (uint32_t)((R::O_Q0 - R::O_QST) * sizeof(double)));
+                if (a.load_q0) pr_prefetch_l2(p + R::O_Q0, (uint32_t)(R::QBSZ * sizeof(double)));
+                if (a.load_q2) pr_prefetch_l2(p + R::O_Q2, (uint32_t)(R::QBSZ * sizeof(double)));
+            }
+            // the head of the record (header, state, nodal statics and sums) of the unit that follows one wave later
+            if ((a.prefetch & 2) && (long)(unit + a.pf_dist) * NE + lane < a.nelem)
+                pr_prefetch_l2(p + (size_t)a.pf_dist * NE * R::REC, (uint32_t)(R::O_QST * sizeof(double)));
+        }
+        if (lane < R::HDR) { PR_FORC hdr[c * R::HDR + lane] = hv[c]; }
+    }
+    if (lane < NP) {
+        const int I = lane;
         double pb[NE], u[NE], v[NE];
         PR_FORC {
             pb[c] = dpp[c] + pbp[c];
@@ -248,8 +298,8 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
             const double t = 1.0 + dpp[c] * oop[c];
             if (ok[c]) {
                 double* r = rec[c];
-                r[R::O_ACCN + I] = c0[c] + t * t; r[R::O_ACCN + NP + I] = c1[c] + u[c]; r[R::O_ACCN + 2 * NP + I] = c2[c] + v[c];
-                r[R::O_ACCN + 3 * NP + I] = c3[c] + dpp[c]; r[R::O_ACCN + 4 * NP + I] = c4[c] + mx[c]; r[R::O_ACCN + 5 * NP + I] = c5[c] + my[c];
+                pr_red(r + R::O_ACCN + I, t * t); pr_red(r + R::O_ACCN + NP + I, u[c]); pr_red(r + R::O_ACCN + 2 * NP + I, v[c]);
+                pr_red(r + R::O_ACCN + 3 * NP + I, dpp[c]); pr_red(r + R::O_ACCN + 4 * NP + I, mx[c]); pr_red(r + R::O_ACCN + 5 * NP + I, my[c]);
             }
         }
         V::st(nod + 0 * NP + I, dpp); V::st(nod + 1 * NP + I, mx); V::st(nod + 2 * NP + I, my); V::st(nod + 3 * NP + I, pb);
@@ -257,6 +307,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
         V::st(nod + 7 * NP + I, u); V::st(nod + 8 * NP + I, v);
     }
     __syncwarp();
+    PR_STAMP(1);
     // per-element geometry and flags (registers)
     double ksx[NE], ksy[NE], etx[NE], ety[NE], J[NE];
     int flags[NE];
@@ -265,23 +316,35 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
         ksx[c] = h[0]; ksy[c] = h[1]; etx[c] = h[2]; ety[c] = h[3]; J[c] = h[4];
         flags[c] = reinterpret_cast<const int*>(h + 22)[0];
     }
-    // neighbour traces and owned face sums -> L2 (the header has just told us where they are)
-    if ((a.prefetch & 1) && lane < 4 * NE) {
-        const int c = lane >> 2, s = lane & 3;
-        const int* hi = reinterpret_cast<const int*>(hdr + c * R::HDR + 18);
-        const int nb = hi[s], tr = hi[4 + s];
-        if (tr >= 0) pr_prefetch_l2(a.tr_in + (size_t)tr * R::TSIDE, R::TSIDE * 8u);
-        if (nb < 0 || e[c] < nb) pr_prefetch_l2(a.accf + ((size_t)e[c] * 4 + s) * R::ASIDE, R::ASIDE * 8u);
+    // neighbour traces and owned face sums -> L2 (the header has just told us where they are): one 128-byte line per lane
+    if (a.prefetch & 1) {
+        constexpr int TL = (R::TSIDE * 8 + 127) / 128 + 1, AL = (R::ASIDE * 8 + 127) / 128 + 1;
+        PR_FORC {
+            const int* hi = reinterpret_cast<const int*>(hdr + c * R::HDR + 18);
+            if (lane < 4 * TL) {
+                const int s = lane / TL, ln = lane - s * TL, tr = hi[4 + s];
+                const char* p = reinterpret_cast<const char*>(a.tr_in + (size_t)(tr >= 0 ? tr : 0) * R::TSIDE);
+                const char* q = reinterpret_cast<const char*>((uintptr_t)p & ~(uintptr_t)127) + ln * 128;
+                if (tr >= 0 && q < p + R::TSIDE * 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+            }
+            if (lane < 4 * AL) {
+                const int s = lane / AL, ln = lane - s * AL, nb = hi[s];
+                const char* p = reinterpret_cast<const char*>(a.accf + ((size_t)e[c] * 4 + s) * R::ASIDE);
+                const char* q = reinterpret_cast<const char*>((uintptr_t)p & ~(uintptr_t)127) + ln * 128;
+                if ((nb < 0 || e[c] < nb) && q < p + R::ASIDE * 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+            }
+        }
     }
+    PR_STAMP(12);
     // ---- 2. sum factorisation, pass 1: one nodal row per lane -> T[f][m][i]; LDG gradient lines -> Lr[0..3]
     {
         if (lane < 4 * G) {
             const int f = lane / G, m = lane - f * G;
-            pl_n2q<NE, G, Q, false, 1, 1>(nod + f * NP + m * G, T + f * PER + m * Q);
+            pl_n2q<NE, G, Q, false, 1, 1>(nod + f * NP + m * G, T + f * ST + m * TM);
         }
         if (botfr && lane < 3 * G) {
             const int f = 4 + lane / G, m = lane % G;
-            pl_n2q<NE, G, Q, false, 1, 1>(nod + f * NP + m * G, T + f * PER + m * Q);
+            pl_n2q<NE, G, Q, false, 1, 1>(nod + f * NP + m * G, T + f * ST + m * TM);
         }
         if (VISC && lane < 4 * G) {
             const int kind = lane / (2 * G), r = lane - kind * 2 * G, f = r / G, l = r - f * G;
@@ -289,33 +352,15 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
             pl_grad<NE, G, false>(nod + (7 + f) * NP + off, Lr + (2 * kind + f) * NP + off, stride);
         }
     }
-    // quadrature-point operands of a block of 32 points: 7 statics + 6 running sums per element, loaded one block ahead
-    struct QL { double s[7][NE]; double acc[6][NE]; };
-    auto qload = [&](int it, QL& L) {
-        const int q = it * 32 + lane;
-        if (q < NQ2) {
-            PR_FORC {
-                const double* rs = rec[c] + R::O_QST + q;
-                const double* ra = rec[c] + R::O_ACCQ + q;
-#pragma unroll
-                for (int k = 0; k < 5; ++k) L.s[k][c] = rs[k * NQ2];
-                L.s[5][c] = (flags[c] & PF_COR) ? rs[5 * NQ2] : 0.0;
-                L.s[6][c] = (flags[c] & PF_TWX) ? rs[6 * NQ2] : 0.0;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) L.acc[k][c] = ra[k * NQ2];
-            }
-        }
-    };
-    QL qbuf[2];
-    qload(0, qbuf[0]);
     __syncwarp();
+    PR_STAMP(2);
     // ---- 3. pass 2: one quadrature column per lane -> X[f][j][i]; LDG: G = grad(ub,vb), flux variable, weighted metric terms
     {
         const int nlines = (botfr ? 7 : 4) * Q;
 #pragma unroll 1
         for (int it = lane; it < nlines; it += 32) {
             const int f = it / Q, i = it - f * Q;
-            pl_n2q<NE, G, Q, false, Q, Q>(T + f * PER + i, X + f * NQ2 + i);
+            pl_n2q<NE, G, Q, false, TM, Q>(T + f * ST + i, X + f * SX + i);
         }
         if (VISC && lane < NP) {
             const int I = lane, m = I / G, n = I - m * G;
@@ -338,18 +383,18 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
         }
     }
     __syncwarp();
+    PR_STAMP(3);
     // ---- 4. pointwise physics at the quadrature points (mod_rhs_btp.F90:136-192); the fluxes overwrite X in place
 #pragma unroll
     for (int it = 0; it < NQIT; ++it) {
-        QL& qcur = qbuf[it & 1];
-        if (it + 1 < NQIT) qload(it + 1, qbuf[(it + 1) & 1]);
-        const int q = it * 32 + lane;
-        if (q < NQ2) {
+        const int q = min(it * 32 + lane, NQ2 - 1);
+        const bool qvalid = (it + 1) * 32 <= NQ2 || it * 32 + lane < NQ2;
+        {
             const int j = q / Q, i = q - j * Q;
             const double w0 = c_ops.wq[i] * c_ops.wq[j];
             double dpp[NE], udp[NE], vdp[NE], dp[NE], pp[NE], up[NE], vp[NE];
-            V::ld(X + 0 * NQ2 + q, dpp); V::ld(X + 1 * NQ2 + q, udp); V::ld(X + 2 * NQ2 + q, vdp); V::ld(X + 3 * NQ2 + q, dp);
-            if (botfr) { V::ld(X + 4 * NQ2 + q, pp); V::ld(X + 5 * NQ2 + q, up); V::ld(X + 6 * NQ2 + q, vp); }
+            V::ld(X + 0 * SX + q, dpp); V::ld(X + 1 * SX + q, udp); V::ld(X + 2 * SX + q, vdp); V::ld(X + 3 * SX + q, dp);
+            if (botfr) { V::ld(X + 4 * SX + q, pp); V::ld(X + 5 * SX + q, up); V::ld(X + 6 * SX + q, vp); }
             double o0[NE], o1[NE], o2[NE], o3[NE], o4[NE], o5[NE], o6[NE], o7[NE];
             PR_FORC {
                 const double wq = w0 * J[c];
@@ -358,17 +403,15 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
                 double tb_u = 0.0, tb_v = 0.0;
                 if (botfr) {
                     const double ubot = up[c] + ub, vbot = vp[c] + vb;
-                    const double spd = (a.botfr == 1) ? a.cd_g * pp[c] : a.cd_alpha * sqrt(ubot * ubot + vbot * vbot);
+                    const double spd = (BOTFR == 1) ? a.cd_g * pp[c] : a.cd_alpha * sqrt(ubot * ubot + vbot * vbot);
                     tb_u = spd * ubot; tb_v = spd * vbot;
                 }
-                const double s_oop = qcur.s[0][c], s_H = qcur.s[1][c], s_uu = qcur.s[2][c], s_uv = qcur.s[3][c], s_vv = qcur.s[4][c];
-                const double fcor = qcur.s[5][c], s_twx = qcur.s[6][c];
-                double s_twy = 0.0, s_gzx = 0.0, s_gzy = 0.0;
-                if (flags[c] & (PF_TWY | PF_GZ)) {   // rare forcing fields are read on demand
-                    const double* rs = rec[c] + R::O_QSTR + q;
-                    if (flags[c] & PF_TWY) s_twy = rs[0];
-                    if (flags[c] & PF_GZ) { s_gzx = rs[NQ2]; s_gzy = rs[2 * NQ2]; }
-                }
+                const double s_oop = qs[it][0][c], s_H = qs[it][1][c], s_uu = qs[it][2][c], s_uv = qs[it][3][c], s_vv = qs[it][4][c];
+                const double fcor = qs[it][5][c], s_twx = qs[it][6][c];
+                // rare forcing fields are read on demand (predicated loads, no branch)
+                const double* rs = rec[c] + R::O_QSTR + q;
+                const double s_twy = (flags[c] & PF_TWY) ? rs[0] : 0.0;
+                const double s_gzx = (flags[c] & PF_GZ) ? rs[NQ2] : 0.0, s_gzy = (flags[c] & PF_GZ) ? rs[2 * NQ2] : 0.0;
                 const double sc_x = fcor * vdp[c] + a.g * (s_twx - tb_u) - a.g * dp[c] * s_gzx;
                 const double sc_y = -fcor * udp[c] + a.g * (s_twy - tb_v) - a.g * dp[c] * s_gzy;
                 const double ope = 1.0 + dpp[c] * s_oop;
@@ -377,11 +420,11 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
                 const double qu = ub * udp[c] + ope * s_uu;
                 const double quv = ub * vdp[c] + ope * s_uv;
                 const double qv = vb * vdp[c] + ope * s_vv;
-                if (ok[c]) {
+                if (qvalid && ok[c]) {
                     double* ra = rec[c] + R::O_ACCQ + q;
-                    ra[0] = qcur.acc[0][c] + qu; ra[NQ2] = qcur.acc[1][c] + qv; ra[2 * NQ2] = qcur.acc[2][c] + quv;
-                    ra[3 * NQ2] = qcur.acc[3][c] + ope2; ra[4 * NQ2] = qcur.acc[4][c] + ub; ra[5 * NQ2] = qcur.acc[5][c] + vb;
-                    if (a.botfr == 2) { double* rr_ = rec[c] + R::O_ACCQR + q; rr_[0] += tb_u; rr_[NQ2] += tb_v; }
+                    pr_red(ra, qu); pr_red(ra + NQ2, qv); pr_red(ra + 2 * NQ2, quv);
+                    pr_red(ra + 3 * NQ2, ope2); pr_red(ra + 4 * NQ2, ub); pr_red(ra + 5 * NQ2, vb);
+                    if (BOTFR == 2) { double* rr_ = rec[c] + R::O_ACCQR + q; pr_red(rr_, tb_u); pr_red(rr_ + NQ2, tb_v); }
                 }
                 const double Fx2 = Hq + qu, Fy3 = Hq + qv;
                 o0[c] = wq * (ksx[c] * udp[c] + ksy[c] * vdp[c]);   // Fk1
@@ -393,8 +436,9 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
                 o6[c] = wq * (ksx[c] * quv + ksy[c] * Fy3);         // Fk3
                 o7[c] = wq * (etx[c] * quv + ety[c] * Fy3);         // Fe3
             }
-            V::st(X + 0 * NQ2 + q, o0); V::st(X + 1 * NQ2 + q, o1); V::st(X + 2 * NQ2 + q, o2); V::st(X + 3 * NQ2 + q, o3);
-            V::st(X + 4 * NQ2 + q, o4); V::st(X + 5 * NQ2 + q, o5); V::st(X + 6 * NQ2 + q, o6); V::st(X + 7 * NQ2 + q, o7);
+            // array order in X: Fk1 Fk2 Fk3 | Fe1 Fe2 Fe3 | S2 S3  (field f of a kind at a constant offset: conflict-free scatter)
+            V::st(X + 0 * SX + q, o0); V::st(X + 3 * SX + q, o1); V::st(X + 6 * SX + q, o2); V::st(X + 1 * SX + q, o3);
+            V::st(X + 4 * SX + q, o4); V::st(X + 7 * SX + q, o5); V::st(X + 2 * SX + q, o6); V::st(X + 5 * SX + q, o7);
         }
     }
     // neighbour traces and the neighbour's viscosity statics of face node (s,n), issued one phase ahead
@@ -417,27 +461,25 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
         }
     }
     __syncwarp();
+    PR_STAMP(4);
     // ---- 5. scatter pass 1 (contraction over j): lane (f,i) -> TB_f = A.Fk_f, TA_f = B.Fe_f + A.S_f, as T[f][m][i], T[3+f][m][i]
     if (lane < 3 * Q) {
         const int f = lane / Q, i = lane - f * Q;
         double tb[G][NE], ta[G][NE];
+        pl_q2n_acc<NE, G, Q, false, Q, true>(X + f * SX + i, tb);
+        pl_q2n_acc<NE, G, Q, true, Q, true>(X + (3 + f) * SX + i, ta);
+        if (f > 0) pl_q2n_acc<NE, G, Q, false, Q, false>(X + (5 + f) * SX + i, ta);
 #pragma unroll
-        for (int m = 0; m < G; ++m) { PR_FORC { tb[m][c] = 0.0; ta[m][c] = 0.0; } }
-        pl_q2n_acc<NE, G, Q, false, Q>(X + (3 * f) * NQ2 + i, tb);
-        pl_q2n_acc<NE, G, Q, true, Q>(X + (3 * f + 1) * NQ2 + i, ta);
-        if (f > 0) pl_q2n_acc<NE, G, Q, false, Q>(X + (3 * f - 1) * NQ2 + i, ta);
-#pragma unroll
-        for (int m = 0; m < G; ++m) { V::st(T + f * PER + m * Q + i, tb[m]); V::st(T + (3 + f) * PER + m * Q + i, ta[m]); }
+        for (int m = 0; m < G; ++m) { V::st(T + f * ST + m * TM + i, tb[m]); V::st(T + (3 + f) * ST + m * TM + i, ta[m]); }
     }
     __syncwarp();
+    PR_STAMP(5);
     // ---- 6. scatter pass 2 (contraction over i): lane (f,m) -> rhs[f][m][n] = B.TB_f + A.TA_f
     if (lane < 3 * G) {
         const int f = lane / G, m = lane - f * G;
         double r[G][NE];
-#pragma unroll
-        for (int n = 0; n < G; ++n) { PR_FORC r[n][c] = 0.0; }
-        pl_q2n_acc<NE, G, Q, true, 1>(T + f * PER + m * Q, r);
-        pl_q2n_acc<NE, G, Q, false, 1>(T + (3 + f) * PER + m * Q, r);
+        pl_q2n_acc<NE, G, Q, true, 1, true>(T + f * ST + m * TM, r);
+        pl_q2n_acc<NE, G, Q, false, 1, false>(T + (3 + f) * ST + m * TM, r);
 #pragma unroll
         for (int n = 0; n < G; ++n) V::st(X + R::X_RHS + f * NP + m * G + n, r[n]);
     }
@@ -508,38 +550,32 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
                 lfu[c] = sgn * flux_qu; lfv[c] = sgn * flux_qv;
             }
         }
-        VT* FL = X + R::X_FL + (s * 4) * G + n;
-        VT* FR = X + R::X_FR + (s * 4) * G + n;
-        V::st(FL, L0); V::st(FL + G, L1); V::st(FL + 2 * G, L2); V::st(FL + 3 * G, L3);
-        V::st(FR, R0); V::st(FR + G, R1); V::st(FR + 2 * G, R2); V::st(FR + 3 * G, R3);
+        VT* FL = X + R::X_FL + lane;   // [side][var][s][n]: the word index follows the lane number
+        VT* FR = X + R::X_FR + lane;
+        V::st(FL, L0); V::st(FL + 4 * G, L1); V::st(FL + 8 * G, L2); V::st(FL + 12 * G, L3);
+        V::st(FR, R0); V::st(FR + 4 * G, R1); V::st(FR + 8 * G, R2); V::st(FR + 12 * G, R3);
         if (VISC) { V::st(X + R::X_LF + (s * 2 + 0) * G + n, lfu); V::st(X + R::X_LF + (s * 2 + 1) * G + n, lfv); }
     }
-    // face coefficients and (owner only) running sums of the face quadrature points, first block, one phase ahead
-    struct FLd { double cf[11][NE]; double acc[11][NE]; };
-    auto fload = [&](int it, FLd& F) {
-        const int p = it * 32 + lane;
-        if (p < 4 * Q) {
+    // face coefficients of all face quadrature points (11 per point and element), loaded one phase ahead
+    double fc[NFIT][11][NE];
+#pragma unroll
+    for (int it = 0; it < NFIT; ++it) {
+        const int p = min(it * 32 + lane, 4 * Q - 1);
+        {
             const int s = p / Q, iq = p - s * Q;
             PR_FORC {
-                const int nb = reinterpret_cast<const int*>(hdr + c * R::HDR + 18)[s];
                 const double* cf = rec[c] + R::O_FST + s * R::FSIDE + iq;
 #pragma unroll
-                for (int k = 0; k < 11; ++k) F.cf[k][c] = cf[k * Q];
-                if (nb < 0 || e[c] < nb) {
-                    const double* af = a.accf + ((size_t)e[c] * 4 + s) * R::ASIDE + iq;
-#pragma unroll
-                    for (int k = 0; k < 11; ++k) F.acc[k][c] = af[k * Q];
-                }
+                for (int k = 0; k < 11; ++k) fc[it][k][c] = cf[k * Q];
             }
         }
-    };
-    FLd fbuf[2];
-    fload(0, fbuf[0]);
+    }
     __syncwarp();
+    PR_STAMP(6);
     // ---- 7b. interpolate the traces to the face quadrature points: one (side, L/R, variable) line per lane
     {
         const int s = lane >> 3, side = (lane >> 2) & 1, var = lane & 3;   // var: 0 pb 1 pbpert 2 mx 3 my
-        pl_n2q<NE, G, Q, false, 1, 1>(X + R::X_FL + side * 16 * G + (s * 4 + var) * G, T + lane * Q);
+        pl_n2q<NE, G, Q, false, 1, 1>(X + R::X_FL + side * 16 * G + (var * 4 + s) * G, T + lane * Q);
     }
     // update operands of node I, one phase ahead
     double mi[NE], q0v[3][NE], q2v[3][NE];
@@ -555,13 +591,13 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
         }
     }
     __syncwarp();
+    PR_STAMP(7);
     // ---- 7c. face fluxes, canonical left perspective (mod_rhs_btp.F90:237-330)
 #pragma unroll
     for (int it = 0; it < NFIT; ++it) {
-        FLd& fcur = fbuf[it & 1];
-        if (it + 1 < NFIT) fload(it + 1, fbuf[(it + 1) & 1]);
-        const int p = it * 32 + lane;
-        if (p < 4 * Q) {
+        const int p = min(it * 32 + lane, 4 * Q - 1);
+        const bool pvalid = (it + 1) * 32 <= 4 * Q || it * 32 + lane < 4 * Q;
+        {
             const int s = p / Q, iq = p - s * Q;
             const VT* Lp = T + (s * 8) * Q + iq;
             const VT* Rp = T + (s * 8 + 4) * Q + iq;
@@ -575,8 +611,8 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
                 const int nb = reinterpret_cast<const int*>(h + 18)[s];
                 const bool left = (nb < 0) || (e[c] < nb);
                 const double nxl = h[6 + s * 3 + 0], nyl = h[6 + s * 3 + 1], nlen = h[6 + s * 3 + 2];
-                const double cL = fcur.cf[0][c], cR = fcur.cf[1][c], cLR = fcur.cf[2][c], lam = fcur.cf[3][c];
-                const double s_oope = fcur.cf[4][c], s_uue = fcur.cf[5][c], s_uve = fcur.cf[6][c], s_vve = fcur.cf[7][c], s_He = fcur.cf[8][c];
+                const double cL = fc[it][0][c], cR = fc[it][1][c], cLR = fc[it][2][c], lam = fc[it][3][c];
+                const double s_oope = fc[it][4][c], s_uue = fc[it][5][c], s_uve = fc[it][6][c], s_vve = fc[it][7][c], s_He = fc[it][8][c];
                 const double pU_L = nxl * mxL[c] + nyl * myL[c];
                 const double pU_R = -nxl * mxR[c] - nyl * myR[c];
                 const double pbpert_edge = cL * ppL[c] + cR * ppR[c] + cLR * (pU_L + pU_R);
@@ -591,12 +627,12 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
                 const double qvv = 0.5 * (vl * myL[c] + vr * myR[c]) + ope_e * s_vve;
                 const double e2 = ope_e * ope_e;
                 const double Hf = e2 * s_He;
-                if (left && ok[c]) {
-                    const double ol = 1.0 + ppL[c] * fcur.cf[9][c], orr = 1.0 + ppR[c] * fcur.cf[10][c];
+                if (left && pvalid && ok[c]) {
+                    const double ol = 1.0 + ppL[c] * fc[it][9][c], orr = 1.0 + ppR[c] * fc[it][10][c];
                     double* af = a.accf + ((size_t)e[c] * 4 + s) * R::ASIDE + iq;
-                    af[0] = fcur.acc[0][c] + quu; af[Q] = fcur.acc[1][c] + quv; af[2 * Q] = fcur.acc[2][c] + qvu; af[3 * Q] = fcur.acc[3][c] + qvv;
-                    af[4 * Q] = fcur.acc[4][c] + ol * ol; af[5 * Q] = fcur.acc[5][c] + orr * orr; af[6 * Q] = fcur.acc[6][c] + e2;
-                    af[7 * Q] = fcur.acc[7][c] + ul; af[8 * Q] = fcur.acc[8][c] + ur; af[9 * Q] = fcur.acc[9][c] + vl; af[10 * Q] = fcur.acc[10][c] + vr;
+                    pr_red(af, quu); pr_red(af + Q, quv); pr_red(af + 2 * Q, qvu); pr_red(af + 3 * Q, qvv);
+                    pr_red(af + 4 * Q, ol * ol); pr_red(af + 5 * Q, orr * orr); pr_red(af + 6 * Q, e2);
+                    pr_red(af + 7 * Q, ul); pr_red(af + 8 * Q, ur); pr_red(af + 9 * Q, vl); pr_red(af + 10 * Q, vr);
                 }
                 const double wq = wq0 * nlen;
                 const double dispu = 0.5 * lam * (mxR[c] - mxL[c]), dispv = 0.5 * lam * (myR[c] - myL[c]);
@@ -611,16 +647,16 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
         }
     }
     __syncwarp();
+    PR_STAMP(8);
     // ---- 7d. project the face fluxes onto the face nodes: one (side, field) line per lane -> T[0 .. 12G)
     if (lane < 12) {
         double pr[G][NE];
-#pragma unroll
-        for (int n = 0; n < G; ++n) { PR_FORC pr[n][c] = 0.0; }
-        pl_q2n_acc<NE, G, Q, false, 1>(X + R::X_FF + lane * Q, pr);
+        pl_q2n_acc<NE, G, Q, false, 1, true>(X + R::X_FF + lane * Q, pr);
 #pragma unroll
         for (int n = 0; n < G; ++n) V::st(T + lane * G + n, pr[n]);
     }
     __syncwarp();
+    PR_STAMP(9);
     // ---- 8. gather per node, mass matrix, viscosity, SSPRK update, wall projection (mod_rk_mlswe.F90:97-108)
     if (lane < NP) {
         const int I = lane, m = I / G, n = I - m * G;
@@ -685,6 +721,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
         V::st(nod + 7 * NP + I, un_); V::st(nod + 8 * NP + I, vn_);
     }
     __syncwarp();
+    PR_STAMP(10);
     // ---- 9. traces of the new state (+ LDG gradient) for the next stage
     if (VISC) {
         if (lane < 4 * G) {
@@ -693,6 +730,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
             pl_grad<NE, G, false>(nod + (7 + f) * NP + off, Lr + (2 * kind + f) * NP + off, stride);
         }
         __syncwarp();
+        PR_STAMP(11);
     }
     if (lane < 4 * G) {
         const int s = fs, n = fn, I = pr_face_node<G>(s, n);
@@ -712,6 +750,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
             }
         }
     }
+    PR_STAMP(15);
 }
 
 // ---- runtime view of the record layout (pack kernels, host) ------------------------------------------------------
@@ -861,32 +900,45 @@ __global__ void k_pair_sum_traces(int nelem, PairDims D, const double* rec, doub
     for (int k = 0; k < 3; ++k) to[k * D.G] = rec[e * D.REC + D.O_ACCN + (3 + k) * D.NP + I];
 }
 
-template <int G, int Q, int NE, int W>
-static int launch_pair_w(Solver& S, const PairArgs& a) {
+template <int G, int Q, int NE, int W, bool VISC, int BOTFR>
+static int launch_pair_k(Solver& S, const PairArgs& a) {
     using R = PairRec<G, Q>;
     const size_t smem = R::smem_bytes(NE, W);
+    auto kern = k_btp_stage_pair<G, Q, NE, W, VISC, BOTFR>;
     static bool configured = false;
+    static int units_per_wave = 0;
     if (!configured) {
-        cudaError_t e1 = cudaFuncSetAttribute(k_btp_stage_pair<G, Q, NE, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaError_t e2 = cudaFuncSetAttribute(k_btp_stage_pair<G, Q, NE, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("cudaFuncSetAttribute", "shared memory opt-in failed"); return -1; }
-        cudaFuncSetAttribute(k_btp_stage_pair<G, Q, NE, W, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(k_btp_stage_pair<G, Q, NE, W, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            set_error("cudaFuncSetAttribute", "shared memory opt-in failed"); return -1;
+        }
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         configured = true;
         int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_btp_stage_pair<G, Q, NE, W, true>, 32 * W, smem);
-        S.pair_units_per_wave = nb * W * S.num_sms;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * W, smem);
+        units_per_wave = nb * W * S.num_sms;
         if (getenv("HNUMO_DEBUG"))
-            fprintf(stderr, "[hnumo] pair stage kernel NE=%d W=%d: %zu B smem/block, %d blocks/SM (%d warps)\n", NE, W, smem, nb, nb * W);
+            fprintf(stderr, "[hnumo] element-record stage kernel NE=%d W=%d visc=%d botfr=%d: %zu B smem/block, %d blocks/SM (%d warps)\n", NE, W,
+                    (int)VISC, BOTFR, smem, nb, nb * W);
     }
     PairArgs b = a;
-    if (b.pf_dist <= 0) b.pf_dist = S.pair_units_per_wave;
+    if (b.pf_dist <= 0) b.pf_dist = units_per_wave;
     const int units = (S.nelem + NE - 1) / NE;
     const int blocks = (units + W - 1) / W;
-    if (S.has_visc) k_btp_stage_pair<G, Q, NE, W, true><<<blocks, 32 * W, smem, S.stream>>>(b);
-    else k_btp_stage_pair<G, Q, NE, W, false><<<blocks, 32 * W, smem, S.stream>>>(b);
+    kern<<<blocks, 32 * W, smem, S.stream>>>(b);
     S.n_launches++;
     return 0;
+}
+template <int G, int Q, int NE, int W>
+static int launch_pair_w(Solver& S, const PairArgs& a) {
+    const int bf = S.botfr == 1 ? 1 : S.botfr == 2 ? 2 : 0;
+    if (S.has_visc) {
+        if (bf == 1) return launch_pair_k<G, Q, NE, W, true, 1>(S, a);
+        if (bf == 2) return launch_pair_k<G, Q, NE, W, true, 2>(S, a);
+        return launch_pair_k<G, Q, NE, W, true, 0>(S, a);
+    }
+    if (bf == 1) return launch_pair_k<G, Q, NE, W, false, 1>(S, a);
+    if (bf == 2) return launch_pair_k<G, Q, NE, W, false, 2>(S, a);
+    return launch_pair_k<G, Q, NE, W, false, 0>(S, a);
 }
 template <int G, int Q>
 static int launch_pair_t(Solver& S, const PairArgs& a) {

@@ -3,7 +3,7 @@
 N=${N:-500}
 run() {
   echo -n "$* : "
-  python bench.py --variant 4 --nelx $N --nely $N --steps 1 --warmup 1 --no-cpu-baseline --no-e2e "$@" 2>/dev/null | python -c "
+  python bench.py --variant 0 --nelx $N --nely $N --steps 1 --warmup 1 --no-cpu-baseline --no-e2e "$@" 2>/dev/null | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
@@ -11,10 +11,7 @@ for l in sys.stdin:
 "
 }
 run
-run --opt pair_prefetch=1
 run --opt pair_prefetch=0
-run --opt pair_prefetch=2
-run --opt pair_warps=3
-run --opt pair_warps=3 --opt pair_prefetch=1
-run --opt pair_ne=1
-run --opt pair_ne=1 --opt pair_prefetch=1
+run --opt pair_prefetch=3
+run --opt pair_ne=2
+run --opt pair_ne=2 --opt pair_prefetch=2

@@ -24,7 +24,7 @@ DECKS = {
     "noslip_rk3": lambda: dict(hn.decks.SHIPPED["double_gyre"], nelx=6, nely=5, x_boundary=(2, 2), kstages=3, botfr=2, cd_mlswe=1e-3),
     "nop3_5layers": lambda: dict(hn.decks.synthetic_double_gyre(5, 5, nop=3, nlayers=5)),
 }
-VARIANTS = [0, 1, 2, 3, 4]  # 0: warp-per-element fused kernel, 1: simple reference-form kernel, 2/3: record-layout TMA kernels, 4: element-pair kernel
+VARIANTS = [0, 1, 2, 3, 5]  # 0: element-record kernel (default), 1: simple reference-form kernel, 2/3: record-layout TMA kernels, 5: warp-per-element kernel
 
 
 def natural_errors(S, O, deck):
@@ -147,7 +147,7 @@ def test_variants_agree_bitwise_on_mass():
         S.step(3)
         outs.append(S.download_state())
         S.close()
-    for k in (0, 2, 3, 4):
+    for k in (0, 2, 3, 4):   # index into VARIANTS
         assert rel_l2(outs[k][1][:, 0], outs[1][1][:, 0]) < 1e-13
         assert rel_l2(outs[k][0][:, :, 0], outs[1][0][:, :, 0]) < 1e-12
 
@@ -172,7 +172,7 @@ def _run_partitioned(params, nranks, nsteps, gid, variant=0):
     return decks, outs
 
 
-@pytest.mark.parametrize("variant", [0, 4])
+@pytest.mark.parametrize("variant", [0, 5])
 @pytest.mark.parametrize("visc", [0.0, 50.0])
 @pytest.mark.parametrize("nranks", [2, 4])
 def test_partitioned_equals_single(nranks, visc, variant):
