@@ -389,8 +389,8 @@ static int btp_solve_pair(Solver& S, Planes& qb, const Planes& qprime) {
         const double* nstp[11] = {S.pbprime_df, S.oop_df, S.massinv, qprime[0 * S.nl + bl], qprime[1 * S.nl + bl], qprime[2 * S.nl + bl],
                                   S.pbprime_visc, S.btp_dpp_graduv[0], S.btp_dpp_graduv[1], S.btp_dpp_graduv[2], S.btp_dpp_graduv[3]};
         for (int v = 0; v < 11; ++v) p.nstp[v] = nstp[v];
-        const double* qstp[10] = {S.oop_q, S.Hbcl, S.Quu, S.Quv, S.Qvv, S.coriolis_q, S.tauw_q, S.tauw_q + S.npoin_q, S.gradzb_q, S.gradzb_q + S.npoin_q};
-        for (int v = 0; v < 10; ++v) p.qstp[v] = qstp[v];
+        const double* qstp[9] = {S.Hbcl, S.Quu, S.Quv, S.Qvv, S.coriolis_q, S.tauw_q, S.tauw_q + S.npoin_q, S.gradzb_q, S.gradzb_q + S.npoin_q};
+        for (int v = 0; v < 9; ++v) p.qstp[v] = qstp[v];
         const double* fstp[11] = {S.cL, S.cR, S.cLR, S.lam, S.oop_edge, S.Quu_e, S.Quv_e, S.Qvv_e, S.Hbcl_e, S.pbl, S.pbr};
         for (int v = 0; v < 11; ++v) p.fstp[v] = fstp[v];
         for (int v = 0; v < 4; ++v) p.bdg[v] = S.btp_dpp_graduv[v];

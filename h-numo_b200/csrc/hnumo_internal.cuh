@@ -136,7 +136,7 @@ struct Solver {
     void* d_nbx = nullptr;
     // record layout of the element-pair stage kernel (stage_pair.cuh): one record per element, face sums, traces
     double *p_rec = nullptr, *p_accf = nullptr, *p_tr[2] = {nullptr, nullptr};
-    int pair_ne = 1, pair_warps = 4, pair_prefetch = 1, pair_pf_dist = 0, pair_units_per_wave = 0;
+    int pair_ne = 1, pair_warps = 4, pair_prefetch = 0, pair_pf_dist = 0, pair_units_per_wave = 0;
     int num_sms = 148, tma_blocks_per_sm = 0;
     int use_graph = 0;
     int pf_blocks = -1;   // L2 prefetch distance of the fused stage kernel, in thread blocks

@@ -43,9 +43,9 @@ struct PairRec {
     static constexpr int NST_NF = 11;
     static constexpr int O_NST = O_QB + QBSZ;
     static constexpr int O_ACCN = O_NST + pr_pad2(NST_NF * NP);   // 0 ope2_df 1 ub 2 vb 3 S_pbpert 4 S_mx 5 S_my
-    // quadrature statics: 0 1/pbprime 1 H_bcl 2 Quu 3 Quv 4 Qvv 5 coriolis 6 tau_x 7 tau_y 8 dzb/dx 9 dzb/dy
-    // (7 tau_y, 8 dzb/dx, 9 dzb/dy live in the rarely-read tail of the record)
-    static constexpr int QST_NF = 7, QST_RARE = 3;
+    // quadrature statics: 0 H_bcl 1 Quu 2 Quv 3 Qvv 4 coriolis 5 tau_x; rarely-read tail of the record: tau_y dzb/dx dzb/dy
+    // (1/pbprime at the quadrature points is not stored: it is 1/(pb - pbpert) of the interpolated state)
+    static constexpr int QST_NF = 6, QST_RARE = 3;
     static constexpr int O_QST = O_ACCN + pr_pad2(6 * NP);
     static constexpr int O_ACCQ = O_QST + pr_pad2(QST_NF * NQ2);  // 0 Qu 1 Qv 2 Quv 3 ope2 4 ub 5 vb (tail: 6,7 tau_bot, botfr==2)
     // face statics per side: cL cR cLR lam oop_edge Quu_e Quv_e Qvv_e Hbcl_e 1/pbl 1/pbr (copy of the owner's values)
@@ -258,16 +258,16 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
             }
         }
     }
-    // quadrature-point statics of all blocks of 32 points (7 per point and element): issued with the first loads, they
+    // quadrature-point statics of all blocks of 32 points (6 per point and element): issued with the first loads, they
     // are consumed three phases later.  Lanes past the last point re-read it (branch-free phases; they never store sums).
-    double qs[NQIT][7][NE];
+    double qs[NQIT][R::QST_NF][NE];
 #pragma unroll
     for (int it = 0; it < NQIT; ++it) {
         const int q = min(it * 32 + lane, NQ2 - 1);
         PR_FORC {
             const double* rs = rec[c] + R::O_QST + q;
 #pragma unroll
-            for (int k = 0; k < 7; ++k) qs[it][k][c] = rs[k * NQ2];
+            for (int k = 0; k < R::QST_NF; ++k) qs[it][k][c] = rs[k * NQ2];
         }
     }
     // ---- 0. header -> shared memory (issued after the nodal loads so that the two round trips overlap); the tail of
@@ -406,8 +406,10 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
                     const double spd = (BOTFR == 1) ? a.cd_g * pp[c] : a.cd_alpha * sqrt(ubot * ubot + vbot * vbot);
                     tb_u = spd * ubot; tb_v = spd * vbot;
                 }
-                const double s_oop = qs[it][0][c], s_H = qs[it][1][c], s_uu = qs[it][2][c], s_uv = qs[it][3][c], s_vv = qs[it][4][c];
-                const double fcor = qs[it][5][c], s_twx = qs[it][6][c];
+                const double pbq = dp[c] - dpp[c];             // pbprime at the point: pb = pbpert + pbprime, all interpolated
+                const double s_oop = pbq > 0.0 ? pr_rcp(pbq) : 0.0;   // guarded as in initial_conditions.F90:344-348
+                const double s_H = qs[it][0][c], s_uu = qs[it][1][c], s_uv = qs[it][2][c], s_vv = qs[it][3][c];
+                const double fcor = qs[it][4][c], s_twx = qs[it][5][c];
                 // rare forcing fields are read on demand (predicated loads, no branch)
                 const double* rs = rec[c] + R::O_QSTR + q;
                 const double s_twy = (flags[c] & PF_TWY) ? rs[0] : 0.0;
@@ -564,9 +566,17 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
         {
             const int s = p / Q, iq = p - s * Q;
             PR_FORC {
-                const double* cf = rec[c] + R::O_FST + s * R::FSIDE + iq;
+                // a face's coefficients live once, in the record of its left (owner) element: the other side reads them
+                // there (its neighbour is in flight at the same time, so this is an L2 hit, not a second DRAM read)
+                const int* hi = reinterpret_cast<const int*>(hdr + c * R::HDR + 18);
+                const int nb = hi[s];
+                const bool left = (nb < 0) || (e[c] < nb);
+                const double* cf = left ? rec[c] + R::O_FST + s * R::FSIDE + iq
+                                        : a.rec + (size_t)nb * R::REC + R::O_FST + (hi[4 + s] - 4 * nb) * R::FSIDE + iq;
 #pragma unroll
-                for (int k = 0; k < 11; ++k) fc[it][k][c] = cf[k * Q];
+                for (int k = 0; k < 9; ++k) fc[it][k][c] = cf[k * Q];
+                fc[it][9][c] = left ? cf[9 * Q] : 0.0;
+                fc[it][10][c] = left ? cf[10 * Q] : 0.0;
             }
         }
     }
@@ -775,7 +785,7 @@ struct PairPackArgs {
     PairDims D;
     const double* qb[3];
     const double* nstp[11];
-    const double* qstp[10];
+    const double* qstp[9];
     const double* fstp[11];   // the last two (pbl, pbr) are stored as reciprocals
     const double* bdg[4];
     const double* pbv;
@@ -818,11 +828,11 @@ __global__ void k_pair_pack(PairPackArgs a) {
     for (int t = tid; t < 6 * NP; t += nt) r[D.O_ACCN + t] = 0.0;
     // quadrature statics (+ forcing sparsity flags), quadrature sums
     int fl = 0;
-    for (int t = tid; t < 10 * NQ2; t += nt) {
+    for (int t = tid; t < 9 * NQ2; t += nt) {
         const int f = t / NQ2;
         const double x = a.qstp[f][qbase + t % NQ2];
-        r[(f < 7 ? D.O_QST : D.O_QSTR - 7 * NQ2) + t] = x;
-        if (x != 0.0) fl |= (f == 5) ? PF_COR : (f == 6) ? PF_TWX : (f == 7) ? PF_TWY : (f >= 8) ? PF_GZ : 0;
+        r[(f < 6 ? D.O_QST : D.O_QSTR - 6 * NQ2) + t] = x;
+        if (x != 0.0) fl |= (f == 4) ? PF_COR : (f == 5) ? PF_TWX : (f == 6) ? PF_TWY : (f >= 7) ? PF_GZ : 0;
     }
     if (fl) atomicOr(&s_flags, fl);
     for (int t = tid; t < 6 * NQ2; t += nt) r[D.O_ACCQ + t] = 0.0;
@@ -832,9 +842,11 @@ __global__ void k_pair_pack(PairPackArgs a) {
         int s = t / (11 * Q), rr = t - s * 11 * Q, f = rr / Q, iq = rr - f * Q;
         int slot = e * 4 + s, nb = a.M.nbr[slot], nbs = a.M.nbslot[slot];
         bool left = (nb < 0) || (e < nb);
-        int oslot = left ? slot : nb * 4 + nbs;
-        double x = a.fstp[f][(size_t)oslot * Q + iq];
-        if (f >= 9) x = 1.0 / x;
+        double x = 0.0;
+        if (left) {   // the right element reads the owner's copy
+            x = a.fstp[f][(size_t)slot * Q + iq];
+            if (f >= 9) x = 1.0 / x;
+        }
         r[D.O_FST + s * D.FSIDE + rr] = x;
     }
     for (int t = tid; t < NP; t += nt) {
