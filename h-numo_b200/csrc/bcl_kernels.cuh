@@ -42,9 +42,11 @@ struct CoeffArgs {
     double alpha[HN_MAXL];
     int has_visc;
 };
+template <int G_, int Q_, int NL_>
 __global__ void k_bcl_coeffs(CoeffArgs a) {
     extern __shared__ double sm[];
-    const int ngl = a.M.ngl, nq = a.M.nq, npts = a.M.npts, nq2 = a.M.nq2, nl = a.M.nl, per = ngl * nq;
+    const int ngl = G_ ? G_ : a.M.ngl, nq = Q_ ? Q_ : a.M.nq, npts = ngl * ngl, nq2 = nq * nq, nl = NL_ ? NL_ : a.M.nl, per = ngl * nq;
+    constexpr int LMAX = NL_ ? NL_ : HN_MAXL;   // per-thread layer arrays stay in registers when the layer count is a compile-time constant
     const int e = blockIdx.x, tid = threadIdx.x;
     SOps o = load_sops(sm, ngl, nq);
     double* nod = sm + sops_doubles(ngl, nq);  // [3][npts]
@@ -151,9 +153,11 @@ struct MassArgs {
     int* flag;
     double dt;
 };
+template <int G_, int Q_, int NL_>
 __global__ void k_layer_mass(MassArgs a) {
     extern __shared__ double sm[];
-    const int ngl = a.M.ngl, nq = a.M.nq, npts = a.M.npts, nq2 = a.M.nq2, nl = a.M.nl, per = ngl * nq;
+    const int ngl = G_ ? G_ : a.M.ngl, nq = Q_ ? Q_ : a.M.nq, npts = ngl * ngl, nq2 = nq * nq, nl = NL_ ? NL_ : a.M.nl, per = ngl * nq;
+    constexpr int LMAX = NL_ ? NL_ : HN_MAXL;   // per-thread layer arrays stay in registers when the layer count is a compile-time constant
     const int e = blockIdx.x, tid = threadIdx.x;
     SOps o = load_sops(sm, ngl, nq);
     double* nod = sm + sops_doubles(ngl, nq);
@@ -266,9 +270,11 @@ struct ConsArgs {
     const double* slmf_f[2];
     double dt;
 };
+template <int G_, int Q_, int NL_>
 __global__ void k_consistency(ConsArgs a) {
     extern __shared__ double sm[];
-    const int ngl = a.M.ngl, nq = a.M.nq, npts = a.M.npts, nq2 = a.M.nq2, nl = a.M.nl, per = ngl * nq;
+    const int ngl = G_ ? G_ : a.M.ngl, nq = Q_ ? Q_ : a.M.nq, npts = ngl * ngl, nq2 = nq * nq, nl = NL_ ? NL_ : a.M.nl, per = ngl * nq;
+    constexpr int LMAX = NL_ ? NL_ : HN_MAXL;   // per-thread layer arrays stay in registers when the layer count is a compile-time constant
     const int e = blockIdx.x, tid = threadIdx.x;
     SOps o = load_sops(sm, ngl, nq);
     double* dpp = sm + sops_doubles(ngl, nq);  // [nl][npts] own dpprime_df
@@ -293,7 +299,7 @@ __global__ void k_consistency(ConsArgs a) {
         int s = tid / ngl, n = tid - s * ngl, slot = e * 4 + s, nb = a.M.nbr[slot], nbs = a.M.nbslot[slot];
         int I = face_node(s, n, ngl);
         if (nb >= 0 || nb == NBR_HALO) {
-            double sum = 0.0, vals[HN_MAXL];
+            double sum = 0.0, vals[LMAX];
             for (int k = 0; k < nl; ++k) {
                 vals[k] = nb_nodal(a.M, a.qdp_in + (size_t)k * a.nstride, a.hdp + (size_t)k * a.hstride, nb, nbs, n, 0.0);
                 sum += vals[k];
@@ -374,9 +380,11 @@ struct LapArgs {
     double* rhs_visc;                   // [2*nl]
     double visc;
 };
+template <int G_, int Q_, int NL_>
 __global__ void k_bcl_laplacian(LapArgs a) {
     extern __shared__ double sm[];
-    const int ngl = a.M.ngl, nq = a.M.nq, npts = a.M.npts, nl = a.M.nl;
+    const int ngl = G_ ? G_ : a.M.ngl, nq = Q_ ? Q_ : a.M.nq, npts = ngl * ngl, nl = NL_ ? NL_ : a.M.nl;
+    constexpr int LMAX = NL_ ? NL_ : HN_MAXL;
     const int e = blockIdx.x, tid = threadIdx.x;
     SOps o = load_sops(sm, ngl, nq);
     double* gub = sm + sops_doubles(ngl, nq);  // [4][npts]
@@ -466,9 +474,11 @@ struct MomVolArgs {
     double alpha[HN_MAXL];
     double g;
 };
+template <int G_, int Q_, int NL_>
 __global__ void k_mom_volume(MomVolArgs a) {
     extern __shared__ double sm[];
-    const int ngl = a.M.ngl, nq = a.M.nq, npts = a.M.npts, nq2 = a.M.nq2, nl = a.M.nl, per = ngl * nq;
+    const int ngl = G_ ? G_ : a.M.ngl, nq = Q_ ? Q_ : a.M.nq, npts = ngl * ngl, nq2 = nq * nq, nl = NL_ ? NL_ : a.M.nl, per = ngl * nq;
+    constexpr int LMAX = NL_ ? NL_ : HN_MAXL;   // per-thread layer arrays stay in registers when the layer count is a compile-time constant
     const int e = blockIdx.x, tid = threadIdx.x;
     SOps o = load_sops(sm, ngl, nq);
     double* nod = sm + sops_doubles(ngl, nq);  // [5][npts]: dp',u',v', udp, vdp of the current layer; also z levels
@@ -483,8 +493,8 @@ __global__ void k_mom_volume(MomVolArgs a) {
     const double eps1 = 1.0e-20;
     const double Pstress = (a.g / a.alpha[0]) * 50.0, Pbstress = (a.g / a.alpha[nl - 1]) * 10.0;
     // per quadrature point, per layer
-    double p_tmp[HN_MAXL + 1], H_tmp[HN_MAXL], u_udp[HN_MAXL], v_vdp[HN_MAXL], u_vdp1[HN_MAXL], u_vdp2[HN_MAXL],
-        temp_uu[HN_MAXL], temp_vv[HN_MAXL], gradz1[HN_MAXL + 1], gradz2[HN_MAXL + 1], dpq[HN_MAXL];
+    double p_tmp[LMAX + 1], H_tmp[LMAX], u_udp[LMAX], v_vdp[LMAX], u_vdp1[LMAX], u_vdp2[LMAX],
+        temp_uu[LMAX], temp_vv[LMAX], gradz1[LMAX + 1], gradz2[LMAX + 1], dpq[LMAX];
     double qp_last[3] = {0, 0, 0};
     const int j = tid / nq, i = tid - j * nq;
     const bool qa = tid < nq2;
@@ -602,9 +612,11 @@ struct MomFaceArgs {
     double g, dt;
     int full_prime;  // 1: evaluate_bcl (predictor), 0: evaluate_bcl_v1 (corrector)
 };
+template <int G_, int Q_, int NL_>
 __global__ void k_mom_faces_update(MomFaceArgs a) {
     extern __shared__ double sm[];
-    const int ngl = a.M.ngl, nq = a.M.nq, npts = a.M.npts, nl = a.M.nl;
+    const int ngl = G_ ? G_ : a.M.ngl, nq = Q_ ? Q_ : a.M.nq, npts = ngl * ngl, nl = NL_ ? NL_ : a.M.nl;
+    constexpr int LMAX = NL_ ? NL_ : HN_MAXL;
     const int e = blockIdx.x, tid = threadIdx.x;
     SOps o = load_sops(sm, ngl, nq);
     double* ownq = sm + sops_doubles(ngl, nq);  // [4][3][nl][ngl]
@@ -637,9 +649,9 @@ __global__ void k_mom_faces_update(MomFaceArgs a) {
         double nxl = a.M.fgeom[slot * 3], nyl = a.M.fgeom[slot * 3 + 1], nlen = a.M.fgeom[slot * 3 + 2];
         const double* tl = left ? ownq : nbq;
         const double* tr = left ? nbq : ownq;
-        double ql0[HN_MAXL], qr0[HN_MAXL];
-        double udpl[HN_MAXL], udpr[HN_MAXL], vdpl[HN_MAXL], vdpr[HN_MAXL];
-        double uf0[HN_MAXL], uf1[HN_MAXL], vf0[HN_MAXL], vf1[HN_MAXL], HL[HN_MAXL], HR[HN_MAXL];
+        double ql0[LMAX], qr0[LMAX];
+        double udpl[LMAX], udpr[LMAX], vdpl[LMAX], vdpr[LMAX];
+        double uf0[LMAX], uf1[LMAX], vf0[LMAX], vf1[LMAX], HL[LMAX], HR[LMAX];
         double qbl0 = a.ave_f[7][fo], qbl1 = a.ave_f[12][fo], qbl2 = a.ave_f[14][fo];
         double qbr0 = a.ave_f[8][fo], qbr1 = a.ave_f[13][fo], qbr2 = a.ave_f[15][fo];
         for (int k = 0; k < nl; ++k) {
@@ -681,8 +693,8 @@ __global__ void k_mom_faces_update(MomFaceArgs a) {
             vf1[k] = vf1[k] + w * vv_def;
         }
         // pressure forcing H_face (mod_create_rhs_mlswe.F90:627-773)
-        double pfl[HN_MAXL + 1], pfr[HN_MAXL + 1], zfl[HN_MAXL + 1], zfr[HN_MAXL + 1];
-        double pep[HN_MAXL + 1], pem[HN_MAXL + 1], zep[HN_MAXL + 1], zem[HN_MAXL + 1];
+        double pfl[LMAX + 1], pfr[LMAX + 1], zfl[LMAX + 1], zfr[LMAX + 1];
+        double pep[LMAX + 1], pem[LMAX + 1], zep[LMAX + 1], zem[LMAX + 1];
         double ope_l = sqrt(a.ave_f[9][fo]), ope_r = sqrt(a.ave_f[10][fo]);
         pfl[0] = 0.0; pfr[0] = 0.0;
         for (int k = 0; k < nl; ++k) { pfl[k + 1] = pfl[k] + ope_l * ql0[k]; pfr[k + 1] = pfr[k] + ope_r * qr0[k]; }
@@ -758,7 +770,7 @@ __global__ void k_mom_faces_update(MomFaceArgs a) {
     __syncthreads();
     if (tid < npts) {
         int m = tid / ngl, n = tid - m * ngl;
-        double qd[HN_MAXL], qx[HN_MAXL], qy[HN_MAXL];
+        double qd[LMAX], qx[LMAX], qy[LMAX];
         double mi = a.massinv[nbase + tid];
         double f2 = a.fdt2[nbase + tid], ab = a.a_bcl[nbase + tid], bb = a.b_bcl[nbase + tid];
         for (int k = 0; k < nl; ++k) {
@@ -800,7 +812,7 @@ __global__ void k_mom_faces_update(MomFaceArgs a) {
         // evaluate_bcl / evaluate_bcl_v1: two passes of extract_velocity
         double pb = a.qb[0][nbase + tid] + a.pbprime_df[nbase + tid];
         double mbx = a.qb[1][nbase + tid], mby = a.qb[2][nbase + tid];
-        double uk[HN_MAXL], vk[HN_MAXL];
+        double uk[LMAX], vk[LMAX];
         for (int pass = 0; pass < 2; ++pass) {
             double ubar = 0.0, vbar = 0.0;
             for (int k = 0; k < nl; ++k) { uk[k] = qx[k] / qd[k]; vk[k] = qy[k] / qd[k]; }

@@ -479,9 +479,10 @@ struct FinalizeArgs {
     int botfr;
     int derive_graduvb;  // 1: graduvb_ave = grad(uvb_ave_df) (the gradient is linear); 0: acc_n[6..9] hold the per-stage sums
 };
+template <int G_, int Q_>
 __global__ void k_btp_finalize(FinalizeArgs a) {
     extern __shared__ double sm[];
-    const int ngl = a.M.ngl, nq = a.M.nq, npts = a.M.npts, nq2 = a.M.nq2, per = ngl * nq;
+    const int ngl = G_ ? G_ : a.M.ngl, nq = Q_ ? Q_ : a.M.nq, npts = ngl * ngl, nq2 = nq * nq, per = ngl * nq;
     const int e = blockIdx.x, tid = threadIdx.x;
     SOps o = load_sops(sm, ngl, nq);
     double* nod = sm + sops_doubles(ngl, nq);  // 0 S_pbpert 1 S_mx 2 S_my 3 pp 4 up 5 vp 6 ub_ave 7 vb_ave

@@ -34,6 +34,23 @@ void upload_ops(const Ops& ops) { cudaMemcpyToSymbol(c_ops, &ops, sizeof(Ops)); 
 static bool use_fused(const Solver& S) { return S.variant == 5 && stage_fused_supported(S); }
 static bool use_pair(const Solver& S) { return (S.variant == 0 || S.variant == 4) && S.p_rec != nullptr; }
 
+// kernels templated on (ngl, nq[, nlayers]): compile-time sizes for the shipped orders, 0 = run-time size
+#define HN_LAUNCH_GQ(kern, S, smem, args)                                                                     \
+    do {                                                                                                      \
+        if ((S).ngl == 5 && (S).nq == 9) kern<5, 9><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args);  \
+        else if ((S).ngl == 4 && (S).nq == 7) kern<4, 7><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args); \
+        else kern<0, 0><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args);                              \
+    } while (0)
+#define HN_LAUNCH_GQL(kern, S, smem, args)                                                                    \
+    do {                                                                                                      \
+        if ((S).ngl == 5 && (S).nq == 9 && (S).nl == 2) kern<5, 9, 2><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args);      \
+        else if ((S).ngl == 5 && (S).nq == 9 && (S).nl == 3) kern<5, 9, 3><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args); \
+        else if ((S).ngl == 5 && (S).nq == 9) kern<5, 9, 0><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args);                \
+        else if ((S).ngl == 4 && (S).nq == 7) kern<4, 7, 0><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args);                \
+        else kern<0, 0, 0><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args);                            \
+    } while (0)
+
+static int threads_for(const Solver& S);
 static int threads_for(const Solver& S) {
     int t = S.nq2;
     if (t < 4 * S.nq + 4 * S.ngl) t = 4 * S.nq + 4 * S.ngl;
@@ -262,7 +279,7 @@ int btp_solve(Solver& S, Planes& qb, const Planes& qprime) {
         f.S = (double)(S.kstages * S.N_btp); f.N_inv = 1.0 / (double)(S.kstages * S.N_btp); f.cd_over_g = S.cd / S.g;
         f.botfr = S.botfr;
         size_t sm = (sops_doubles_host(S.ngl, S.nq) + 8 * S.npts + 6 * S.ngl * S.nq) * sizeof(double);
-        k_btp_finalize<<<S.nelem, threads_for(S), sm, S.stream>>>(f);
+        HN_LAUNCH_GQ(k_btp_finalize, S, sm, f);
         S.n_launches++;
         // halo copy of the averaged LDG gradient traces (graduvb_face_ave side 2 on processor boundaries)
         if (S.has_visc && S.nhalo > 0 && f.derive_graduvb) {
@@ -366,7 +383,7 @@ static int btp_solve_rec(Solver& S, Planes& qb, const Planes& qprime) {
     f.S = (double)(S.kstages * S.N_btp); f.N_inv = 1.0 / (double)(S.kstages * S.N_btp); f.cd_over_g = S.cd / S.g;
     f.botfr = S.botfr;
     size_t sm = (sops_doubles_host(S.ngl, S.nq) + 8 * S.npts + 6 * S.ngl * S.nq) * sizeof(double);
-    k_btp_finalize<<<S.nelem, threads_for(S), sm, S.stream>>>(f);
+    HN_LAUNCH_GQ(k_btp_finalize, S, sm, f);
     S.n_launches++;
     // graduvb_face_ave side 2 on processor boundaries = the neighbour's averaged gradient at the face nodes
     if (S.has_visc && S.nhalo > 0)
@@ -447,7 +464,7 @@ static int btp_solve_pair(Solver& S, Planes& qb, const Planes& qprime) {
     f.S = (double)(S.kstages * S.N_btp); f.N_inv = 1.0 / (double)(S.kstages * S.N_btp); f.cd_over_g = S.cd / S.g;
     f.botfr = S.botfr;
     size_t sm = (sops_doubles_host(S.ngl, S.nq) + 8 * S.npts + 6 * S.ngl * S.nq) * sizeof(double);
-    k_btp_finalize<<<S.nelem, threads_for(S), sm, S.stream>>>(f);
+    HN_LAUNCH_GQ(k_btp_finalize, S, sm, f);
     S.n_launches++;
     if (S.has_visc && S.nhalo > 0)
         if (halo_exchange_nodal(S, S.ave_n[3], 4, S.ave_n.stride, S.h_gub)) return -1;
@@ -465,7 +482,7 @@ int btp_bcl_coeffs(Solver& S, const Planes& qprime, const Planes& dpv) {
     for (int k = 0; k < S.nl; ++k) a.alpha[k] = S.alpha[k];
     a.has_visc = S.has_visc;
     size_t sm = (sops_doubles_host(S.ngl, S.nq) + 3 * S.npts + 3 * S.ngl * S.nq + 12 * S.ngl) * sizeof(double);
-    k_bcl_coeffs<<<S.nelem, threads_for(S), sm, S.stream>>>(a);
+    HN_LAUNCH_GQL(k_bcl_coeffs, S, sm, a);
     S.n_launches++;
     if (S.has_visc && S.nhalo > 0) {
         // graduv_dpp_face exchange (mod_barotropic_terms.F90:393): per-layer planes and their layer sums
@@ -489,7 +506,7 @@ static int layer_mass_and_consistency(Solver& S, const Planes& qprime, Planes& q
     m.massinv = S.massinv; m.flag = S.d_flag; m.dt = S.dt;
     size_t per = S.ngl * S.nq;
     size_t sm = (sops_doubles_host(S.ngl, S.nq) + 3 * S.npts + 3 * per + 12 * S.ngl + 2 * S.nq2 + 2 * per + S.npts + 4 * S.nq) * sizeof(double);
-    k_layer_mass<<<S.nelem, threads_for(S), sm, S.stream>>>(m);
+    HN_LAUNCH_GQL(k_layer_mass, S, sm, m);
     S.n_launches++;
     // apply_consistency (mod_splitting.F90:324-366)
     if (halo_exchange_nodal(S, q[0], S.nl, q.stride, S.h_dp)) return -1;
@@ -501,7 +518,7 @@ static int layer_mass_and_consistency(Solver& S, const Planes& qprime, Planes& q
     c.slmf_q[0] = S.slmf_q[0]; c.slmf_q[1] = S.slmf_q[1]; c.slmf_f[0] = S.slmf_f[0]; c.slmf_f[1] = S.slmf_f[1];
     c.dt = S.dt;
     sm = (sops_doubles_host(S.ngl, S.nq) + (size_t)S.nl * S.npts + 4 * S.nl * S.ngl + per + 2 * S.nq2 + 2 * per + S.npts + 4 * S.nq) * sizeof(double);
-    k_consistency<<<S.nelem, threads_for(S), sm, S.stream>>>(c);
+    HN_LAUNCH_GQL(k_consistency, S, sm, c);
     S.n_launches++;
     cudaMemcpyAsync(q[0], S.qdp_tmp.p, (size_t)S.nl * q.stride * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
     return 0;
@@ -516,7 +533,7 @@ static int momentum_update(Solver& S, const Planes& qprime_in, Planes& q, Planes
         l.h_dpv = S.h_dpv.p; l.h_dpg = S.h_dpg.p; l.h_gub = S.h_gub.p; l.hstride = S.h_dpv.stride;
         l.massinv = S.massinv; l.rhs_visc = S.rhs_visc.p; l.visc = S.visc;
         size_t sm = (sops_doubles_host(S.ngl, S.nq) + 8 * S.npts + 8 * S.ngl) * sizeof(double);
-        k_bcl_laplacian<<<S.nelem, threads_for(S), sm, S.stream>>>(l);
+        HN_LAUNCH_GQL(k_bcl_laplacian, S, sm, l);
         S.n_launches++;
     }
     MomVolArgs v; memset(&v, 0, sizeof(v));
@@ -527,7 +544,7 @@ static int momentum_update(Solver& S, const Planes& qprime_in, Planes& q, Planes
     for (int k = 0; k < S.nl; ++k) v.alpha[k] = S.alpha[k];
     v.g = S.g;
     size_t sm = (sops_doubles_host(S.ngl, S.nq) + 5 * S.npts + 6 * per + 6 * S.nq2 + 4 * per + 2 * S.npts) * sizeof(double);
-    k_mom_volume<<<S.nelem, threads_for(S), sm, S.stream>>>(v);
+    HN_LAUNCH_GQL(k_mom_volume, S, sm, v);
     S.n_launches++;
     MomFaceArgs f; memset(&f, 0, sizeof(f));
     f.M = S.mesh; f.qprime = qprime_in.p; f.q = q.p; f.qprime_out = qprime_out.p; f.nstride = q.stride; f.hq = S.h_q.p; f.hstride = S.h_q.stride;
@@ -539,7 +556,7 @@ static int momentum_update(Solver& S, const Planes& qprime_in, Planes& q, Planes
     for (int k = 0; k < S.nl; ++k) f.alpha[k] = S.alpha[k];
     f.g = S.g; f.dt = S.dt; f.full_prime = full_prime;
     sm = (sops_doubles_host(S.ngl, S.nq) + 24 * (size_t)S.nl * S.ngl + 8 * (size_t)S.nl * S.nq) * sizeof(double);
-    k_mom_faces_update<<<S.nelem, threads_for(S), sm, S.stream>>>(f);
+    HN_LAUNCH_GQL(k_mom_faces_update, S, sm, f);
     S.n_launches++;
     return 0;
 }

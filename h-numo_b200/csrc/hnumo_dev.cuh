@@ -19,7 +19,7 @@ struct SOps {
     const double *A, *B, *D, *wq, *wg;
 };
 __device__ __forceinline__ int sops_doubles(int ngl, int nq) { return 2 * ngl * nq + ngl * ngl + nq + ngl; }
-__device__ inline SOps load_sops(double* s, int ngl, int nq) {
+__device__ __forceinline__ SOps load_sops(double* s, int ngl, int nq) {
     double* A = s; double* B = A + ngl * nq; double* D = B + ngl * nq; double* wq = D + ngl * ngl; double* wg = wq + nq;
     for (int t = threadIdx.x; t < ngl * nq; t += blockDim.x) { A[t] = c_ops.A[t]; B[t] = c_ops.B[t]; }
     for (int t = threadIdx.x; t < ngl * ngl; t += blockDim.x) D[t] = c_ops.D[t];
@@ -31,7 +31,7 @@ __device__ inline SOps load_sops(double* s, int ngl, int nq) {
 
 // first sum-factorisation pass for NF nodal fields held in shared memory:
 //   tA[f][m][i] = sum_n A(n,i) nod[f][m][n]      (and tB with B if tB != nullptr)
-__device__ inline void sf_pass1(const SOps& o, int ngl, int nq, int NF, const double* nod, int nod_stride, double* tA,
+__device__ __forceinline__ void sf_pass1(const SOps& o, int ngl, int nq, int NF, const double* nod, int nod_stride, double* tA,
                                 double* tB) {
     const int per = ngl * nq;
     for (int t = threadIdx.x; t < NF * per; t += blockDim.x) {
@@ -66,7 +66,7 @@ __device__ __forceinline__ double sf_eval_B(const SOps& o, int ngl, int nq, cons
 // S, Fk, Fe already contain the quadrature weight and metric factors.  Any of S may be null.
 // tP,tR: scratch [NF][ngl*nq].  Caller must __syncthreads() before (inputs ready) -- this routine
 // syncs internally between the passes and after the result is written.
-__device__ inline void sf_scatter(const SOps& o, int ngl, int nq, int NF, const double* S, const double* Fk,
+__device__ __forceinline__ void sf_scatter(const SOps& o, int ngl, int nq, int NF, const double* S, const double* Fk,
                                   const double* Fe, int qstride, double* tP, double* tR, double* out, int out_stride,
                                   bool accumulate) {
     const int per = ngl * nq;
