@@ -112,6 +112,16 @@ def test_step_parity(name, nsteps, variant):
     S.close()
 
 
+def test_high_order_many_layers():
+    """BASELINE config 5 in small: nop=8 (ngl=9, nq=17), 10 layers -- orders without a compile-time instantiation run the
+    run-time-size kernels; nl > 3 uses the intent semantics of SURVEY 8 hazard 1 in both the oracle and the library"""
+    deck, S, O = make_pair(hn.decks.synthetic_double_gyre(3, 3, nop=8, nlayers=10))
+    assert S.step(2) == 0 and O.step(2) == 0
+    e = natural_errors(S, O, deck)
+    assert e["mass"] < 1e-10 and e["mom"] < 1e-11, e
+    S.close()
+
+
 def test_100_steps_bump():
     """north-star check: 100 baroclinic steps (56000 barotropic stages) of the bump deck"""
     deck, S, O = make_pair(DECKS["bump"]())
