@@ -243,8 +243,9 @@ def main():
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "stage_kernel_traffic.json")))
-        if prof.get("nelem") == deck["nelem"]:
-            traffic = prof.get("dram_bytes_per_launch")
+        # ncu capture of one launch over prof["nelem"] elements; a launch of this rank covers deck["nelem"] elements
+        if args.variant in (0, 4) and args.nop == 4 and has_visc:
+            traffic = prof.get("dram_bytes_per_launch") * deck["nelem"] / prof.get("nelem")
     except Exception:
         pass
     # ---- end-to-end arm: host buffers through the drop-in entry point
