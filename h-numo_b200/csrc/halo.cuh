@@ -136,15 +136,16 @@ inline void halo_comm_destroy(Solver& S) {
 }
 
 // move S.d_send -> neighbours' S.d_recv ; `per_face` doubles per halo face
-static int halo_sendrecv(Solver& S, size_t per_face, double* recv_base = nullptr) {
+static int halo_sendrecv(Solver& S, size_t per_face, double* recv_base = nullptr, cudaStream_t st = nullptr) {
     if (!recv_base) recv_base = S.d_recv;
+    if (!st) st = S.stream;
     if ((size_t)S.nhalo * per_face > S.halo_capacity) { set_error("halo", "staging buffer too small"); return -1; }
     if (S.nccl_comm) {
         int rc = g_nccl.GroupStart();
         for (size_t i = 0; i < S.nbh_rank.size() && !rc; ++i) {
             size_t off = (size_t)S.nbh_offset[i] * per_face, cnt = (size_t)S.nbh_count[i] * per_face;
-            rc = g_nccl.Send(S.d_send + off, cnt, NCCL_DOUBLE, S.nbh_rank[i], S.nccl_comm, S.stream);
-            if (!rc) rc = g_nccl.Recv(recv_base + off, cnt, NCCL_DOUBLE, S.nbh_rank[i], S.nccl_comm, S.stream);
+            rc = g_nccl.Send(S.d_send + off, cnt, NCCL_DOUBLE, S.nbh_rank[i], S.nccl_comm, st);
+            if (!rc) rc = g_nccl.Recv(recv_base + off, cnt, NCCL_DOUBLE, S.nbh_rank[i], S.nccl_comm, st);
         }
         int rc2 = g_nccl.GroupEnd();
         if (rc || rc2) { set_error("ncclSend/Recv", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc ? rc : rc2) : "error"); return -1; }
@@ -152,7 +153,7 @@ static int halo_sendrecv(Solver& S, size_t per_face, double* recv_base = nullptr
     }
     if (S.local_group) {
         LocalGroup* G = (LocalGroup*)S.local_group;
-        if (cudaStreamSynchronize(S.stream) != cudaSuccess) { set_error("halo", "stream sync failed"); return -1; }
+        if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("halo", "stream sync failed"); return -1; }
         pthread_barrier_wait(&G->barrier);  // every rank's send buffer is complete
         for (size_t i = 0; i < S.nbh_rank.size(); ++i) {
             Solver* P = G->peers[S.nbh_rank[i]];
@@ -162,9 +163,9 @@ static int halo_sendrecv(Solver& S, size_t per_face, double* recv_base = nullptr
                 if (P->nbh_rank[j] == S.desc.rank) { poff = (size_t)P->nbh_offset[j] * per_face; found = true; break; }
             if (!found) { set_error("halo", "asymmetric neighbour lists"); return -1; }
             size_t off = (size_t)S.nbh_offset[i] * per_face, cnt = (size_t)S.nbh_count[i] * per_face;
-            cudaMemcpyAsync(recv_base + off, P->d_send + poff, cnt * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
+            cudaMemcpyAsync(recv_base + off, P->d_send + poff, cnt * sizeof(double), cudaMemcpyDeviceToDevice, st);
         }
-        if (cudaStreamSynchronize(S.stream) != cudaSuccess) { set_error("halo", "copy failed"); return -1; }
+        if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("halo", "copy failed"); return -1; }
         pthread_barrier_wait(&G->barrier);  // peers may overwrite their send buffers now
         return 0;
     }

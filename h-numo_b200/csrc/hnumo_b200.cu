@@ -39,7 +39,7 @@ static bool use_pair(const Solver& S) { return (S.variant == 0 || S.variant == 4
     do {                                                                                                      \
         if ((S).ngl == 5 && (S).nq == 9) kern<5, 9><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args);  \
         else if ((S).ngl == 4 && (S).nq == 7) kern<4, 7><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args); \
-        else kern<0, 0><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args);                              \
+        else { smem_opt_in(kern<0, 0>, smem); kern<0, 0><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args); } \
     } while (0)
 #define HN_LAUNCH_GQL(kern, S, smem, args)                                                                    \
     do {                                                                                                      \
@@ -47,7 +47,7 @@ static bool use_pair(const Solver& S) { return (S.variant == 0 || S.variant == 4
         else if ((S).ngl == 5 && (S).nq == 9 && (S).nl == 3) kern<5, 9, 3><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args); \
         else if ((S).ngl == 5 && (S).nq == 9) kern<5, 9, 0><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args);                \
         else if ((S).ngl == 4 && (S).nq == 7) kern<4, 7, 0><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args);                \
-        else kern<0, 0, 0><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args);                            \
+        else { smem_opt_in(kern<0, 0, 0>, smem); kern<0, 0, 0><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args); } \
     } while (0)
 
 static int threads_for(const Solver& S);
@@ -187,9 +187,16 @@ static void fill_stage_args(Solver& S, StageArgs& a, Planes& qb, const Planes& q
     a.botfr = S.botfr; a.has_visc = S.has_visc; a.acc_graduvb = !use_fused(S); a.pf_blocks = S.pf_blocks;
 }
 
+// run-time-size kernels need the shared-memory opt-in above 48 kB (nop 8: 58 kB for the simple stage kernel)
+template <typename K>
+static void smem_opt_in(K kern, size_t bytes) {
+    if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 static int launch_stage(Solver& S, const StageArgs& a) {
     if (use_fused(S)) return launch_stage_fused(S, a);
     StageSmem L(S.ngl, S.nq);
+    smem_opt_in(k_btp_stage_simple, L.total * sizeof(double));
     k_btp_stage_simple<<<S.nelem, threads_for(S), L.total * sizeof(double), S.stream>>>(a);
     S.n_launches++;
     return 0;
@@ -214,6 +221,7 @@ int rhs_btp_only(Solver& S, Planes& qb, const Planes& qprime, double* d_rhs_out)
     a.tr_in = S.trace[0].p; a.tr_out = S.trace[1].p; a.rhs_only = 1;
     for (int v = 0; v < 3; ++v) a.rhs_out[v] = d_rhs_out + (size_t)v * S.npoin;
     StageSmem L(S.ngl, S.nq);
+    smem_opt_in(k_btp_stage_simple, L.total * sizeof(double));
     k_btp_stage_simple<<<S.nelem, threads_for(S), L.total * sizeof(double), S.stream>>>(a);
     S.n_launches++;
     HN_CUDA(cudaGetLastError());
@@ -298,12 +306,13 @@ int btp_solve(Solver& S, Planes& qb, const Planes& qprime) {
 }
 
 // halo exchange of trace records: gather -> send/recv straight into the halo region of the trace buffer
-static int halo_exchange_trace_records(Solver& S, double* tr, int tside) {
+static int halo_exchange_trace_records(Solver& S, double* tr, int tside, cudaStream_t st = nullptr) {
     if (S.nhalo == 0) return 0;
+    if (!st) st = S.stream;
     size_t tot = (size_t)S.nhalo * tside;
-    k_pack_trace_records<<<(tot + 255) / 256, 256, 0, S.stream>>>(tr, S.d_halo_slot, S.nhalo, tside, S.d_send);
+    k_pack_trace_records<<<(tot + 255) / 256, 256, 0, st>>>(tr, S.d_halo_slot, S.nhalo, tside, S.d_send);
     S.n_launches++;
-    return halo_sendrecv(S, (size_t)tside, tr + (size_t)S.nslots * tside);
+    return halo_sendrecv(S, (size_t)tside, tr + (size_t)S.nslots * tside, st);
 }
 
 // ti_barotropic_ssprk_mlswe (mod_rk_mlswe.F90:19-151) on the record layout with the TMA stage kernel
@@ -426,6 +435,12 @@ static int btp_solve_pair(Solver& S, Planes& qb, const Planes& qprime) {
     a.rec = S.p_rec; a.accf = S.p_accf;
     a.g = S.g; a.cd_g = S.cd / S.g; a.cd_alpha = S.cd / S.alpha[S.nl - 1]; a.visc = S.visc; a.botfr = S.botfr;
     a.prefetch = S.pair_prefetch; a.pf_dist = S.pair_pf_dist;
+    // Overlap: a stage of the elements that own a processor face runs on comm_stream, followed by the pack and
+    // the send/recv of their new traces; the stage of every other element runs on `stream` at the same time.  Both need
+    // only results of the previous stage: ev_int = "interior stage done" (awaited by the next boundary stage, which reads
+    // the traces of interior neighbours), ev_halo = "boundary stage + exchange done" (awaited by the next interior stage).
+    const bool overlap = S.overlap && S.nhalo > 0 && S.n_belem > 0;
+    if (overlap) { cudaEventRecord(S.ev0, S.stream); cudaEventRecord(S.ev1, S.stream); }
     for (int mstep = 1; mstep <= S.N_btp; ++mstep) {
         for (int ik = 1; ik <= S.kstages; ++ik) {
             a.a1 = S.ssprk_a[ik - 1][0]; a.a2 = S.ssprk_a[ik - 1][1]; a.a3 = S.ssprk_a[ik - 1][2];
@@ -435,11 +450,26 @@ static int btp_solve_pair(Solver& S, Planes& qb, const Planes& qprime) {
             a.store_q0 = (ik == 1 && S.kstages > 1);
             a.store_q2 = (S.kstages == 5 && ik == 2);
             a.tr_in = S.p_tr[cur]; a.tr_out = S.p_tr[cur ^ 1];
+            if (!overlap) {
+                a.part = 0;
+                if (launch_stage_pair(S, a)) return -1;
+                cur ^= 1;
+                if (halo_exchange_trace_records(S, S.p_tr[cur], D.TSIDE)) return -1;
+                continue;
+            }
+            cudaStreamWaitEvent(S.comm_stream, S.ev0, 0);   // interior stage s-1
+            cudaStreamWaitEvent(S.stream, S.ev1, 0);        // boundary stage s-1 and its exchange
+            a.part = 2;
+            if (launch_stage_pair(S, a)) return -1;
+            cudaEventRecord(S.ev0, S.stream);
+            a.part = 1; a.elist = S.d_belems; a.count = S.n_belem;
             if (launch_stage_pair(S, a)) return -1;
             cur ^= 1;
-            if (halo_exchange_trace_records(S, S.p_tr[cur], D.TSIDE)) return -1;
+            if (halo_exchange_trace_records(S, S.p_tr[cur], D.TSIDE, S.comm_stream)) return -1;
+            cudaEventRecord(S.ev1, S.comm_stream);
         }
     }
+    if (overlap) cudaStreamWaitEvent(S.stream, S.ev1, 0);
     cudaEventRecord(e_stop, S.stream);
     S.n_stages += (long)S.N_btp * S.kstages;
     // state back to planes, time averages
@@ -637,12 +667,17 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     if (d->device > 0) cudaSetDevice(d->device - 1);
     cudaGetDevice(&S.device);
     HN_CUDA(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
-    HN_CUDA(cudaStreamCreateWithFlags(&S.comm_stream, cudaStreamNonBlocking));
+    {   // the boundary/exchange stream overtakes the interior work
+        int pr_lo = 0, pr_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi);
+        HN_CUDA(cudaStreamCreateWithPriority(&S.comm_stream, cudaStreamNonBlocking, pr_hi));
+    }
     cudaEventCreate(&S.ev0); cudaEventCreate(&S.ev1); cudaEventCreate(&S.ev2); cudaEventCreate(&S.ev3);
     S.nelem = d->nelem; S.ngl = d->ngl; S.nq = d->nq; S.npts = d->ngl * d->ngl; S.nq2 = d->nq * d->nq; S.nl = d->nlayers; S.nface = d->nface;
     S.npoin = S.nelem * S.npts; S.npoin_q = S.nelem * S.nq2; S.nslots = S.nelem * 4;
     S.kstages = d->kstages; S.N_btp = d->N_btp; S.botfr = d->botfr; S.dt = d->dt; S.dt_btp = d->dt_btp; S.g = d->gravity; S.cd = d->cd_mlswe;
     S.visc = d->visc_mlswe; S.has_visc = (d->visc_mlswe != 0.0);
+    if (getenv("HNUMO_FORCE_VISC")) S.has_visc = 1;   // debugging aid: run the LDG code path with visc == 0
     S.variant = d->stage_kernel_variant;
     for (int k = 0; k < S.nl; ++k) S.alpha[k] = d->alpha_mlswe[k];
     for (int ik = 0; ik < S.kstages; ++ik) {
@@ -715,6 +750,13 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     if (S.nhalo > 0) {
         HN_CUDA(cudaMalloc(&S.d_halo_slot, S.nhalo * sizeof(int)));
         cudaMemcpy(S.d_halo_slot, S.halo_slot.data(), S.nhalo * sizeof(int), cudaMemcpyHostToDevice);
+        // elements that own a processor face, in element order (they advance ahead of the interior, see btp_solve_pair)
+        std::vector<int> bel;
+        for (int e = 0; e < S.nelem; ++e)
+            if (nbr[e * 4] == NBR_HALO || nbr[e * 4 + 1] == NBR_HALO || nbr[e * 4 + 2] == NBR_HALO || nbr[e * 4 + 3] == NBR_HALO) bel.push_back(e);
+        S.n_belem = (int)bel.size();
+        HN_CUDA(cudaMalloc(&S.d_belems, std::max<size_t>(bel.size(), 1) * sizeof(int)));
+        cudaMemcpy(S.d_belems, bel.data(), bel.size() * sizeof(int), cudaMemcpyHostToDevice);
     }
     Mesh& M = S.mesh;
     M.nelem = S.nelem; M.ngl = S.ngl; M.nq = S.nq; M.npts = S.npts; M.nq2 = S.nq2; M.nl = S.nl; M.npoin = S.npoin; M.npoin_q = S.npoin_q;
@@ -815,7 +857,7 @@ int hnumo_finalize(hnumo_handle_t h) {
     halo_comm_destroy(S);
     for (void* p : S.allocs) cudaFree(p);
     if (S.d_nbx) cudaFree(S.d_nbx);
-    cudaFree(S.d_nbr); cudaFree(S.d_nbslot); cudaFree(S.d_flag); if (S.d_halo_slot) cudaFree(S.d_halo_slot);
+    cudaFree(S.d_nbr); cudaFree(S.d_nbslot); cudaFree(S.d_flag); if (S.d_halo_slot) cudaFree(S.d_halo_slot); if (S.d_belems) cudaFree(S.d_belems);
     cudaEventDestroy(S.ev0); cudaEventDestroy(S.ev1); cudaEventDestroy(S.ev2); cudaEventDestroy(S.ev3);
     cudaStreamDestroy(S.stream); cudaStreamDestroy(S.comm_stream);
     delete h;
@@ -1025,6 +1067,7 @@ int hnumo_set_option(hnumo_handle_t h, const char* key, double value) {
     if (!strcmp(key, "pair_warps")) { S.pair_warps = (int)value; return 0; }
     if (!strcmp(key, "pair_prefetch")) { S.pair_prefetch = (int)value; return 0; }
     if (!strcmp(key, "pair_pf_dist")) { S.pair_pf_dist = (int)value; return 0; }
+    if (!strcmp(key, "overlap")) { S.overlap = (int)value; return 0; }
     set_error("hnumo_set_option", "unknown key");
     return -2;
 }

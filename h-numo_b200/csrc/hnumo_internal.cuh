@@ -137,6 +137,10 @@ struct Solver {
     // record layout of the element-pair stage kernel (stage_pair.cuh): one record per element, face sums, traces
     double *p_rec = nullptr, *p_accf = nullptr, *p_tr[2] = {nullptr, nullptr};
     int pair_ne = 1, pair_warps = 4, pair_prefetch = 0, pair_pf_dist = 0, pair_units_per_wave = 0;
+    // halo exchange overlapped with interior work: the elements that own a processor face advance on comm_stream
+    // (high priority) followed by pack + send/recv, every other element advances on `stream` at the same time
+    int* d_belems = nullptr;
+    int n_belem = 0, overlap = 1;
     int num_sms = 148, tma_blocks_per_sm = 0;
     int use_graph = 0;
     int pf_blocks = -1;   // L2 prefetch distance of the fused stage kernel, in thread blocks

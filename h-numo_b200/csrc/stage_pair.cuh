@@ -65,7 +65,7 @@ struct PairRec {
     // (profiles/smem_conflicts.py).
     static constexpr int pick(int lo, int mod) { return lo + ((mod - lo) % 16 + 16) % 16; }
     static constexpr int SX = pick(NQ2, Q);         // stride of the quadrature-point arrays
-    static constexpr int TM = 11;                   // row stride of the pass-1 arrays T[f][m][i]
+    static constexpr int TM = (Q <= 9) ? 11 : Q + 2;   // row stride of the pass-1 arrays T[f][m][i]
     static constexpr int ST = pick((G - 1) * TM + Q, Q);
     static constexpr int S_NOD = 0;                 // 0 dpp 1 mx 2 my 3 pb 4 pp 5 up 6 vp 7 u 8 v ; later 4..7 = LDG flux variable
     static constexpr int S_X = S_NOD + 9 * NP;      // 8 quadrature-point arrays; later rhs, face traces, face fluxes
@@ -88,6 +88,11 @@ struct PairArgs {
     double a1, a2, a3, dtt, g, cd_g, cd_alpha, visc;   // cd_g = cd/g (botfr 1), cd_alpha = cd/alpha_bottom (botfr 2)
     int botfr, load_q0, load_q2, store_q0, store_q2;
     int prefetch, pf_dist;   // bit 0: own record tail -> L2 at start; bit 1: head of the record pf_dist units ahead
+    // element subsets of a launch (halo exchange overlapped with interior work):
+    //   part 0: every element; part 1: the `count` elements of `elist` (those with a processor face);
+    //   part 2: every element that has no processor face (warps of the others leave once their header has arrived)
+    int part, count;
+    const int* elist;
 };
 
 // shared-memory vector of NE doubles
@@ -209,18 +214,26 @@ __device__ __forceinline__ int pr_face_node(int s, int n) {
 
 // BOTFR: 0 none, 1 linear bottom drag, 2 quadratic bottom drag (mod_rhs_btp.F90:149-169) -- compile time, so that the
 // pointwise phases are single basic blocks the scheduler can interleave
-template <int G, int Q, int NE, int W, bool VISC, int BOTFR>
+//
+// BLK = false: W warps per block, each warp advances NE elements (lane = thread within the warp, phases separated by
+//              __syncwarp).  Orders up to nop 4 (every per-lane item list fits in 32 lanes).
+// BLK = true : one element per block of NT = 32*W threads, same phases with "lane" = thread within the block and
+//              __syncthreads between them: high orders (nop 8: 81 nodes, 289 quadrature points, 68 face points per element).
+template <int NT> __device__ __forceinline__ void pr_sync() { if (NT == 32) __syncwarp(); else __syncthreads(); }
+template <int G, int Q, int NE, int W, bool VISC, int BOTFR, bool BLK = false>
 __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 168) : 128) k_btp_stage_pair(const PairArgs a) {
     using R = PairRec<G, Q>;
     using V = PV<NE>;
     typedef typename V::T VT;
     constexpr int NP = R::NP, NQ2 = R::NQ2, SX = R::SX, ST = R::ST, TM = R::TM;
-    constexpr int NQIT = (NQ2 + 31) / 32, NFIT = (4 * Q + 31) / 32;
-    static_assert(NP <= 32 && 4 * G <= 32 && 3 * Q <= 32 && 12 <= 32, "polynomial order too high for this lane mapping");
+    constexpr int NT = BLK ? 32 * W : 32;
+    constexpr int NQIT = (NQ2 + NT - 1) / NT, NFIT = (4 * Q + NT - 1) / NT;
+    static_assert(NP <= NT && 4 * G <= NT && 3 * Q <= NT && 12 <= NT && R::HDR <= NT, "polynomial order too high for this lane mapping");
+    static_assert(!BLK || NE == 1, "block-per-element mode advances one element");
     extern __shared__ __align__(16) double sm_all[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int unit = blockIdx.x * W + warp;
-    if (unit * NE >= a.nelem) return;
+    const int lane = BLK ? (int)threadIdx.x : (int)(threadIdx.x & 31), warp = BLK ? 0 : (int)(threadIdx.x >> 5);
+    const int unit = BLK ? (int)blockIdx.x : (int)(blockIdx.x * W + warp);
+    if (unit * NE >= a.count) return;
     PR_STAMP(0);
     double* smw = sm_all + (size_t)warp * ((size_t)R::S_TOTAL * NE + (size_t)R::HDR * NE);
     double* hdr = smw;                                   // [NE][HDR], plain doubles
@@ -235,8 +248,9 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
     double* rec[NE];
     PR_FORC {
         e[c] = unit * NE + c;
-        ok[c] = e[c] < a.nelem;
-        if (!ok[c]) e[c] = a.nelem - 1;
+        ok[c] = e[c] < a.count;
+        if (!ok[c]) e[c] = a.count - 1;
+        if (a.part == 1) e[c] = a.elist[e[c]];
         rec[c] = a.rec + (size_t)e[c] * R::REC;
     }
     constexpr bool botfr = BOTFR != 0;
@@ -263,7 +277,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
     double qs[NQIT][R::QST_NF][NE];
 #pragma unroll
     for (int it = 0; it < NQIT; ++it) {
-        const int q = min(it * 32 + lane, NQ2 - 1);
+        const int q = min(it * NT + lane, NQ2 - 1);
         PR_FORC {
             const double* rs = rec[c] + R::O_QST + q;
 #pragma unroll
@@ -283,10 +297,23 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
                 if (a.load_q2) pr_prefetch_l2(p + R::O_Q2, (uint32_t)(R::QBSZ * sizeof(double)));
             }
             // the head of the record (header, state, nodal statics and sums) of the unit that follows one wave later
-            if ((a.prefetch & 2) && (long)(unit + a.pf_dist) * NE + lane < a.nelem)
+            if ((a.prefetch & 2) && a.part != 1 && (long)(unit + a.pf_dist) * NE + lane < a.nelem)
                 pr_prefetch_l2(p + (size_t)a.pf_dist * NE * R::REC, (uint32_t)(R::O_QST * sizeof(double)));
         }
         if (lane < R::HDR) { PR_FORC hdr[c * R::HDR + lane] = hv[c]; }
+        if (a.part == 2) {   // interior launch: elements with a processor face belong to the boundary launch
+            bool any = false;
+            PR_FORC {
+                bool hb = false;
+                if (lane == 18 || lane == 19) {
+                    const int lo = __double2loint(hv[c]), hi_ = __double2hiint(hv[c]);
+                    hb = (lo == NBR_HALO) || (hi_ == NBR_HALO);
+                }
+                if (BLK ? __syncthreads_or(hb) : (__ballot_sync(0xffffffffu, hb) != 0u)) ok[c] = false;
+                any = any || ok[c];
+            }
+            if (!any) return;
+        }
     }
     if (lane < NP) {
         const int I = lane;
@@ -306,7 +333,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
         if (botfr) { V::st(nod + 4 * NP + I, pp); V::st(nod + 5 * NP + I, up); V::st(nod + 6 * NP + I, vp); }
         V::st(nod + 7 * NP + I, u); V::st(nod + 8 * NP + I, v);
     }
-    __syncwarp();
+    pr_sync<NT>();
     PR_STAMP(1);
     // per-element geometry and flags (registers)
     double ksx[NE], ksy[NE], etx[NE], ety[NE], J[NE];
@@ -352,13 +379,13 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
             pl_grad<NE, G, false>(nod + (7 + f) * NP + off, Lr + (2 * kind + f) * NP + off, stride);
         }
     }
-    __syncwarp();
+    pr_sync<NT>();
     PR_STAMP(2);
     // ---- 3. pass 2: one quadrature column per lane -> X[f][j][i]; LDG: G = grad(ub,vb), flux variable, weighted metric terms
     {
         const int nlines = (botfr ? 7 : 4) * Q;
 #pragma unroll 1
-        for (int it = lane; it < nlines; it += 32) {
+        for (int it = lane; it < nlines; it += NT) {
             const int f = it / Q, i = it - f * Q;
             pl_n2q<NE, G, Q, false, TM, Q>(T + f * ST + i, X + f * SX + i);
         }
@@ -382,13 +409,13 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
             V::st(Lr + 8 * NP + I, z0); V::st(Lr + 9 * NP + I, z1); V::st(Lr + 10 * NP + I, z2); V::st(Lr + 11 * NP + I, z3);
         }
     }
-    __syncwarp();
+    pr_sync<NT>();
     PR_STAMP(3);
     // ---- 4. pointwise physics at the quadrature points (mod_rhs_btp.F90:136-192); the fluxes overwrite X in place
 #pragma unroll
     for (int it = 0; it < NQIT; ++it) {
-        const int q = min(it * 32 + lane, NQ2 - 1);
-        const bool qvalid = (it + 1) * 32 <= NQ2 || it * 32 + lane < NQ2;
+        const int q = min(it * NT + lane, NQ2 - 1);
+        const bool qvalid = (it + 1) * NT <= NQ2 || it * NT + lane < NQ2;
         {
             const int j = q / Q, i = q - j * Q;
             const double w0 = c_ops.wq[i] * c_ops.wq[j];
@@ -439,8 +466,12 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
                 o7[c] = wq * (etx[c] * quv + ety[c] * Fy3);         // Fe3
             }
             // array order in X: Fk1 Fk2 Fk3 | Fe1 Fe2 Fe3 | S2 S3  (field f of a kind at a constant offset: conflict-free scatter)
-            V::st(X + 0 * SX + q, o0); V::st(X + 3 * SX + q, o1); V::st(X + 6 * SX + q, o2); V::st(X + 1 * SX + q, o3);
-            V::st(X + 4 * SX + q, o4); V::st(X + 7 * SX + q, o5); V::st(X + 2 * SX + q, o6); V::st(X + 5 * SX + q, o7);
+            // (lanes past the last point work on a copy of it: within one warp their loads precede every store, across the
+            //  warps of a block they would race with the in-place update of that point)
+            if (NT == 32 || qvalid) {
+                V::st(X + 0 * SX + q, o0); V::st(X + 3 * SX + q, o1); V::st(X + 6 * SX + q, o2); V::st(X + 1 * SX + q, o3);
+                V::st(X + 4 * SX + q, o4); V::st(X + 7 * SX + q, o5); V::st(X + 2 * SX + q, o6); V::st(X + 5 * SX + q, o7);
+            }
         }
     }
     // neighbour traces and the neighbour's viscosity statics of face node (s,n), issued one phase ahead
@@ -462,7 +493,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
             }
         }
     }
-    __syncwarp();
+    pr_sync<NT>();
     PR_STAMP(4);
     // ---- 5. scatter pass 1 (contraction over j): lane (f,i) -> TB_f = A.Fk_f, TA_f = B.Fe_f + A.S_f, as T[f][m][i], T[3+f][m][i]
     if (lane < 3 * Q) {
@@ -474,7 +505,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
 #pragma unroll
         for (int m = 0; m < G; ++m) { V::st(T + f * ST + m * TM + i, tb[m]); V::st(T + (3 + f) * ST + m * TM + i, ta[m]); }
     }
-    __syncwarp();
+    pr_sync<NT>();
     PR_STAMP(5);
     // ---- 6. scatter pass 2 (contraction over i): lane (f,m) -> rhs[f][m][n] = B.TB_f + A.TA_f
     if (lane < 3 * G) {
@@ -562,7 +593,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
     double fc[NFIT][11][NE];
 #pragma unroll
     for (int it = 0; it < NFIT; ++it) {
-        const int p = min(it * 32 + lane, 4 * Q - 1);
+        const int p = min(it * NT + lane, 4 * Q - 1);
         {
             const int s = p / Q, iq = p - s * Q;
             PR_FORC {
@@ -580,10 +611,10 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
             }
         }
     }
-    __syncwarp();
+    pr_sync<NT>();
     PR_STAMP(6);
     // ---- 7b. interpolate the traces to the face quadrature points: one (side, L/R, variable) line per lane
-    {
+    if (NT == 32 || lane < 32) {
         const int s = lane >> 3, side = (lane >> 2) & 1, var = lane & 3;   // var: 0 pb 1 pbpert 2 mx 3 my
         pl_n2q<NE, G, Q, false, 1, 1>(X + R::X_FL + side * 16 * G + (var * 4 + s) * G, T + lane * Q);
     }
@@ -600,13 +631,13 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
             }
         }
     }
-    __syncwarp();
+    pr_sync<NT>();
     PR_STAMP(7);
     // ---- 7c. face fluxes, canonical left perspective (mod_rhs_btp.F90:237-330)
 #pragma unroll
     for (int it = 0; it < NFIT; ++it) {
-        const int p = min(it * 32 + lane, 4 * Q - 1);
-        const bool pvalid = (it + 1) * 32 <= 4 * Q || it * 32 + lane < 4 * Q;
+        const int p = min(it * NT + lane, 4 * Q - 1);
+        const bool pvalid = (it + 1) * NT <= 4 * Q || it * NT + lane < 4 * Q;
         {
             const int s = p / Q, iq = p - s * Q;
             const VT* Lp = T + (s * 8) * Q + iq;
@@ -656,7 +687,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
             V::st(ff, f0); V::st(ff + Q, f1); V::st(ff + 2 * Q, f2);
         }
     }
-    __syncwarp();
+    pr_sync<NT>();
     PR_STAMP(8);
     // ---- 7d. project the face fluxes onto the face nodes: one (side, field) line per lane -> T[0 .. 12G)
     if (lane < 12) {
@@ -665,7 +696,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
 #pragma unroll
         for (int n = 0; n < G; ++n) V::st(T + lane * G + n, pr[n]);
     }
-    __syncwarp();
+    pr_sync<NT>();
     PR_STAMP(9);
     // ---- 8. gather per node, mass matrix, viscosity, SSPRK update, wall projection (mod_rk_mlswe.F90:97-108)
     if (lane < NP) {
@@ -730,7 +761,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
         V::st(nod + 0 * NP + I, nw0); V::st(nod + 1 * NP + I, nw1); V::st(nod + 2 * NP + I, nw2);
         V::st(nod + 7 * NP + I, un_); V::st(nod + 8 * NP + I, vn_);
     }
-    __syncwarp();
+    pr_sync<NT>();
     PR_STAMP(10);
     // ---- 9. traces of the new state (+ LDG gradient) for the next stage
     if (VISC) {
@@ -739,7 +770,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
             const int stride = kind ? G : 1, off = kind ? l : l * G;
             pl_grad<NE, G, false>(nod + (7 + f) * NP + off, Lr + (2 * kind + f) * NP + off, stride);
         }
-        __syncwarp();
+        pr_sync<NT>();
         PR_STAMP(11);
     }
     if (lane < 4 * G) {
@@ -777,8 +808,8 @@ inline PairDims make_pairdims_t() {
     d.FSIDE = R::FSIDE; d.VSIDE = R::VSIDE; d.ASIDE = R::ASIDE; d.TSIDE = R::TSIDE;
     return d;
 }
-inline bool stage_pair_supported(const Solver& S) { return (S.ngl == 5 && S.nq == 9) || (S.ngl == 4 && S.nq == 7); }
-inline PairDims make_pairdims(int G, int Q) { return (G == 5) ? make_pairdims_t<5, 9>() : make_pairdims_t<4, 7>(); }
+inline bool stage_pair_supported(const Solver& S) { return (S.ngl == 5 && S.nq == 9) || (S.ngl == 4 && S.nq == 7) || (S.ngl == 9 && S.nq == 17); }
+inline PairDims make_pairdims(int G, int Q) { return (G == 9) ? make_pairdims_t<9, 17>() : (G == 5) ? make_pairdims_t<5, 9>() : make_pairdims_t<4, 7>(); }
 
 struct PairPackArgs {
     Mesh M;
@@ -912,11 +943,11 @@ __global__ void k_pair_sum_traces(int nelem, PairDims D, const double* rec, doub
     for (int k = 0; k < 3; ++k) to[k * D.G] = rec[e * D.REC + D.O_ACCN + (3 + k) * D.NP + I];
 }
 
-template <int G, int Q, int NE, int W, bool VISC, int BOTFR>
+template <int G, int Q, int NE, int W, bool VISC, int BOTFR, bool BLK = false>
 static int launch_pair_k(Solver& S, const PairArgs& a) {
     using R = PairRec<G, Q>;
-    const size_t smem = R::smem_bytes(NE, W);
-    auto kern = k_btp_stage_pair<G, Q, NE, W, VISC, BOTFR>;
+    const size_t smem = R::smem_bytes(NE, BLK ? 1 : W);
+    auto kern = k_btp_stage_pair<G, Q, NE, W, VISC, BOTFR, BLK>;
     static bool configured = false;
     static int units_per_wave = 0;
     if (!configured) {
@@ -927,30 +958,32 @@ static int launch_pair_k(Solver& S, const PairArgs& a) {
         configured = true;
         int nb = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * W, smem);
-        units_per_wave = nb * W * S.num_sms;
+        units_per_wave = nb * (BLK ? 1 : W) * S.num_sms;
         if (getenv("HNUMO_DEBUG"))
-            fprintf(stderr, "[hnumo] element-record stage kernel NE=%d W=%d visc=%d botfr=%d: %zu B smem/block, %d blocks/SM (%d warps)\n", NE, W,
-                    (int)VISC, BOTFR, smem, nb, nb * W);
+            fprintf(stderr, "[hnumo] element-record stage kernel G=%d NE=%d W=%d blk=%d visc=%d botfr=%d: %zu B smem/block, %d blocks/SM (%d warps)\n", G, NE, W,
+                    (int)BLK, (int)VISC, BOTFR, smem, nb, nb * W);
     }
     PairArgs b = a;
     if (b.pf_dist <= 0) b.pf_dist = units_per_wave;
-    const int units = (S.nelem + NE - 1) / NE;
-    const int blocks = (units + W - 1) / W;
-    kern<<<blocks, 32 * W, smem, S.stream>>>(b);
+    if (b.part != 1) b.count = S.nelem;
+    if (b.count <= 0) return 0;
+    const int units = (b.count + NE - 1) / NE;
+    const int blocks = BLK ? units : (units + W - 1) / W;
+    kern<<<blocks, 32 * W, smem, b.part == 1 ? S.comm_stream : S.stream>>>(b);
     S.n_launches++;
     return 0;
 }
-template <int G, int Q, int NE, int W>
+template <int G, int Q, int NE, int W, bool BLK = false>
 static int launch_pair_w(Solver& S, const PairArgs& a) {
     const int bf = S.botfr == 1 ? 1 : S.botfr == 2 ? 2 : 0;
     if (S.has_visc) {
-        if (bf == 1) return launch_pair_k<G, Q, NE, W, true, 1>(S, a);
-        if (bf == 2) return launch_pair_k<G, Q, NE, W, true, 2>(S, a);
-        return launch_pair_k<G, Q, NE, W, true, 0>(S, a);
+        if (bf == 1) return launch_pair_k<G, Q, NE, W, true, 1, BLK>(S, a);
+        if (bf == 2) return launch_pair_k<G, Q, NE, W, true, 2, BLK>(S, a);
+        return launch_pair_k<G, Q, NE, W, true, 0, BLK>(S, a);
     }
-    if (bf == 1) return launch_pair_k<G, Q, NE, W, false, 1>(S, a);
-    if (bf == 2) return launch_pair_k<G, Q, NE, W, false, 2>(S, a);
-    return launch_pair_k<G, Q, NE, W, false, 0>(S, a);
+    if (bf == 1) return launch_pair_k<G, Q, NE, W, false, 1, BLK>(S, a);
+    if (bf == 2) return launch_pair_k<G, Q, NE, W, false, 2, BLK>(S, a);
+    return launch_pair_k<G, Q, NE, W, false, 0, BLK>(S, a);
 }
 template <int G, int Q>
 static int launch_pair_t(Solver& S, const PairArgs& a) {
@@ -961,6 +994,8 @@ static int launch_pair_t(Solver& S, const PairArgs& a) {
 inline int launch_stage_pair(Solver& S, const PairArgs& a) {
     if (S.ngl == 5 && S.nq == 9) return launch_pair_t<5, 9>(S, a);
     if (S.ngl == 4 && S.nq == 7) return launch_pair_t<4, 7>(S, a);
+    // nop 8: one element per block of 128 threads (81 nodes, 119 pass-2 lines, 68 face points fit; 289 quadrature points in 3 sweeps)
+    if (S.ngl == 9 && S.nq == 17) return launch_pair_w<9, 17, 1, 4, true>(S, a);
     return -1;
 }
 

@@ -16,6 +16,11 @@ import oracle_lib
 
 pytestmark = pytest.mark.gpu
 
+def _nop8_small_step():
+    base = hn.decks.synthetic_double_gyre(3, 4, nop=8, nlayers=2)
+    return hn.decks.synthetic_double_gyre(3, 4, nop=8, nlayers=2, dt_btp=base["dt_btp"] / 2.5, dt=base["dt_btp"] * 4)
+
+
 DECKS = {
     "bump": lambda: dict(hn.decks.SHIPPED["bump"]),
     "lake": lambda: dict(hn.decks.SHIPPED["lake"]),
@@ -23,6 +28,11 @@ DECKS = {
     "synth3": lambda: hn.decks.synthetic_double_gyre(8, 8, nop=4, nlayers=3),
     "noslip_rk3": lambda: dict(hn.decks.SHIPPED["double_gyre"], nelx=6, nely=5, x_boundary=(2, 2), kstages=3, botfr=2, cd_mlswe=1e-3),
     "nop3_5layers": lambda: dict(hn.decks.synthetic_double_gyre(5, 5, nop=3, nlayers=5)),
+    # BASELINE config 5 in small: nop 8 runs the element-record kernel in its block-per-element form (variant 0)
+    "nop8": lambda: dict(hn.decks.synthetic_double_gyre(4, 3, nop=8, nlayers=3)),
+    # SSPRK(3,3) needs a smaller barotropic step than the shipped SSP(5,3) at the same resolution
+    "nop8_noslip_drag2": lambda: dict(_nop8_small_step(), x_boundary=(2, 2), botfr=2, cd_mlswe=1e-3, kstages=3),
+    "nop8_inviscid": lambda: dict(hn.decks.synthetic_double_gyre(3, 3, nop=8, nlayers=2), visc_mlswe=0.0, botfr=0),
 }
 VARIANTS = [0, 1, 2, 3, 5]  # 0: element-record kernel (default), 1: simple reference-form kernel, 2/3: record-layout TMA kernels, 5: warp-per-element kernel
 
@@ -98,6 +108,18 @@ def test_phase_parity(name, variant):
     S.close()
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("name", ["nop8", "nop8_noslip_drag2", "nop8_inviscid"])
+def test_phase_parity_high_order(name, variant):
+    test_phase_parity(name, variant)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("name,nsteps", [("nop8", 2), ("nop8_noslip_drag2", 2), ("nop8_inviscid", 2)])
+def test_step_parity_high_order(name, nsteps, variant):
+    test_step_parity(name, nsteps, variant)
+
+
 @pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("name,nsteps", [("bump", 5), ("lake", 5), ("double_gyre", 5), ("synth3", 5), ("noslip_rk3", 4), ("nop3_5layers", 4)])
 def test_step_parity(name, nsteps, variant):
@@ -162,11 +184,13 @@ def test_variants_agree_bitwise_on_mass():
         assert rel_l2(outs[k][0][:, :, 0], outs[1][0][:, :, 0]) < 1e-12
 
 
-def _run_partitioned(params, nranks, nsteps, gid, variant=0):
+def _run_partitioned(params, nranks, nsteps, gid, variant=0, options=()):
     decks = [hn.decks.build_deck(params, r, nranks) for r in range(nranks)]
     solvers = [hn.Solver(d, variant=variant) for d in decks]
     for S, d in zip(solvers, decks):
         S.comm_init(hn.local_group_id(gid))
+        for k, v in options:
+            S.set_option(k, v)
         S.upload_state(d["q_df"], d["qb_df"], d["qprime_df"])
     rcs = [None] * nranks
 
@@ -211,3 +235,34 @@ def test_partitioned_equals_single(nranks, visc, variant):
             assert np.linalg.norm(qb[:, v] - qb1[idx, v]) / (c * np.linalg.norm(qb1[idx, 0])) < tol
         for v in (1, 2):
             assert np.linalg.norm(q[:, :, v] - q1[:, idx, v]) / (c * np.linalg.norm(q1[:, idx, 0])) < tol
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_partitioned_high_order(nranks):
+    """nop 8 on 2 and 4 partitions (block-per-element stage kernel, overlapped exchange) == 1 partition"""
+    params = dict(hn.decks.synthetic_double_gyre(3, 4, nop=8, nlayers=2), visc_mlswe=0.0)
+    single = hn.decks.build_deck(params)
+    S = hn.Solver(single)
+    S.upload_state(single["q_df"], single["qb_df"], single["qprime_df"])
+    assert S.step(2) == 0
+    q1, qb1, qp1 = S.download_state()
+    S.close()
+    decks, outs = _run_partitioned(params, nranks, 2, gid=400 + nranks)
+    npts = single["npts"]
+    c = np.sqrt(single["gravity"] * 9928.0)
+    for d, (q, qb, qp) in zip(decks, outs):
+        idx = (d["elem_global"][:, None] * npts + np.arange(npts)[None, :]).ravel()
+        assert rel_l2(qb[:, 0], qb1[idx, 0]) < 1e-13
+        for v in (2, 3):
+            assert np.linalg.norm(qb[:, v] - qb1[idx, v]) / (c * np.linalg.norm(qb1[idx, 0])) < 1e-13
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_overlapped_exchange_is_bitwise_the_serial_one(nranks):
+    """the boundary elements advance on the exchange stream while the interior advances on the compute
+    stream.  The per-element arithmetic does not change, so the result must be bit-identical to exchange-after-stage."""
+    params = dict(hn.decks.synthetic_double_gyre(9, 8, nop=4, nlayers=3))
+    _, on = _run_partitioned(params, nranks, 3, gid=300 + nranks, options=(("overlap", 1),))
+    _, off = _run_partitioned(params, nranks, 3, gid=310 + nranks, options=(("overlap", 0),))
+    for (q, qb, qp), (q0, qb0, qp0) in zip(on, off):
+        assert np.array_equal(q, q0) and np.array_equal(qb, qb0) and np.array_equal(qp, qp0)
