@@ -147,6 +147,20 @@ __device__ __forceinline__ void pr_red(double* p, double v) { }
 __device__ __forceinline__ void pr_red(double* p, double v) { atomicAdd(p, v); }
 #endif
 
+// Bulk running sums: the contributions of one element are staged in shared memory in the layout of the sum arrays of its
+// record and added to them by ONE asynchronous bulk reduction (cp.reduce.async.bulk .add.f64, executed by the TMA unit)
+// instead of one RED instruction per 32 values: under load every global store/RED instruction holds the issuing warp
+// for 70-150 cycles (profiles/phase_timing.py with -DHN_PAIR_DIAG), 46 of them per element.  Every address still
+// receives exactly one add per launch: bitwise the same sums.
+__device__ __forceinline__ void pr_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void pr_bulk_add(double* gdst, const double* ssrc, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
+                 ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pr_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void pr_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ double* pr_align16(double* p) { return reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15); }
+
 __device__ __forceinline__ void pr_prefetch_l2(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
@@ -219,17 +233,40 @@ __device__ __forceinline__ int pr_face_node(int s, int n) {
 //              __syncwarp).  Orders up to nop 4 (every per-lane item list fits in 32 lanes).
 // BLK = true : one element per block of NT = 32*W threads, same phases with "lane" = thread within the block and
 //              __syncthreads between them: high orders (nop 8: 81 nodes, 289 quadrature points, 68 face points per element).
+#ifndef HN_BLK_MAXNREG
+#define HN_BLK_MAXNREG 96    // registers per thread of the block-per-element form: 96 -> 5 blocks of 128 threads per SM (no spills; 0.494 of the roofline vs 0.464 with 128 registers and 4 blocks)
+#endif
 template <int NT> __device__ __forceinline__ void pr_sync() { if (NT == 32) __syncwarp(); else __syncthreads(); }
 template <int G, int Q, int NE, int W, bool VISC, int BOTFR, bool BLK = false>
-__global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 168) : 128) k_btp_stage_pair(const PairArgs a) {
+__global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE == 2 ? (W == 4 ? 224 : 168) : 128) k_btp_stage_pair(const PairArgs a) {
     using R = PairRec<G, Q>;
     using V = PV<NE>;
     typedef typename V::T VT;
     constexpr int NP = R::NP, NQ2 = R::NQ2, SX = R::SX, ST = R::ST, TM = R::TM;
     constexpr int NT = BLK ? 32 * W : 32;
+    // Running sums by bulk reduction: measured SLOWER than the RED instructions (1.567 vs 1.533 ms per stage at 500x500: the time
+    // of the pointwise phase is the wait for the quadrature statics under a saturated memory system, not the issue of the REDs;
+    // profiles/r1_stage_kernel_experiments.md), so it is compiled only on request.
+#ifdef HN_PAIR_BULK
+    constexpr bool BULK = !BLK && NE == 1;
+#else
+    constexpr bool BULK = false;
+#endif
     constexpr int NQIT = (NQ2 + NT - 1) / NT, NFIT = (4 * Q + NT - 1) / NT;
     static_assert(NP <= NT && 4 * G <= NT && 3 * Q <= NT && 12 <= NT && R::HDR <= NT, "polynomial order too high for this lane mapping");
     static_assert(!BLK || NE == 1, "block-per-element mode advances one element");
+    // BLK: the independent jobs of a line phase are given to different warps of the block (different schedulers) instead of
+    // one after the other to the lowest lanes: job lane offsets (0 in warp mode)
+    constexpr int J2B = BLK ? 4 * G : 0, J2C = BLK ? 64 : 0;   // phase 2: bottom-layer rows, LDG gradient lines
+    constexpr int J5A = BLK ? 64 : 0;                           // phase 5: the B.Fe + A.S contraction
+    constexpr int J6B = BLK ? 32 : 0, J6C = BLK ? 32 + 4 * G : 0;   // phase 6: LDG laplacian lines, face traces
+    static_assert(!BLK || (J2B + 3 * G <= J2C && J2C + 4 * G <= NT && J5A + 3 * Q <= NT && 3 * Q <= J5A && 3 * G <= J6B && J6C + 4 * G <= NT),
+                  "job lane ranges");
+    static_assert(!BULK || (6 * NQ2 + 2 <= R::T_SZ + 4 * NP && 6 * NP + 2 <= 8 * NP), "staging of the quadrature / nodal sums");
+    // staging of the face sums of the 4 sides: behind the face work in X, behind the interpolated traces in T, in Lr[4..11]
+    constexpr int FS_X = (8 * SX - R::X_FF - 12 * Q - 2) / R::ASIDE, FS_T = (R::T_SZ - 32 * Q - 2) / R::ASIDE, FS_L = (8 * NP - 2) / R::ASIDE;
+    static_assert(!BULK || FS_X + FS_T + FS_L >= 4, "staging of the face sums");
+    static_assert(!BULK || ((6 * NQ2 * 8) % 16 == 0 && (R::ASIDE * 8) % 16 == 0 && (6 * NP * 8) % 16 == 0), "bulk sizes are multiples of 16 bytes");
     extern __shared__ __align__(16) double sm_all[];
     const int lane = BLK ? (int)threadIdx.x : (int)(threadIdx.x & 31), warp = BLK ? 0 : (int)(threadIdx.x >> 5);
     const int unit = BLK ? (int)blockIdx.x : (int)(blockIdx.x * W + warp);
@@ -323,7 +360,10 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
             const double rpb = pr_rcp(pb[c]);
             u[c] = mx[c] * rpb; v[c] = my[c] * rpb;
             const double t = 1.0 + dpp[c] * oop[c];
-            if (ok[c]) {
+            if (BULK) {   // staged in Lr[4..11] (free until the LDG part of phase 3)
+                double* sg = pr_align16(reinterpret_cast<double*>(Lr + 4 * NP)) + I;
+                sg[0] = t * t; sg[NP] = u[c]; sg[2 * NP] = v[c]; sg[3 * NP] = dpp[c]; sg[4 * NP] = mx[c]; sg[5 * NP] = my[c];
+            } else if (ok[c]) {
                 double* r = rec[c];
                 pr_red(r + R::O_ACCN + I, t * t); pr_red(r + R::O_ACCN + NP + I, u[c]); pr_red(r + R::O_ACCN + 2 * NP + I, v[c]);
                 pr_red(r + R::O_ACCN + 3 * NP + I, dpp[c]); pr_red(r + R::O_ACCN + 4 * NP + I, mx[c]); pr_red(r + R::O_ACCN + 5 * NP + I, my[c]);
@@ -332,8 +372,14 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
         V::st(nod + 0 * NP + I, dpp); V::st(nod + 1 * NP + I, mx); V::st(nod + 2 * NP + I, my); V::st(nod + 3 * NP + I, pb);
         if (botfr) { V::st(nod + 4 * NP + I, pp); V::st(nod + 5 * NP + I, up); V::st(nod + 6 * NP + I, vp); }
         V::st(nod + 7 * NP + I, u); V::st(nod + 8 * NP + I, v);
+        if (BULK) pr_fence_async_smem();
     }
     pr_sync<NT>();
+    if (BULK && lane == 0) {
+        static_assert((6 * NP * 8) % 16 == 0 || !BULK, "bulk size");
+        pr_bulk_add(rec[0] + R::O_ACCN, pr_align16(reinterpret_cast<double*>(Lr + 4 * NP)), 6 * NP * 8);
+        pr_bulk_commit();
+    }
     PR_STAMP(1);
     // per-element geometry and flags (registers)
     double ksx[NE], ksy[NE], etx[NE], ety[NE], J[NE];
@@ -369,15 +415,16 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
             const int f = lane / G, m = lane - f * G;
             pl_n2q<NE, G, Q, false, 1, 1>(nod + f * NP + m * G, T + f * ST + m * TM);
         }
-        if (botfr && lane < 3 * G) {
-            const int f = 4 + lane / G, m = lane % G;
+        if (botfr && lane >= J2B && lane < J2B + 3 * G) {
+            const int lj = lane - J2B, f = 4 + lj / G, m = lj % G;
             pl_n2q<NE, G, Q, false, 1, 1>(nod + f * NP + m * G, T + f * ST + m * TM);
         }
-        if (VISC && lane < 4 * G) {
-            const int kind = lane / (2 * G), r = lane - kind * 2 * G, f = r / G, l = r - f * G;
+        if (VISC && lane >= J2C && lane < J2C + 4 * G) {
+            const int lj = lane - J2C, kind = lj / (2 * G), r = lj - kind * 2 * G, f = r / G, l = r - f * G;
             const int stride = kind ? G : 1, off = kind ? l : l * G;
             pl_grad<NE, G, false>(nod + (7 + f) * NP + off, Lr + (2 * kind + f) * NP + off, stride);
         }
+        if (BULK && lane == 0) pr_bulk_wait_read();   // the staged nodal sums have been read: Lr[4..11] may be rewritten
     }
     pr_sync<NT>();
     PR_STAMP(2);
@@ -449,7 +496,13 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
                 const double qu = ub * udp[c] + ope * s_uu;
                 const double quv = ub * vdp[c] + ope * s_uv;
                 const double qv = vb * vdp[c] + ope * s_vv;
-                if (qvalid && ok[c]) {
+                if (BULK) {   // staged in T and Lr[0..3] (contiguous; free between phase 3 and the stores of phase 5)
+                    if (qvalid) {
+                        double* sg = pr_align16(reinterpret_cast<double*>(T)) + q;
+                        sg[0] = qu; sg[NQ2] = qv; sg[2 * NQ2] = quv; sg[3 * NQ2] = ope2; sg[4 * NQ2] = ub; sg[5 * NQ2] = vb;
+                        if (BOTFR == 2) { double* rr_ = rec[c] + R::O_ACCQR + q; pr_red(rr_, tb_u); pr_red(rr_ + NQ2, tb_v); }
+                    }
+                } else if (qvalid && ok[c]) {
                     double* ra = rec[c] + R::O_ACCQ + q;
                     pr_red(ra, qu); pr_red(ra + NQ2, qv); pr_red(ra + 2 * NQ2, quv);
                     pr_red(ra + 3 * NQ2, ope2); pr_red(ra + 4 * NQ2, ub); pr_red(ra + 5 * NQ2, vb);
@@ -476,8 +529,10 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
     }
     // neighbour traces and the neighbour's viscosity statics of face node (s,n), issued one phase ahead
     double tn[7][NE], vs[6][NE];
-    const int fs = lane / G, fn = lane - fs * G;   // face node owned by this lane (lane < 4G)
-    if (lane < 4 * G) {
+    const int lf = lane - J6C;                     // face node owned by this lane (0 <= lf < 4G)
+    const bool face_lane = lf >= 0 && lf < 4 * G;
+    const int fs = face_lane ? lf / G : 0, fn = face_lane ? lf - fs * G : 0;
+    if (face_lane) {
         PR_FORC {
             const int tr = reinterpret_cast<const int*>(hdr + c * R::HDR + 18)[4 + fs];
             if (tr >= 0) {
@@ -493,17 +548,32 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
             }
         }
     }
+    if (BULK) pr_fence_async_smem();
     pr_sync<NT>();
+    if (BULK && lane == 0) {
+        pr_bulk_add(rec[0] + R::O_ACCQ, pr_align16(reinterpret_cast<double*>(T)), 6 * NQ2 * 8);
+        pr_bulk_commit();
+    }
     PR_STAMP(4);
     // ---- 5. scatter pass 1 (contraction over j): lane (f,i) -> TB_f = A.Fk_f, TA_f = B.Fe_f + A.S_f, as T[f][m][i], T[3+f][m][i]
     if (lane < 3 * Q) {
         const int f = lane / Q, i = lane - f * Q;
-        double tb[G][NE], ta[G][NE];
+        double tb[G][NE];
         pl_q2n_acc<NE, G, Q, false, Q, true>(X + f * SX + i, tb);
+        if (BULK) {   // the staged quadrature sums (in T) must have been read before T is rewritten
+            if (lane == 0) pr_bulk_wait_read();
+            __syncwarp((1u << (3 * Q < 32 ? 3 * Q : 31)) - 1u);
+        }
+#pragma unroll
+        for (int m = 0; m < G; ++m) V::st(T + f * ST + m * TM + i, tb[m]);
+    }
+    if (lane >= J5A && lane < J5A + 3 * Q) {
+        const int lj = lane - J5A, f = lj / Q, i = lj - f * Q;
+        double ta[G][NE];
         pl_q2n_acc<NE, G, Q, true, Q, true>(X + (3 + f) * SX + i, ta);
         if (f > 0) pl_q2n_acc<NE, G, Q, false, Q, false>(X + (5 + f) * SX + i, ta);
 #pragma unroll
-        for (int m = 0; m < G; ++m) { V::st(T + f * ST + m * TM + i, tb[m]); V::st(T + (3 + f) * ST + m * TM + i, ta[m]); }
+        for (int m = 0; m < G; ++m) V::st(T + (3 + f) * ST + m * TM + i, ta[m]);
     }
     pr_sync<NT>();
     PR_STAMP(5);
@@ -517,14 +587,14 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
         for (int n = 0; n < G; ++n) V::st(X + R::X_RHS + f * NP + m * G + n, r[n]);
     }
     // LDG volume lines (btp_compute_laplacian): lapX[c][m'][n'] = sum_n D(n',n) Zxi_c[m'][n]; lapE[c][m'][n'] = sum_m D(m',m) Zeta_c[m][n']
-    if (VISC && lane < 4 * G) {
-        const int kind = lane / (2 * G), r = lane - kind * 2 * G, cc = r / G, l = r - cc * G;
+    if (VISC && lane >= J6B && lane < J6B + 4 * G) {
+        const int lj = lane - J6B, kind = lj / (2 * G), r = lj - kind * 2 * G, cc = r / G, l = r - cc * G;
         const int stride = kind ? G : 1, off = kind ? l : l * G;
         pl_grad<NE, G, true>(Lr + (8 + 2 * kind + cc) * NP + off, Lr + (2 * kind + cc) * NP + off, stride);
     }
     // ---- 7a. face traces: own and neighbour state in canonical (left, right) order; LDG face flux at the face nodes,
     //          as written (btp_extract_df; mod_laplacian_quad.F90:85-98,427-519)
-    if (lane < 4 * G) {
+    if (face_lane) {
         const int s = fs, n = fn, I = pr_face_node<G>(s, n);
         double ow0[NE], ow1[NE], ow2[NE], pbo[NE];
         V::ld(nod + 0 * NP + I, ow0); V::ld(nod + 1 * NP + I, ow1); V::ld(nod + 2 * NP + I, ow2); V::ld(nod + 3 * NP + I, pbo);
@@ -583,8 +653,8 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
                 lfu[c] = sgn * flux_qu; lfv[c] = sgn * flux_qv;
             }
         }
-        VT* FL = X + R::X_FL + lane;   // [side][var][s][n]: the word index follows the lane number
-        VT* FR = X + R::X_FR + lane;
+        VT* FL = X + R::X_FL + lf;   // [side][var][s][n]: the word index follows the lane number
+        VT* FR = X + R::X_FR + lf;
         V::st(FL, L0); V::st(FL + 4 * G, L1); V::st(FL + 8 * G, L2); V::st(FL + 12 * G, L3);
         V::st(FR, R0); V::st(FR + 4 * G, R1); V::st(FR + 8 * G, R2); V::st(FR + 12 * G, R3);
         if (VISC) { V::st(X + R::X_LF + (s * 2 + 0) * G + n, lfu); V::st(X + R::X_LF + (s * 2 + 1) * G + n, lfv); }
@@ -668,7 +738,17 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
                 const double qvv = 0.5 * (vl * myL[c] + vr * myR[c]) + ope_e * s_vve;
                 const double e2 = ope_e * ope_e;
                 const double Hf = e2 * s_He;
-                if (left && pvalid && ok[c]) {
+                if (BULK) {   // staged per side: sides 0..2 behind the face work in X, side 3 behind the traces in T
+                    if (left && pvalid) {
+                        const double ol = 1.0 + ppL[c] * fc[it][9][c], orr = 1.0 + ppR[c] * fc[it][10][c];
+                        double* sg = (s < FS_X ? pr_align16(reinterpret_cast<double*>(X) + R::X_FF + 12 * Q) + s * R::ASIDE
+                                      : s < FS_X + FS_T ? pr_align16(reinterpret_cast<double*>(T) + 32 * Q) + (s - FS_X) * R::ASIDE
+                                                        : pr_align16(reinterpret_cast<double*>(Lr + 4 * NP)) + (s - FS_X - FS_T) * R::ASIDE) + iq;
+                        sg[0] = quu; sg[Q] = quv; sg[2 * Q] = qvu; sg[3 * Q] = qvv; sg[4 * Q] = ol * ol; sg[5 * Q] = orr * orr; sg[6 * Q] = e2;
+                        sg[7 * Q] = ul; sg[8 * Q] = ur; sg[9 * Q] = vl; sg[10 * Q] = vr;
+                        if (11 * Q < R::ASIDE && iq == 0) sg[11 * Q] = 0.0;   // pad word of the side
+                    }
+                } else if (left && pvalid && ok[c]) {
                     const double ol = 1.0 + ppL[c] * fc[it][9][c], orr = 1.0 + ppR[c] * fc[it][10][c];
                     double* af = a.accf + ((size_t)e[c] * 4 + s) * R::ASIDE + iq;
                     pr_red(af, quu); pr_red(af + Q, quv); pr_red(af + 2 * Q, qvu); pr_red(af + 3 * Q, qvv);
@@ -687,7 +767,19 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
             V::st(ff, f0); V::st(ff + Q, f1); V::st(ff + 2 * Q, f2);
         }
     }
+    if (BULK) pr_fence_async_smem();
     pr_sync<NT>();
+    if (BULK && lane < 4) {   // one bulk reduction per owned side
+        const int nb = reinterpret_cast<const int*>(hdr + 18)[lane];
+        if ((nb < 0) || (e[0] < nb)) {
+            const int s = lane;
+            const double* sg = s < FS_X ? pr_align16(reinterpret_cast<double*>(X) + R::X_FF + 12 * Q) + s * R::ASIDE
+                               : s < FS_X + FS_T ? pr_align16(reinterpret_cast<double*>(T) + 32 * Q) + (s - FS_X) * R::ASIDE
+                                                 : pr_align16(reinterpret_cast<double*>(Lr + 4 * NP)) + (s - FS_X - FS_T) * R::ASIDE;
+            pr_bulk_add(a.accf + ((size_t)e[0] * 4 + lane) * R::ASIDE, sg, R::ASIDE * 8);
+            pr_bulk_commit();
+        }
+    }
     PR_STAMP(8);
     // ---- 7d. project the face fluxes onto the face nodes: one (side, field) line per lane -> T[0 .. 12G)
     if (lane < 12) {
@@ -773,7 +865,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
         pr_sync<NT>();
         PR_STAMP(11);
     }
-    if (lane < 4 * G) {
+    if (face_lane) {
         const int s = fs, n = fn, I = pr_face_node<G>(s, n);
         double t0[NE], t1[NE], t2[NE], dku[NE], dkv[NE], deu[NE], dev[NE];
         V::ld(nod + 0 * NP + I, t0); V::ld(nod + 1 * NP + I, t1); V::ld(nod + 2 * NP + I, t2);
@@ -791,6 +883,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(NE == 2 ? (W == 4 ? 224 : 
             }
         }
     }
+    if (BULK && lane < 4) pr_bulk_wait_read();   // the staged face sums must have been read before the shared memory is released
     PR_STAMP(15);
 }
 
@@ -995,7 +1088,7 @@ inline int launch_stage_pair(Solver& S, const PairArgs& a) {
     if (S.ngl == 5 && S.nq == 9) return launch_pair_t<5, 9>(S, a);
     if (S.ngl == 4 && S.nq == 7) return launch_pair_t<4, 7>(S, a);
     // nop 8: one element per block of 128 threads (81 nodes, 119 pass-2 lines, 68 face points fit; 289 quadrature points in 3 sweeps)
-    if (S.ngl == 9 && S.nq == 17) return launch_pair_w<9, 17, 1, 4, true>(S, a);
+    if (S.ngl == 9 && S.nq == 17) return launch_pair_w<9, 17, 1, 4, true>(S, a);   // (96 threads per element measured slower: 0.41 vs 0.47)
     return -1;
 }
 

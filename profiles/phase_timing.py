@@ -8,7 +8,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hnumo_loader import hnumo_b200 as hn
 
 nel = int(sys.argv[1]) if len(sys.argv) > 1 else 250
-p = hn.decks.synthetic_double_gyre(nel, nel, nop=4, nlayers=3, dt=12.0 * 1000.0 / nel, dt_btp=0.6 * (1 + 1e-9) * 1000.0 / nel)
+nop = int(os.environ.get("NOP", "4"))   # NOP=8: block-per-element form of the kernel
+if nop == 4:
+    p = hn.decks.synthetic_double_gyre(nel, nel, nop=4, nlayers=3, dt=12.0 * 1000.0 / nel, dt_btp=0.6 * (1 + 1e-9) * 1000.0 / nel)
+else:
+    p = hn.decks.synthetic_double_gyre(nel, nel, nop=nop, nlayers=int(os.environ.get("LAYERS", "3")))
 deck = hn.decks.build_deck(p)
 S = hn.Solver(deck, variant=0)
 for kv in sys.argv[2:]:
