@@ -61,7 +61,7 @@ class Desc(C.Structure):
 
 EXPORTS = ["hnumo_init", "hnumo_finalize", "hnumo_last_error", "hnumo_upload_state", "hnumo_download_state",
            "hnumo_step", "hnumo_ti_rk_bcl", "hnumo_btp_bcl_coeffs", "hnumo_btp_substeps", "hnumo_rhs_btp",
-           "hnumo_get_array", "hnumo_comm_get_unique_id", "hnumo_comm_init", "hnumo_timing", "hnumo_set_option"]
+           "hnumo_get_array", "hnumo_diagnostics", "hnumo_comm_get_unique_id", "hnumo_comm_init", "hnumo_timing", "hnumo_set_option"]
 
 
 def load_library():
@@ -82,6 +82,8 @@ def load_library():
         L.hnumo_rhs_btp.argtypes = [C.c_void_p, C.c_void_p]
         L.hnumo_get_array.restype = C.c_int64
         L.hnumo_get_array.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
+        L.hnumo_diagnostics.restype = C.c_int64
+        L.hnumo_diagnostics.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.hnumo_comm_get_unique_id.argtypes = [C.c_void_p]
         L.hnumo_comm_init.argtypes = [C.c_void_p, C.c_void_p]
         L.hnumo_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
@@ -199,6 +201,23 @@ class Solver:
         self.L.hnumo_timing(self.h, out, 1 if reset else 0)
         return dict(ms_btp=out[0], stages=int(out[1]), ms_step=out[2], steps=int(out[3]), launches=int(out[4]),
                     ms_btp_last=out[5], ms_step_last=out[6])
+
+    def diagnostics(self):
+        """Device-side diagnostics of the resident state (hnumo_diagnostics): dict of per-layer mass and (max, min) of
+        h, u, v, dp, elevation; (max, min) of qb; cfl_b, cfl, min_dx, min_dy."""
+        nl = self.deck["nlayers"]
+        out = np.zeros(11 * nl + 12)
+        n = self.L.hnumo_diagnostics(self.h, out.ctypes.data_as(C.c_void_p), C.c_int64(out.size))
+        if n < 0:
+            raise HnumoError("diagnostics failed (%d): %s" % (n, self.L.hnumo_last_error().decode()))
+        per = out[:11 * nl].reshape(nl, 11)
+        d = dict(mass=per[:, 0].copy())
+        for i, f in enumerate(("h", "u", "v", "dp", "ssh")):
+            d[f] = np.stack([per[:, 1 + i], per[:, 6 + i]], axis=1)   # [layer] -> (max, min)
+        t = out[11 * nl:]
+        d["qb"] = np.stack([t[0:4], t[4:8]], axis=1)
+        d.update(cfl_b=float(t[8]), cfl=float(t[9]), min_dx=float(t[10]), min_dy=float(t[11]))
+        return d
 
     def set_option(self, key, value):
         return self._check(self.L.hnumo_set_option(self.h, key.encode(), float(value)), "set_option")

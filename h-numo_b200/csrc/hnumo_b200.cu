@@ -10,6 +10,7 @@
 #include "stage_tma.cuh"
 #include "stage_rec.cuh"
 #include "stage_pair.cuh"
+#include "diag.cuh"
 
 namespace hn {
 
@@ -152,6 +153,28 @@ __global__ void k_pb_to_aos(double* aos, const double* pbpert, const double* pbp
 }
 
 static size_t nblk(size_t n, int t = 256) { return (n + t - 1) / t; }
+
+// Legendre-Gauss-Lobatto nodes: roots of (1 - x^2) P'_N(x), Newton iteration from the Chebyshev-Gauss-Lobatto points
+// (same points as mod_legendre.F90:54-111 computes; used only for the sub-cell sizes of the Courant number)
+static void lgl_nodes(int ngl, double* x) {
+    const int N = ngl - 1;
+    const double pi = 3.14159265358979323846;
+    for (int i = 0; i <= N; ++i) {
+        double xi = -cos(pi * i / N);
+        if (i == 0) xi = -1.0; else if (i == N) xi = 1.0;
+        else
+            for (int it = 0; it < 100; ++it) {
+                double p0 = 1.0, p1 = xi;   // Legendre recurrence up to P_N
+                for (int k = 2; k <= N; ++k) { double p2 = ((2.0 * k - 1.0) * xi * p1 - (k - 1.0) * p0) / k; p0 = p1; p1 = p2; }
+                // q(x) = (1 - x^2) P_N'(x) = N (P_{N-1} - x P_N);  q'(x) = -N (N + 1) P_N
+                double q = N * (p0 - xi * p1), dq = -(double)N * (N + 1.0) * p1;
+                double dx = q / dq;
+                xi -= dx;
+                if (fabs(dx) < 1e-16) break;
+            }
+        x[i] = xi;
+    }
+}
 
 static void harvest_events(Solver& S);
 static void take_event_pair(Solver& S, int kind, cudaEvent_t& a, cudaEvent_t& b) {
@@ -690,6 +713,7 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     for (int i = 0; i < S.ngl * S.ngl; ++i) S.ops.D[i] = d->dpsi[i];
     for (int i = 0; i < S.nq; ++i) S.ops.wq[i] = d->wnq[i];
     for (int i = 0; i < S.ngl; ++i) S.ops.wg[i] = d->wgl[i];
+    lgl_nodes(S.ngl, S.ops.xg);
     for (int n = 0; n < S.ngl; ++n)
         for (int i = 0; i < S.nq; ++i) { S.ops.AT[i + S.nq * n] = S.ops.A[n + S.ngl * i]; S.ops.BT[i + S.nq * n] = S.ops.B[n + S.ngl * i]; }
     for (int n = 0; n < S.ngl; ++n)
@@ -857,6 +881,8 @@ int hnumo_finalize(hnumo_handle_t h) {
     halo_comm_destroy(S);
     for (void* p : S.allocs) cudaFree(p);
     if (S.d_nbx) cudaFree(S.d_nbx);
+    if (S.d_diag_partial) cudaFree(S.d_diag_partial);
+    if (S.d_diag_res) cudaFree(S.d_diag_res);
     cudaFree(S.d_nbr); cudaFree(S.d_nbslot); cudaFree(S.d_flag); if (S.d_halo_slot) cudaFree(S.d_halo_slot); if (S.d_belems) cudaFree(S.d_belems);
     cudaEventDestroy(S.ev0); cudaEventDestroy(S.ev1); cudaEventDestroy(S.ev2); cudaEventDestroy(S.ev3);
     cudaStreamDestroy(S.stream); cudaStreamDestroy(S.comm_stream);
@@ -1041,6 +1067,39 @@ int64_t hnumo_get_array(hnumo_handle_t h, const char* name, double* out, int64_t
 #endif
     set_error("hnumo_get_array", "unknown array name");
     return -5;
+}
+
+// device-side diagnostics (diag.cuh): per layer mass, max/min of h u v dp elevation; max/min of qb; Courant numbers
+int64_t hnumo_diagnostics(hnumo_handle_t h, double* out, int64_t capacity) {
+    if (!h || !out) return -2;
+    Solver& S = h->S;
+    const int nvals = S.nl * DIAG_PER_LAYER + 14, nout = S.nl * DIAG_PER_LAYER + DIAG_TAIL;
+    if (capacity < nout) { set_error("hnumo_diagnostics", "output buffer too small (need 11*nlayers + 12 doubles)"); return -4; }
+    if (!S.d_diag_partial) {
+        HN_CUDA(cudaMalloc(&S.d_diag_partial, (size_t)nvals * S.nelem * sizeof(double)));
+        HN_CUDA(cudaMalloc(&S.d_diag_res, (size_t)nvals * sizeof(double)));
+    }
+    DiagArgs a; memset(&a, 0, sizeof(a));
+    a.M = S.mesh; a.q = S.q.p; a.nstride = S.q.stride;
+    for (int v = 0; v < 3; ++v) a.qb[v] = S.qb[v];
+    a.pbprime_df = S.pbprime_df; a.zbot_df = S.zbot_df; a.massinv = S.massinv;
+    for (int k = 0; k < S.nl; ++k) a.alpha_over_g[k] = S.alpha[k] / S.g;
+    a.dt = S.dt; a.dt_btp = S.dt_btp; a.partial = S.d_diag_partial; a.nvals = nvals;
+    const size_t sm = (size_t)(2 * S.nl + 2) * S.npts * sizeof(double);
+    smem_opt_in(k_diag_partial, sm);
+    k_diag_partial<<<S.nelem, threads_for(S), sm, S.stream>>>(a);
+    k_diag_final<<<nvals, 256, 0, S.stream>>>(S.d_diag_partial, S.nelem, S.nl, S.d_diag_res);
+    S.n_launches += 2;
+    std::vector<double> res(nvals);
+    HN_CUDA(cudaMemcpyAsync(res.data(), S.d_diag_res, nvals * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+    HN_CUDA(cudaStreamSynchronize(S.stream));
+    const int nm = S.nl * DIAG_PER_LAYER + 8;
+    for (int j = 0; j < nm; ++j) out[j] = res[j];
+    const double cbx = res[nm], cby = res[nm + 1], mdx = res[nm + 2], mdy = res[nm + 3], cx = res[nm + 4], cy = res[nm + 5];
+    out[nm + 0] = std::max(cbx * S.dt_btp / mdx, cby * S.dt_btp / mdy);   // CFL_B (courant.F90:98-99, as written: with p_b*ubar)
+    out[nm + 1] = std::max(cx * S.dt / mdx, cy * S.dt / mdy);            // CFL   (courant.F90:116-117)
+    out[nm + 2] = mdx; out[nm + 3] = mdy;
+    return nout;
 }
 
 int hnumo_comm_get_unique_id(void* id128) { return halo_get_unique_id(id128); }

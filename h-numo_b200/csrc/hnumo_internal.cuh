@@ -44,6 +44,7 @@ struct alignas(16) Ops {
     double D[HN_MAXNGL * HN_MAXNGL];  // dpsi(k,n) = l_k'(x_n) -> D[k + ngl*n]
     double wq[HN_MAXNQ];
     double wg[HN_MAXNGL];
+    double xg[HN_MAXNGL];             // LGL nodes (recomputed from ngl: the descriptor carries weights and matrices only)
     // transposed copies (output index fastest) for the line contractions of stage_pair.cuh: consecutive entries feed
     // independent accumulators, and one 128-bit uniform load brings two of them
     alignas(16) double AT[HN_MAXNGL * HN_MAXNQ];   // AT[i + nq*n] = A[n + ngl*i]
@@ -141,6 +142,7 @@ struct Solver {
     // (high priority) followed by pack + send/recv, every other element advances on `stream` at the same time
     int* d_belems = nullptr;
     int n_belem = 0, overlap = 1;
+    double *d_diag_partial = nullptr, *d_diag_res = nullptr;   // device-side diagnostics (diag.cuh), allocated on first use
     int num_sms = 148, tma_blocks_per_sm = 0;
     int use_graph = 0;
     int pf_blocks = -1;   // L2 prefetch distance of the fused stage kernel, in thread blocks

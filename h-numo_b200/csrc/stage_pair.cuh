@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
     constexpr int J2B = BLK ? 4 * G : 0, J2C = BLK ? 64 : 0;   // phase 2: bottom-layer rows, LDG gradient lines
     constexpr int J5A = BLK ? 64 : 0;                           // phase 5: the B.Fe + A.S contraction
     constexpr int J6B = BLK ? 32 : 0, J6C = BLK ? 32 + 4 * G : 0;   // phase 6: LDG laplacian lines, face traces
+    // (splitting scatter pass 2 into its B.TB and A.TA halves on two warps was measured neutral: 1.435 vs 1.422 ms)
     static_assert(!BLK || (J2B + 3 * G <= J2C && J2C + 4 * G <= NT && J5A + 3 * Q <= NT && 3 * Q <= J5A && 3 * G <= J6B && J6C + 4 * G <= NT),
                   "job lane ranges");
     static_assert(!BULK || (6 * NQ2 + 2 <= R::T_SZ + 4 * NP && 6 * NP + 2 <= 8 * NP), "staging of the quadrature / nodal sums");
@@ -795,6 +796,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
         const int I = lane, m = I / G, n = I - m * G;
         double r0[NE], r1[NE], r2[NE], l0[NE], l1[NE];
         V::ld(X + R::X_RHS + 0 * NP + I, r0); V::ld(X + R::X_RHS + 1 * NP + I, r1); V::ld(X + R::X_RHS + 2 * NP + I, r2);
+
         if (VISC) {
             double t0[NE], t1[NE], t2[NE], t3[NE];
             V::ld(Lr + 0 * NP + I, t0); V::ld(Lr + 1 * NP + I, t1); V::ld(Lr + 2 * NP + I, t2); V::ld(Lr + 3 * NP + I, t3);

@@ -73,6 +73,14 @@ module hnumo_b200_iface
             type(c_ptr), value :: handle
             character(kind=c_char), intent(in) :: id128(128)
         end function
+        ! device-side diagnostics: replaces diagnostics / compute_conserved / the max-min and Courant part of
+        ! print_diagnostics_mlswe for the resident state (out: 11*nlayers + 12 values, see include/hnumo_b200.h)
+        integer(c_int64_t) function hnumo_diagnostics(handle, out, capacity) bind(C, name="hnumo_diagnostics")
+            import :: c_int64_t, c_ptr, c_double
+            type(c_ptr), value :: handle
+            real(c_double), intent(out) :: out(*)
+            integer(c_int64_t), value :: capacity
+        end function
         integer(c_int) function hnumo_timing(handle, out8, reset) bind(C, name="hnumo_timing")
             import :: c_int, c_ptr, c_double, c_int32_t
             type(c_ptr), value :: handle

@@ -131,6 +131,17 @@ int64_t hnumo_get_array(hnumo_handle_t h, const char* name, double* out, int64_t
 int hnumo_comm_get_unique_id(void* id128);
 int hnumo_comm_init(hnumo_handle_t h, const void* id128);
 
+/* ---- device-side diagnostics ------------------------------------------------
+ * Replaces, for the resident state, what the reference computes on the host at every output step:
+ *   diagnostics (src/diagnostics.F90:24-45: h = alpha_k/g dp, u, v, dp, interface elevation),
+ *   compute_conserved (src/compute_conserved.F90:29-41: layer mass = sum wjac_df h),
+ *   print_diagnostics_mlswe (src/print_diagnostics.F90:59-128: max/min per layer and of qb(1:4,:)),
+ *   courant_cube_mlswe (src/courant.F90:34-126: CFL_B as written with qb(3:4,:) = p_b*(ubar,vbar), CFL with the layer velocities).
+ * out[k*11 + 0] = mass of layer k, [k*11 + 1..5] = max of h,u,v,dp,elevation, [k*11 + 6..10] = min of the same;
+ * then qb max (4), qb min (4), CFL_B, CFL, min dx, min dy.  Values are those of this rank's elements: reduce over ranks like the
+ * reference's mpi_reduce (sum for the mass, max, min).  Returns 11*nlayers + 12 or <0. */
+int64_t hnumo_diagnostics(hnumo_handle_t h, double* out, int64_t capacity);
+
 /* ---- measurement ------------------------------------------------------------------------------ */
 /* out[0] = GPU ms spent in barotropic stages since the last reset (CUDA events on the compute stream),
  * out[1] = number of barotropic stages, out[2] = GPU ms in whole steps, out[3] = steps,

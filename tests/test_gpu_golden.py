@@ -71,3 +71,46 @@ def test_negative_thickness_is_reported():
     assert S.step(1) == 1
     assert "Negative mass" in hn.load_library().hnumo_last_error().decode()
     S.close()
+
+
+def _host_courant(deck, q, qb):
+    """numpy restatement of courant_cube_mlswe (courant.F90:34-126), with the minimum cell size taken over all cells first"""
+    ngl, npts, nl = deck["ngl"], deck["npts"], deck["nlayers"]
+    ne = deck["nelem"]
+    xy = deck["coord"][:, :2].reshape(ne, ngl, ngl, 2)
+    corners = lambda a: np.stack([a[:, :-1, :-1], a[:, :-1, 1:], a[:, 1:, :-1], a[:, 1:, 1:]], axis=-1)
+    cx, cy = corners(xy[..., 0]), corners(xy[..., 1])
+    dx = (cx.max(-1) - cx.min(-1)).min(); dy = (cy.max(-1) - cy.min(-1)).min()
+    mean4 = lambda f: np.abs(corners(f.reshape(ne, ngl, ngl)).sum(-1) / 4.0).max()
+    cfl_b = max(mean4(qb[:, 2]) * deck["dt_btp"] / dx, mean4(qb[:, 3]) * deck["dt_btp"] / dy)
+    cfl = 0.0
+    for k in range(nl):
+        cfl = max(cfl, mean4(q[k, :, 1] / q[k, :, 0]) * deck["dt"] / dx, mean4(q[k, :, 2] / q[k, :, 0]) * deck["dt"] / dy)
+    return cfl_b, cfl, dx, dy
+
+
+@pytest.mark.parametrize("name,over", [("double_gyre", dict(nelx=7, nely=6)), ("bump", {}), ("synth_nop8", {})])
+def test_device_diagnostics_match_host_restatement(name, over):
+    """hnumo_diagnostics (on the device) == diagnostics.F90 / compute_conserved.F90 / print_diagnostics.F90
+    / courant.F90 restated in numpy on the downloaded state"""
+    params = hn.decks.synthetic_double_gyre(4, 3, nop=8, nlayers=5) if name == "synth_nop8" else dict(hn.decks.SHIPPED[name], **over)
+    deck = hn.decks.build_deck(params)
+    S = hn.Solver(deck)
+    S.upload_state(deck["q_df"], deck["qb_df"], deck["qprime_df"])
+    assert S.step(3) == 0
+    d = S.diagnostics()
+    q, qb, qp = S.download_state()
+    S.close()
+    ref = hn.decks.diagnostics(deck, q)
+    nl = deck["nlayers"]
+    assert np.allclose(d["mass"], ref["mass"], rtol=1e-13, atol=0.0)
+    qq = np.asarray(q).reshape(nl, -1, 3)
+    fields = dict(h=ref["h"], u=ref["u"], v=ref["v"], dp=qq[:, :, 0], ssh=ref["ssh"])
+    for f, a in fields.items():
+        # the device divides and sums in the same order as the host: agreement to the last bits
+        assert np.allclose(d[f][:, 0], a.max(axis=1), rtol=1e-14, atol=1e-300), f
+        assert np.allclose(d[f][:, 1], a.min(axis=1), rtol=1e-14, atol=1e-300), f
+    assert np.array_equal(d["qb"][:, 0], qb.max(axis=0)) and np.array_equal(d["qb"][:, 1], qb.min(axis=0))
+    cfl_b, cfl, dx, dy = _host_courant(deck, qq, qb)
+    assert abs(d["min_dx"] - dx) < 1e-9 * dx and abs(d["min_dy"] - dy) < 1e-9 * dy
+    assert abs(d["cfl_b"] - cfl_b) <= 1e-9 * cfl_b and abs(d["cfl"] - cfl) <= 1e-9 * cfl + 1e-300
