@@ -114,3 +114,33 @@ def test_device_diagnostics_match_host_restatement(name, over):
     cfl_b, cfl, dx, dy = _host_courant(deck, qq, qb)
     assert abs(d["min_dx"] - dx) < 1e-9 * dx and abs(d["min_dy"] - dy) < 1e-9 * dy
     assert abs(d["cfl_b"] - cfl_b) <= 1e-9 * cfl_b and abs(d["cfl"] - cfl) <= 1e-9 * cfl + 1e-300
+
+
+@pytest.mark.parametrize("cfg", ["config4_1000x1000_nop4_3layers", "config5_500x500_nop8_10layers"])
+def test_full_size_invariants(cfg):
+    """BASELINE configs 4 and 5 at their full sizes (too large for the CPU oracle): size-independent properties --
+    layer mass conserved to round-off (check.F90:58), no negative thickness flag, finite fields, Courant numbers in the
+    stable range, and the barotropic/baroclinic consistency pb = pbprime + sum_k dp_k to round-off.  Everything is reduced
+    on the device (hnumo_diagnostics); only one plane is downloaded for the consistency check."""
+    if cfg.startswith("config4"):
+        p = hn.decks.synthetic_double_gyre(1000, 1000, nop=4, nlayers=3, dt=12.0, dt_btp=0.6 * (1 + 1e-9))
+        nsteps = 2
+    else:
+        p = hn.decks.synthetic_double_gyre(500, 500, nop=8, nlayers=10, dt=35.0, dt_btp=0.35 * (1 + 1e-9))
+        nsteps = 1
+    deck = hn.decks.build_deck(p)
+    S = hn.Solver(deck)
+    S.upload_state(deck["q_df"], deck["qb_df"], deck["qprime_df"])
+    d0 = S.diagnostics()
+    assert S.step(nsteps) == 0
+    d1 = S.diagnostics()
+    nl = deck["nlayers"]
+    for k in range(nl):
+        assert abs(d1["mass"][k] - d0["mass"][k]) <= 1e-12 * abs(d0["mass"][k]), (k, d0["mass"][k], d1["mass"][k])
+        assert d1["dp"][k, 1] > 0.0 and np.isfinite(d1["u"][k]).all() and np.isfinite(d1["v"][k]).all()
+    assert 0.0 <= d1["cfl"] < 1.0 and np.isfinite(d1["cfl_b"])
+    assert np.abs(d1["u"]).max() > 0.0          # the wind and the thickness perturbation have set the layers in motion
+    q, qb, qp = S.download_state()
+    S.close()
+    col = q[:, :, 0].sum(axis=0)                # sum_k dp_k
+    assert np.abs(col - qb[:, 0]).max() <= 1e-12 * np.abs(qb[:, 0]).max()
