@@ -140,6 +140,16 @@ def cpu_oracle_rate(args, nsteps=1, warmup=0):
                 sample="%dx%d elements, nop=%d, %d layers, %d baroclinic step(s) = %d barotropic stages" % (n, n, args.nop, args.layers, nsteps, stages))
 
 
+def reference_build_probe():
+    """the preferred CPU baseline is the Fortran reference itself (`make hnumo`, mpirun -np C ./numo3d); it needs
+    an MPI Fortran compiler, p4est and NetCDF-Fortran on the box.  Say explicitly what is missing."""
+    import shutil
+    missing = [t for t in ("mpif90", "gfortran", "mpirun", "nf-config") if shutil.which(t) is None]
+    if missing:
+        return "reference build unavailable on this box: no " + ", ".join(missing) + " (p4est 2.8 is not vendored either)"
+    return "toolchain present; the reference still needs its un-vendored p4est 2.8 download (no network)"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -152,7 +162,8 @@ def run_reference(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "synthetic double gyre %dx%d elements nop=%d %d layers (BASELINE config 4)" % (args.nelx, args.nely, args.nop, args.layers),
                    "note": "reference arm = CPU port of the reference algorithm (C++ oracle, OpenMP); the Fortran/MPI build cannot be "
-                           "compiled here (no gfortran/MPI/p4est/NetCDF); each step is a bounded sample: " + r["sample"]},
+                           "compiled here (no gfortran/MPI/p4est/NetCDF); each step is a bounded sample: " + r["sample"],
+                   "reference_build": reference_build_probe()},
         "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

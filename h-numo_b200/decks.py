@@ -155,8 +155,41 @@ def synthetic_double_gyre(nelx, nely, nop=4, nlayers=3, dt=None, dt_btp=None, pe
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def element_owner(p, nranks):
+    """Owning rank of every element of the nelx x nely brick (global row-major numbering).
+
+    p["partition"]: "rows" (default: nranks row blocks), "blocks:PXxPY" (2-D blocks: ranks with up to 4 neighbours),
+    "morton" (contiguous chunks of the Morton / z-order curve, the shape of a uniform-weight p4est partition,
+    p4est.c:1178)."""
+    nelx, nely = p["nelx"], p["nely"]
+    kind = p.get("partition", "rows")
+    g = np.arange(nelx * nely)
+    ex, ey = g % nelx, g // nelx
+    if nranks == 1:
+        return np.zeros(nelx * nely, dtype=np.int64)
+    if kind == "rows":
+        if nely % nranks != 0:
+            raise ValueError("row-block partition needs nely divisible by the number of ranks")
+        return ey // (nely // nranks)
+    if kind.startswith("blocks:"):
+        px, py = (int(t) for t in kind.split(":")[1].split("x"))
+        if px * py != nranks or nelx % px or nely % py:
+            raise ValueError("blocks partition: PX*PY must equal the number of ranks and divide the brick")
+        return (ey // (nely // py)) * px + ex // (nelx // px)
+    if kind == "morton":
+        code = np.zeros(nelx * nely, dtype=np.int64)
+        for b in range(16):
+            code |= ((ex >> b) & 1) << (2 * b)
+            code |= ((ey >> b) & 1) << (2 * b + 1)
+        order = np.argsort(code, kind="stable")
+        owner = np.empty(nelx * nely, dtype=np.int64)
+        owner[order] = (np.arange(nelx * nely) * nranks) // (nelx * nely)
+        return owner
+    raise ValueError("unknown partition " + kind)
+
+
 def build_deck(params, rank=0, nranks=1):
-    """Arrays for one rank of a row-block partition of the nelx x nely brick.
+    """Arrays for one rank of a partition of the nelx x nely brick (element_owner: row blocks, 2-D blocks, Morton chunks).
 
     Returns a dict whose keys match hnumo_desc_t members, plus 'q_df', 'qb_df', 'qprime_df' (initial state in the
     reference AoS layout), 'coord', 'elem_global' (global row-major element number of each local element).
@@ -169,14 +202,16 @@ def build_deck(params, rank=0, nranks=1):
     xg = B["xgl"]
     Lx = p["xdims"][1] - p["xdims"][0]
     Ly = p["ydims"][1] - p["ydims"][0]
-    if nely % nranks != 0:
-        raise ValueError("row-block partition needs nely divisible by the number of ranks")
-    rows = nely // nranks
-    ey0 = rank * rows
-    nelem = nelx * rows
+    owner = element_owner(p, nranks)                 # owning rank of every global (row-major) element
+    gl = np.nonzero(owner == rank)[0]                # local elements keep the global order: left element = lower number
+    nelem = gl.size
+    if nelem == 0:
+        raise ValueError("partition leaves rank %d without elements" % rank)
     npoin = nelem * npts
-    ex = np.tile(np.arange(nelx), rows)
-    ey = np.repeat(np.arange(ey0, ey0 + rows), nelx)
+    ex = gl % nelx
+    ey = gl // nelx
+    g2l = np.full(nelx * nely, -1, dtype=np.int64)
+    g2l[gl] = np.arange(nelem)
     # coordinates (p4est.c:204-236): bilinear blend of the tree corners, then rescaled to xdims/ydims
     rl = xg[None, :]
     rm = xg[:, None]
@@ -192,39 +227,41 @@ def build_deck(params, rank=0, nranks=1):
     # face table (p4est.c:1590-1704): p4est faces f=0..3 (-x,+x,-y,+y) -> numa local faces 5,6,3,4
     transform = np.array([5, 6, 3, 4], dtype=np.int32)
     qq = np.arange(nelem)
-    qx, qy = qq % nelx, qq // nelx
     cols = []
     for f in range(4):
-        nx_ = qx + (-1 if f == 0 else 1 if f == 1 else 0)
-        ny_ = qy + (-1 if f == 2 else 1 if f == 3 else 0)
-        gy = ny_ + ey0
-        wall = (nx_ < 0) | (nx_ >= nelx) | (gy < 0) | (gy >= nely)
-        proc = ~wall & ((ny_ < 0) | (ny_ >= rows))
+        nx_ = ex + (-1 if f == 0 else 1 if f == 1 else 0)
+        ny_ = ey + (-1 if f == 2 else 1 if f == 3 else 0)
+        wall = (nx_ < 0) | (nx_ >= nelx) | (ny_ < 0) | (ny_ >= nely)
+        ng = np.where(wall, 0, nx_ + nelx * ny_)     # global number of the neighbour
+        nrank = np.where(wall, rank, owner[ng])
+        proc = ~wall & (nrank != rank)
         inter = ~wall & ~proc
-        nq_ = nx_ + nelx * ny_
+        nq_ = np.where(inter, g2l[ng], -1)
         bc = (p["x_boundary"][0] if f == 0 else p["x_boundary"][1] if f == 1 else
               p["y_boundary"][0] if f == 2 else p["y_boundary"][1])
         er = np.where(wall, -bc, np.where(proc, 0, nq_ + 1)).astype(np.int32)
         ilocr = np.where(inter, transform[f ^ 1], 0).astype(np.int32)
         keep = wall | proc | (inter & (qq < nq_))
-        side = np.where(proc & (ny_ < 0), 1, np.where(proc & (ny_ >= rows), 2, 0))
-        cols.append((np.full(nelem, transform[f], dtype=np.int32), ilocr, (qq + 1).astype(np.int32), er, keep, side))
+        cols.append((np.full(nelem, transform[f], dtype=np.int32), ilocr, (qq + 1).astype(np.int32), er, keep,
+                     np.where(proc, nrank, -1), np.minimum(gl, ng), np.maximum(gl, ng)))
     ilocl = np.stack([c[0] for c in cols], axis=1).ravel()
     ilocr = np.stack([c[1] for c in cols], axis=1).ravel()
     el = np.stack([c[2] for c in cols], axis=1).ravel()
     er = np.stack([c[3] for c in cols], axis=1).ravel()
     keep = np.stack([c[4] for c in cols], axis=1).ravel()
-    side = np.stack([c[5] for c in cols], axis=1).ravel()[keep]
+    prank = np.stack([c[5] for c in cols], axis=1).ravel()[keep]
+    glo = np.stack([c[6] for c in cols], axis=1).ravel()[keep]
+    ghi = np.stack([c[7] for c in cols], axis=1).ravel()[keep]
     nface = int(keep.sum())
     face = np.zeros((nface, 8), dtype=np.int32)
     face[:, 4] = ilocl[keep]; face[:, 5] = ilocr[keep]; face[:, 6] = el[keep]; face[:, 7] = er[keep]
-    halo_lo = (np.nonzero(side == 1)[0] + 1).tolist()  # 1-based face numbers, ordered by ex
-    halo_hi = (np.nonzero(side == 2)[0] + 1).tolist()
+    # neighbour lists (p4est.c:1340-1420, mod_parallel.F90:141-171): per neighbour rank, the shared faces in an order both
+    # sides agree on -- here by the pair of global element numbers of the face
     nbh_proc, num_send_recv, nbh_send_recv = [], [], []
-    if halo_lo:
-        nbh_proc.append(rank); num_send_recv.append(len(halo_lo)); nbh_send_recv += halo_lo      # rank-1, 1-based = rank
-    if halo_hi:
-        nbh_proc.append(rank + 2); num_send_recv.append(len(halo_hi)); nbh_send_recv += halo_hi  # rank+1, 1-based
+    for r in sorted(set(prank[prank >= 0].tolist())):
+        fi = np.nonzero(prank == r)[0]
+        fi = fi[np.lexsort((ghi[fi], glo[fi]))]
+        nbh_proc.append(r + 1); num_send_recv.append(len(fi)); nbh_send_recv += (fi + 1).tolist()   # 1-based
     # geometry: axis-aligned rectangles
     dx, dy = Lx / nelx, Ly / nely
     em = np.zeros((nelem, 5))
@@ -343,7 +380,7 @@ def build_deck(params, rank=0, nranks=1):
         rank=rank, nranks=nranks, nbh_proc=np.array(nbh_proc, dtype=np.int32),
         num_send_recv=np.array(num_send_recv, dtype=np.int32), nbh_send_recv=np.array(nbh_send_recv, dtype=np.int32),
         q_df=q, qb_df=qb, qprime_df=qprime, coord=np.stack([x, y], axis=1),
-        elem_global=(ex + nelx * ey), npoin=npoin, npts=npts,
+        elem_global=gl.copy(), npoin=npoin, npts=npts,
     )
     return deck
 

@@ -237,6 +237,36 @@ def test_partitioned_equals_single(nranks, visc, variant):
             assert np.linalg.norm(q[:, :, v] - q1[:, idx, v]) / (c * np.linalg.norm(q1[:, idx, 0])) < tol
 
 
+@pytest.mark.parametrize("visc", [0.0, 50.0])
+@pytest.mark.parametrize("partition,nranks", [("blocks:2x2", 4), ("morton", 4), ("morton", 3), ("blocks:3x2", 6)])
+def test_general_partitions_equal_single(partition, nranks, visc):
+    """Partitions the way p4est produces them: 2-D blocks and chunks of the Morton curve -- ranks with up to
+    four neighbours, non-contiguous boundary elements, several messages per exchange -- give the 1-rank result
+    (to round-off without viscosity; see test_partitioned_equals_single for the O(visc) partition dependence of the
+    reference's as-written LDG face flux)."""
+    params = dict(hn.decks.SHIPPED["double_gyre"], nelx=6, nely=8, visc_mlswe=visc, partition=partition)
+    tol = 1e-13 if visc == 0.0 else 1e-10
+    single = hn.decks.build_deck(params)
+    S = hn.Solver(single)
+    S.upload_state(single["q_df"], single["qb_df"], single["qprime_df"])
+    assert S.step(3) == 0
+    q1, qb1, qp1 = S.download_state()
+    S.close()
+    gid = 500 + 10 * nranks + (1 if visc else 0) + (5 if partition == "morton" else 0)
+    decks, outs = _run_partitioned(params, nranks, 3, gid=gid)
+    npts = single["npts"]
+    c = np.sqrt(single["gravity"] * 9928.0)
+    assert sorted(np.concatenate([d["elem_global"] for d in decks]).tolist()) == list(range(48))
+    for d, (q, qb, qp) in zip(decks, outs):
+        idx = (d["elem_global"][:, None] * npts + np.arange(npts)[None, :]).ravel()
+        assert rel_l2(qb[:, 0], qb1[idx, 0]) < tol
+        assert rel_l2(q[:, :, 0], q1[:, idx, 0]) < 10 * tol
+        for v in (2, 3):
+            assert np.linalg.norm(qb[:, v] - qb1[idx, v]) / (c * np.linalg.norm(qb1[idx, 0])) < tol
+        for v in (1, 2):
+            assert np.linalg.norm(q[:, :, v] - q1[:, idx, v]) / (c * np.linalg.norm(q1[:, idx, 0])) < tol
+
+
 @pytest.mark.parametrize("nranks", [2, 4])
 def test_partitioned_high_order(nranks):
     """nop 8 on 2 and 4 partitions (block-per-element stage kernel, overlapped exchange) == 1 partition"""
