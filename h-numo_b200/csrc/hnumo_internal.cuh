@@ -137,7 +137,7 @@ struct Solver {
     void* d_nbx = nullptr;
     // record layout of the element-pair stage kernel (stage_pair.cuh): one record per element, face sums, traces
     double *p_rec = nullptr, *p_accf = nullptr, *p_tr[2] = {nullptr, nullptr};
-    int pair_ne = 1, pair_warps = 4, pair_prefetch = 0, pair_pf_dist = 0, pair_units_per_wave = 0;
+    int pair_ne = 1, pair_warps = 4, pair_prefetch = 6, pair_pf_dist = 0, pair_units_per_wave = 0;
     // halo exchange overlapped with interior work: the elements that own a processor face advance on comm_stream
     // (high priority) followed by pack + send/recv, every other element advances on `stream` at the same time
     int* d_belems = nullptr;

@@ -87,7 +87,8 @@ struct PairArgs {
     double* tr_out;
     double a1, a2, a3, dtt, g, cd_g, cd_alpha, visc;   // cd_g = cd/g (botfr 1), cd_alpha = cd/alpha_bottom (botfr 2)
     int botfr, load_q0, load_q2, store_q0, store_q2;
-    int prefetch, pf_dist;   // bit 0: own record tail -> L2 at start; bit 1: head of the record pf_dist units ahead
+    int prefetch, pf_dist;   // L2 prefetch: bit 0: own record tail at start; bits 1,2: head (header, state, nodal statics and sums) and
+                             // quadrature statics of the record pf_dist units ahead (default 6); bits 3-5: experiments, slower
     // element subsets of a launch (halo exchange overlapped with interior work):
     //   part 0: every element; part 1: the `count` elements of `elist` (those with a processor face);
     //   part 2: every element that has no processor face (warps of the others leave once their header has arrived)
@@ -337,6 +338,18 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
             // the head of the record (header, state, nodal statics and sums) of the unit that follows one wave later
             if ((a.prefetch & 2) && a.part != 1 && (long)(unit + a.pf_dist) * NE + lane < a.nelem)
                 pr_prefetch_l2(p + (size_t)a.pf_dist * NE * R::REC, (uint32_t)(R::O_QST * sizeof(double)));
+            // ... its face coefficients and neighbour viscosity statics (bit 3)
+            if ((a.prefetch & 8) && a.part != 1 && (long)(unit + a.pf_dist) * NE + lane < a.nelem)
+                pr_prefetch_l2(p + (size_t)a.pf_dist * NE * R::REC + R::O_FST, (uint32_t)((R::O_Q0 - R::O_FST) * sizeof(double)));
+            // ... its quadrature running sums, the RED targets of phase 4 (bit 4), its four trace records of the previous stage,
+            //     which its neighbours read (bit 5)
+            if ((a.prefetch & 16) && a.part != 1 && (long)(unit + a.pf_dist) * NE + lane < a.nelem)
+                pr_prefetch_l2(p + (size_t)a.pf_dist * NE * R::REC + R::O_ACCQ, (uint32_t)((R::O_FST - R::O_ACCQ) * sizeof(double)));
+            if ((a.prefetch & 32) && a.part != 1 && (long)(unit + a.pf_dist) * NE + lane < a.nelem)
+                pr_prefetch_l2(a.tr_in + ((size_t)(unit + a.pf_dist) * NE + lane) * 4 * R::TSIDE, (uint32_t)(4 * R::TSIDE * sizeof(double)));
+            // ... and its quadrature statics (bit 2)
+            if ((a.prefetch & 4) && a.part != 1 && (long)(unit + a.pf_dist) * NE + lane < a.nelem)
+                pr_prefetch_l2(p + (size_t)a.pf_dist * NE * R::REC + R::O_QST, (uint32_t)((R::O_ACCQ - R::O_QST) * sizeof(double)));
         }
         if (lane < R::HDR) { PR_FORC hdr[c * R::HDR + lane] = hv[c]; }
         if (a.part == 2) {   // interior launch: elements with a processor face belong to the boundary launch
@@ -1059,7 +1072,9 @@ static int launch_pair_k(Solver& S, const PairArgs& a) {
                     (int)BLK, (int)VISC, BOTFR, smem, nb, nb * W);
     }
     PairArgs b = a;
-    if (b.pf_dist <= 0) b.pf_dist = units_per_wave;
+    // L2 prefetch distance in units (warps, or blocks in block-per-element mode): a quarter / half of the resident wave
+    // (measured: 296-1480 units are equivalent at nop 4, 185-370 blocks best at nop 8; profiles/r1_stage_kernel_experiments.md)
+    if (b.pf_dist <= 0) b.pf_dist = BLK ? units_per_wave / 2 : units_per_wave / 4;
     if (b.part != 1) b.count = S.nelem;
     if (b.count <= 0) return 0;
     const int units = (b.count + NE - 1) / NE;
