@@ -403,6 +403,14 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
         ksx[c] = h[0]; ksy[c] = h[1]; etx[c] = h[2]; ety[c] = h[3]; J[c] = h[4];
         flags[c] = reinterpret_cast<const int*>(h + 22)[0];
     }
+    // the rarely-read forcing fields (tau_y, grad z_bot) of the record pf_dist units ahead -> L2 when this element has them
+    // (neighbouring elements are alike): without it every quadrature point pays two dependent DRAM loads in phase 4
+    if ((a.prefetch & 4) && a.part != 1 && lane < NE) {
+        PR_FORC {
+            if (lane == c && (flags[c] & (PF_GZ | PF_TWY)) && (long)(unit + a.pf_dist) * NE + c < a.nelem)
+                pr_prefetch_l2(rec[c] + (size_t)a.pf_dist * NE * R::REC + R::O_QSTR, (uint32_t)(pr_pad2(R::QST_RARE * NQ2) * sizeof(double)));
+        }
+    }
     // neighbour traces and owned face sums -> L2 (the header has just told us where they are): one 128-byte line per lane
     if (a.prefetch & 1) {
         constexpr int TL = (R::TSIDE * 8 + 127) / 128 + 1, AL = (R::ASIDE * 8 + 127) / 128 + 1;
