@@ -411,6 +411,19 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
                 pr_prefetch_l2(rec[c] + (size_t)a.pf_dist * NE * R::REC + R::O_QSTR, (uint32_t)(pr_pad2(R::QST_RARE * NQ2) * sizeof(double)));
         }
     }
+    // face coefficients of the four sides (own record for owned sides, the owner's record otherwise) and the neighbour
+    // viscosity statics -> L2 now that the header says where they are: they are loaded in phase 6 and used in phase 7 (bit 6)
+    if ((a.prefetch & 64) && NE == 1 && lane < 5) {
+        const int* hi = reinterpret_cast<const int*>(hdr + 18);
+        if (lane < 4) {
+            const int nb = hi[lane];
+            const bool left = (nb < 0) || (e[0] < nb);
+            const double* cf = left ? rec[0] + R::O_FST + lane * R::FSIDE : a.rec + (size_t)nb * R::REC + R::O_FST + (hi[4 + lane] - 4 * nb) * R::FSIDE;
+            pr_prefetch_l2(cf, (uint32_t)(R::FSIDE * sizeof(double)));
+        } else {
+            pr_prefetch_l2(rec[0] + R::O_VST, (uint32_t)(4 * R::VSIDE * sizeof(double)));
+        }
+    }
     // neighbour traces and owned face sums -> L2 (the header has just told us where they are): one 128-byte line per lane
     if (a.prefetch & 1) {
         constexpr int TL = (R::TSIDE * 8 + 127) / 128 + 1, AL = (R::ASIDE * 8 + 127) / 128 + 1;
