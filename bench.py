@@ -160,7 +160,7 @@ def run_reference(args):
         "impl": "reference", "metric": "DG DOF-updates/s per RK stage", "value": r["value"], "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["wall"] / max(args.steps, 1), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic double gyre %dx%d elements nop=%d %d layers (BASELINE config 4)" % (args.nelx, args.nely, args.nop, args.layers),
+        "config": {"workload": "synthetic double gyre %dx%d elements nop=%d %d layers (BASELINE config %s)" % (args.nelx, args.nely, args.nop, args.layers, "5" if args.nop == 8 else "4"),
                    "note": "reference arm = CPU port of the reference algorithm (C++ oracle, OpenMP); the Fortran/MPI build cannot be "
                            "compiled here (no gfortran/MPI/p4est/NetCDF); each step is a bounded sample: " + r["sample"],
                    "reference_build": reference_build_probe()},
@@ -291,7 +291,7 @@ def main():
             "metric": "DG DOF-updates/s per RK stage", "value": value, "unit": "DOF-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic double gyre %dx%d elements nop=%d %d layers (BASELINE config 4)" % (args.nelx, args.nely, args.nop, args.layers),
+            "config": {"workload": "synthetic double gyre %dx%d elements nop=%d %d layers (BASELINE config %s)" % (args.nelx, args.nely, args.nop, args.layers, "5" if args.nop == 8 else "4"),
                        "nelem": params["nelx"] * params["nely"], "npoin": npoin_global, "stages_per_step": stages_per_step,
                        "dt": params["dt"], "dt_btp": deck["dt_btp"], "partition": "row blocks, %d rank(s)" % world,
                        "l2_policy": "inputs larger than L2 (>= 60 GB of resident state per job vs 126 MB L2)",

@@ -3,21 +3,23 @@
 // Same operator as k_btp_stage_simple / k_btp_stage_fused (reference src/mod_rhs_btp.F90:28-370,
 // src/mod_barotropic_terms.F90:25-97,165-217, src/mod_laplacian_quad.F90:32-121,357-519, src/mod_rk_mlswe.F90:87-114).
 //
-// Why this shape (profiles/r1_fused_kernel_summary.md): the warp-per-element kernel issues 4 360 warp instructions per
-// element of which only 27 % are FP64 math; 46 % are integer/address/control work and the issue slots are 43 % busy at
-// 0.41 of the HBM roofline -- the kernel is bound by instruction issue (and by board power), not by DRAM.  Here
-//   * one warp advances NE = 2 elements at once: every shared-memory word is a double2 {element A, element B}
-//     (LDS.128 / STS.128), every lane works on the same line / point of both elements, so loop control, index
-//     arithmetic, the uniform-register loads of the operator entries (LDCU) and the shared-memory traffic are paid
-//     once per pair, and each lane carries two independent dependency chains;
-//   * everything an element needs for a stage lives in ONE contiguous record (state, statics, accumulators, face
-//     coefficients): one base pointer per element, compile-time offsets, no per-plane address arithmetic; the record
-//     is pulled into L2 by a single bulk prefetch instruction (cp.async.bulk.prefetch.L2) when the warp starts;
-//   * only 9 warps are resident per SM (shared memory), so each thread may use 224 registers: the global loads of a
-//     phase are issued one phase ahead and held in registers, which hides the L2 latency behind FP64 work;
+// Shape (history and measurements: profiles/r1_fused_kernel_summary.md, r1_record_kernel_summary.md,
+// r1_stage_kernel_experiments.md):
+//   * everything an element needs for a stage lives in ONE contiguous record (state, statics, running sums, face
+//     coefficients): one base pointer per element, compile-time offsets, no per-plane address arithmetic;
+//   * default at nop 3/4: one warp advances one element (NE = 1), 4 warps per block, 16 warps per SM (13.7 kB of shared
+//     memory per warp, 128 registers); the loads of a phase are issued one phase ahead and held in registers, the statics
+//     of the whole element are requested when the warp starts; every warp prefetches the head and the quadrature statics
+//     of the record a quarter wave ahead into L2 (cp.async.bulk.prefetch.L2);
+//   * NE = 2 (two elements per warp, every shared-memory word a double2) is kept as an option: fewer instructions per
+//     element but half the resident warps -- measured slower;
+//   * nop 8: the same source with BLK = true, one element per block of 128 threads, phases separated by __syncthreads,
+//     independent line jobs of a phase on different warps, 96 registers (5 blocks per SM);
 //   * the LDG face flux is evaluated by the lane that gathers the traces (no staging of gradient traces), and the two
-//     scatter passes are one iteration each (27 and 15 lanes) with the psiq/dpsiq parts chained in registers.
-// The kernel is bandwidth bound by design (1.3 flop/B); tensor cores do not apply (FP64, 5x9 operators).
+//     scatter passes are one iteration each with the psiq/dpsiq parts chained in registers;
+//   * running sums are fire-and-forget RED.E.ADD.F64 (one add per address and launch).
+// The kernel is memory bound by design (1.3 flop/B); tensor cores do not apply (FP64, 5x9 / 9x17 operators, FP64 pipe
+// 35 % busy at both orders).
 #pragma once
 #include <cstdio>
 #include <cstdlib>
