@@ -61,7 +61,8 @@ class Desc(C.Structure):
 
 EXPORTS = ["hnumo_init", "hnumo_finalize", "hnumo_last_error", "hnumo_upload_state", "hnumo_download_state",
            "hnumo_step", "hnumo_ti_rk_bcl", "hnumo_btp_bcl_coeffs", "hnumo_btp_substeps", "hnumo_rhs_btp",
-           "hnumo_get_array", "hnumo_diagnostics", "hnumo_comm_get_unique_id", "hnumo_comm_init", "hnumo_timing", "hnumo_set_option"]
+           "hnumo_get_array", "hnumo_diagnostics", "hnumo_snapshot_write", "hnumo_snapshot_info",
+           "hnumo_snapshot_read_restart", "hnumo_comm_get_unique_id", "hnumo_comm_init", "hnumo_timing", "hnumo_set_option"]
 
 
 def load_library():
@@ -82,6 +83,11 @@ def load_library():
         L.hnumo_rhs_btp.argtypes = [C.c_void_p, C.c_void_p]
         L.hnumo_get_array.restype = C.c_int64
         L.hnumo_get_array.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
+        L.hnumo_snapshot_write.argtypes = [C.c_char_p, C.c_int32, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_double]
+        L.hnumo_snapshot_info.argtypes = [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.hnumo_snapshot_read_restart.argtypes = [C.c_char_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p]
         L.hnumo_diagnostics.restype = C.c_int64
         L.hnumo_diagnostics.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.hnumo_comm_get_unique_id.argtypes = [C.c_void_p]
@@ -221,6 +227,43 @@ class Solver:
 
     def set_option(self, key, value):
         return self._check(self.L.hnumo_set_option(self.h, key.encode(), float(value)), "set_option")
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def snapshot_write(path, deck, q_df, qb_df):
+    """Reference-format text snapshot (`mlswe####`, diagnostics.F90:73-91) of a state in the reference layouts."""
+    L = load_library()
+    q = np.ascontiguousarray(q_df, dtype=np.float64); qb = np.ascontiguousarray(qb_df, dtype=np.float64)
+    coord = np.ascontiguousarray(deck["coord"], dtype=np.float64)
+    zb = np.ascontiguousarray(deck["zbot_df"], dtype=np.float64); al = np.ascontiguousarray(deck["alpha_mlswe"], dtype=np.float64)
+    rc = L.hnumo_snapshot_write(str(path).encode(), deck["nlayers"], deck["npoin"], deck["dt"], deck["dt_btp"], _ptr(coord), _ptr(q), _ptr(qb),
+                                _ptr(zb), _ptr(al), deck["gravity"])
+    if rc != 0:
+        raise HnumoError("snapshot_write failed (%d): %s" % (rc, L.hnumo_last_error().decode()))
+
+
+def snapshot_info(path):
+    L = load_library()
+    nl, npn, dt, dtb = C.c_int32(), C.c_int64(), C.c_double(), C.c_double()
+    rc = L.hnumo_snapshot_info(str(path).encode(), C.byref(nl), C.byref(npn), C.byref(dt), C.byref(dtb))
+    if rc != 0:
+        raise HnumoError("snapshot_info failed (%d): %s" % (rc, L.hnumo_last_error().decode()))
+    return dict(nlayers=nl.value, npoin=npn.value, dt=dt.value, dt_btp=dtb.value)
+
+
+def snapshot_read_restart(path, deck):
+    """restart_mlswe (mod_restart.F90:15-66): (q_df, qb_df, qprime_df, coord) rebuilt from a text snapshot for upload_state."""
+    L = load_library()
+    nl, npn = deck["nlayers"], deck["npoin"]
+    q = np.zeros((nl, npn, 3)); qb = np.zeros((npn, 4)); qp = np.zeros((nl, npn, 3)); coord = np.zeros((npn, 2))
+    pbp = np.ascontiguousarray(deck["pbprime_df"], dtype=np.float64); al = np.ascontiguousarray(deck["alpha_mlswe"], dtype=np.float64)
+    rc = L.hnumo_snapshot_read_restart(str(path).encode(), nl, npn, _ptr(pbp), _ptr(al), deck["gravity"], _ptr(q), _ptr(qb), _ptr(qp), _ptr(coord))
+    if rc != 0:
+        raise HnumoError("snapshot_read_restart failed (%d): %s" % (rc, L.hnumo_last_error().decode()))
+    return q, qb, qp, coord
 
 
 def nccl_unique_id():

@@ -1137,3 +1137,5 @@ int hnumo_set_option(hnumo_handle_t h, const char* key, double value) {
 }
 
 }  // extern "C"
+
+#include "snapshot.cuh"   // host-only text snapshots / restart conversion (extern "C" entry points)

@@ -142,6 +142,20 @@ int hnumo_comm_init(hnumo_handle_t h, const void* id128);
  * reference's mpi_reduce (sum for the mass, max, min).  Returns 11*nlayers + 12 or <0. */
 int64_t hnumo_diagnostics(hnumo_handle_t h, double* out, int64_t capacity);
 
+/* ---- text snapshots and restart (host only, no GPU needed) -------------------
+ * hnumo_snapshot_write: the `mlswe####` text files of src/diagnostics.F90:73-91 (nlayers, npoin, dt, dt_btp, then one d23.16
+ *   value per line: coordinates, pb, pb*ub, pb*vb, h, u, v, interface elevations, zbot) from arrays in the reference layouts
+ *   (what hnumo_download_state returns).  coord (2,npoin) may be NULL.
+ * hnumo_snapshot_info: header of such a file.
+ * hnumo_snapshot_read_restart: load_data_mlswe + restart_mlswe (src/mod_restart.F90:15-66,88-160): reads the file and rebuilds
+ *   q_df, qb_df, qprime_df for hnumo_upload_state with the statics of the restarting run.
+ * Return 0, -6 I/O error, -7 malformed file, -8 nlayers/npoin mismatch. */
+int hnumo_snapshot_write(const char* path, int32_t nlayers, int64_t npoin, double dt, double dt_btp, const double* coord,
+                         const double* q_df, const double* qb_df, const double* zbot_df, const double* alpha_mlswe, double gravity);
+int hnumo_snapshot_info(const char* path, int32_t* nlayers, int64_t* npoin, double* dt, double* dt_btp);
+int hnumo_snapshot_read_restart(const char* path, int32_t nlayers, int64_t npoin, const double* pbprime_df, const double* alpha_mlswe,
+                                double gravity, double* q_df, double* qb_df, double* qprime_df, double* coord_out);
+
 /* ---- measurement ------------------------------------------------------------------------------ */
 /* out[0] = GPU ms spent in barotropic stages since the last reset (CUDA events on the compute stream),
  * out[1] = number of barotropic stages, out[2] = GPU ms in whole steps, out[3] = steps,

@@ -155,3 +155,73 @@ def test_gloo_halo_ordering_world2():
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("HALO_OK") == 2, r.stdout + r.stderr
+
+
+def test_snapshot_roundtrip_and_restart(tmp_path):
+    """text snapshots in the reference's format (diagnostics.F90:73-91: one d23.16 value per line) and the
+    restart conversion of mod_restart.F90:15-66.  Host-only entry points of the C-ABI library (no GPU)."""
+    import numpy as np
+
+    p = hn.decks.synthetic_double_gyre(3, 2, nop=4, nlayers=3)
+    deck = hn.decks.build_deck(p)
+    rng = np.random.default_rng(7)
+    q = deck["q_df"].copy(); qb = deck["qb_df"].copy()
+    # a state in motion, consistent like the model keeps it: qb momentum = sum of the layer momenta, pb = sum of dp
+    for k in range(3):
+        q[k, :, 1] = q[k, :, 0] * rng.normal(0.0, 0.3, deck["npoin"])
+        q[k, :, 2] = q[k, :, 0] * rng.normal(0.0, 0.3, deck["npoin"])
+    qb[:, 2] = q[:, :, 1].sum(axis=0); qb[:, 3] = q[:, :, 2].sum(axis=0)
+    path = tmp_path / "mlswe0007"
+    hn.snapshot_write(path, deck, q, qb)
+    lines = open(path).read().split("\n")
+    npn, nl = deck["npoin"], 3
+    assert lines[0] == "%4d" % nl and lines[1] == "%10d" % npn
+    # Fortran d23.16: 23 characters, "0.dddddddddddddddd" mantissa with 16 digits, D exponent
+    import re
+    assert all(len(x) == 23 and re.fullmatch(r" *-?0\.\d{16}D[+-]\d\d", x) for x in lines[2:200])
+    assert len([x for x in lines if x]) == 4 + 2 * npn + 3 * npn + 4 * nl * npn + npn
+    # (16 significant digits: the reference's format does not round-trip the last bit of a double)
+    assert abs(float(lines[2].replace("D", "E")) - deck["dt"]) <= 1e-15 * deck["dt"]
+    info = hn.snapshot_info(path)
+    assert info["nlayers"] == nl and info["npoin"] == npn
+    assert abs(info["dt"] - deck["dt"]) <= 1e-15 * deck["dt"] and abs(info["dt_btp"] - deck["dt_btp"]) <= 1e-15 * deck["dt_btp"]
+    # layer thickness h of layer 1 at the first point, as diagnostics.F90 defines it
+    h0 = float(lines[4 + 2 * npn + 3 * npn].replace("D", "E"))
+    assert abs(h0 - deck["alpha_mlswe"][0] / deck["gravity"] * q[0, 0, 0]) <= 1e-15 * abs(h0)
+    q2, qb2, qp2, coord = hn.snapshot_read_restart(path, deck)
+    assert np.allclose(coord, deck["coord"], rtol=1e-15, atol=1e-9)
+    assert np.allclose(qb2[:, [0, 2, 3]], qb[:, [0, 2, 3]], rtol=2e-15, atol=1e-300)
+    assert np.allclose(qb2[:, 1], qb2[:, 0] - deck["pbprime_df"], rtol=0, atol=0)
+    assert np.allclose(q2, q, rtol=4e-15, atol=1e-12)
+    # primes as restart_mlswe rebuilds them
+    ope = q2[:, :, 0].sum(axis=0) / deck["pbprime_df"]
+    for k in range(nl):
+        assert np.allclose(qp2[k, :, 0], q2[k, :, 0] / ope, rtol=1e-15)
+        assert np.allclose(qp2[k, :, 1], q2[k, :, 1] / q2[k, :, 0] - qb2[:, 2] / qb2[:, 0], rtol=1e-13, atol=1e-15)
+    # error behaviour: size mismatch and missing file
+    other = hn.decks.build_deck(hn.decks.synthetic_double_gyre(2, 2, nop=4, nlayers=3))
+    with pytest.raises(hn.HnumoError, match="-8"):
+        hn.snapshot_read_restart(path, other)
+    with pytest.raises(hn.HnumoError, match="-6"):
+        hn.snapshot_info(tmp_path / "missing")
+
+
+def test_fortran_d23_16_formatting(tmp_path):
+    """corner cases of the d23.16 writer / reader: zero, negative, tiny, huge (three-digit exponents drop the letter)"""
+    import numpy as np
+
+    deck = dict(hn.decks.build_deck(hn.decks.synthetic_double_gyre(1, 1, nop=2, nlayers=2)))
+    vals = [0.0, -1.5, 1.0, 9.999999999999999e22, 1e-5, -2.2250738585072014e-308, 1.6e308, 123456.789e100, 0.1]
+    npn = deck["npoin"]
+    coord = np.zeros((npn, 2)); coord.flat[:len(vals)] = vals[:2 * npn]
+    deck["coord"] = coord
+    path = tmp_path / "mlswe0000"
+    hn.snapshot_write(path, deck, deck["q_df"], deck["qb_df"])
+    lines = open(path).read().split("\n")
+    got = lines[4:4 + 2 * npn]
+    assert got[0] == " 0.0000000000000000D+00" and got[1] == "-0.1500000000000000D+01" and got[2] == " 0.1000000000000000D+01"
+    assert got[3] == " 0.9999999999999999D+23" and got[4] == " 0.1000000000000000D-04"
+    assert got[5] == "-0.2225073858507201-307" and got[6] == " 0.1600000000000000+309"
+    _, _, _, c2 = hn.snapshot_read_restart(path, deck)
+    for a, b in zip(c2.flat[:2 * npn], coord.flat[:2 * npn]):
+        assert a == b or abs(a - b) <= 1e-15 * abs(b)
