@@ -20,7 +20,8 @@ def face_nodes(ilocal, ngl):
 def main():
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    p = dict(hn.decks.SHIPPED["double_gyre"], nelx=5, nely=6)
+    p = dict(hn.decks.SHIPPED["double_gyre"], nelx=int(os.environ.get("HALO_NELX", "5")), nely=int(os.environ.get("HALO_NELY", "6")),
+             partition=os.environ.get("HALO_PARTITION", "rows"))
     d = hn.decks.build_deck(p, rank, world)
     ngl, npts = d["ngl"], d["npts"]
     send, off = [], 0

@@ -157,6 +157,35 @@ def test_gloo_halo_ordering_world2():
     assert r.stdout.count("HALO_OK") == 2, r.stdout + r.stderr
 
 
+def test_gloo_halo_ordering_world4_morton():
+    """the same on 4 ranks of a Morton-curve partition (ranks with two and three neighbours, several messages per exchange)"""
+    script = os.path.join(ROOT, "tests", "gloo_halo_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29543", HALO_NELX="6", HALO_NELY="8", HALO_PARTITION="morton")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+           "--master-port", "29543", script]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("HALO_OK") == 4, r.stdout + r.stderr
+
+
+def test_general_partitions_cover_the_brick_and_pair_up():
+    """element_owner: every element has exactly one owner; neighbour lists are symmetric with equal face counts"""
+    p = dict(hn.decks.SHIPPED["double_gyre"], nelx=6, nely=8)
+    for kind, n in (("rows", 4), ("blocks:2x2", 4), ("blocks:3x2", 6), ("morton", 3), ("morton", 4), ("morton", 8)):
+        pp = dict(p, partition=kind)
+        ds = [hn.decks.build_deck(pp, r, n) for r in range(n)]
+        assert sorted(np.concatenate([d["elem_global"] for d in ds]).tolist()) == list(range(48)), kind
+        for r, d in enumerate(ds):
+            assert d["num_send_recv"].sum() == (d["face"][:, 7] == 0).sum(), kind
+            for nb, cnt in zip(d["nbh_proc"], d["num_send_recv"]):
+                o = ds[nb - 1]
+                j = o["nbh_proc"].tolist().index(r + 1)
+                assert o["num_send_recv"][j] == cnt, (kind, r, nb)
+            # left element of an interior face has the lower local number (p4est.c:1693)
+            inter = d["face"][:, 7] > 0
+            assert np.all(d["face"][inter, 6] < d["face"][inter, 7]), kind
+
+
 def test_snapshot_roundtrip_and_restart(tmp_path):
     """text snapshots in the reference's format (diagnostics.F90:73-91: one d23.16 value per line) and the
     restart conversion of mod_restart.F90:15-66.  Host-only entry points of the C-ABI library (no GPU)."""
