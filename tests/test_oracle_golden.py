@@ -95,3 +95,29 @@ def test_conditioning_noise_floor():
     assert 1e-10 < mom < 1e-5, mom
     c = np.sqrt(9.806 * 40.0)
     assert np.linalg.norm(qa[:, 2] - qb[:, 2]) / (c * np.linalg.norm(qb[:, 0])) < 1e-11
+
+
+def test_oracle_rhs_invariants():
+    """SURVEY 8(c) self-checks of the restated operators that need no Fortran run:
+    (1) lake at rest: the barotropic RHS of the resting state vanishes to round-off of its O(g p_b^2) pressure terms
+        (well-balancedness of volume + face terms, mod_rhs_btp.F90:102-370);
+    (2) discrete mass conservation: sum_I wjac(I) rhs_pbpert(I) = boundary flux = 0 with walls on all sides, on a
+        developed double-gyre state (check.F90:58 is the time-integrated form of this)."""
+    o = oracle_lib.Oracle(hn.decks.SHIPPED["lake"])
+    o.btp_bcl_coeffs()
+    r = o.rhs_btp()
+    pb = o.get("qb_df").reshape(-1, 4)[:, 0]
+    g = 9.806
+    # momentum tendencies are differences of terms of size H_bcl * massinv-weighted derivative ~ g*pb^2/alpha-scale
+    Hn = np.abs(o.get("H_bcl")).max()
+    h_min = np.sqrt((1.0 / o.get("massinv")).min())
+    assert np.abs(r[:, 0]).max() <= 1e-12 * np.abs(pb).max()
+    assert np.abs(r[:, 1:]).max() <= 1e-12 * Hn / h_min
+    o2 = oracle_lib.Oracle(dict(hn.decks.SHIPPED["double_gyre"], nelx=8, nely=8))
+    assert o2.step(2) == 0
+    o2.btp_bcl_coeffs()
+    r2 = o2.rhs_btp()
+    wj = 1.0 / o2.get("massinv")
+    total = float((wj * r2[:, 0]).sum())
+    scale = float((wj * np.abs(r2[:, 0])).sum())
+    assert scale > 0.0 and abs(total) <= 1e-12 * scale
