@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library tuning option key=value (hnumo_set_option)")
+    ap.add_argument("--partition", default="rows", help="element partition for --gpus > 1: rows (default), blocks:PXxPY, morton (decks.element_owner)")
     return ap.parse_args()
 
 
@@ -190,6 +191,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hn.build_library()
     params = workload(args)
+    params["partition"] = args.partition
     deck = hn.decks.build_deck(params, rank, world)
     S = hn.Solver(deck, device=local_rank + 1, variant=args.variant)
     if world > 1:
@@ -293,7 +295,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "synthetic double gyre %dx%d elements nop=%d %d layers (BASELINE config %s)" % (args.nelx, args.nely, args.nop, args.layers, "5" if args.nop == 8 else "4"),
                        "nelem": params["nelx"] * params["nely"], "npoin": npoin_global, "stages_per_step": stages_per_step,
-                       "dt": params["dt"], "dt_btp": deck["dt_btp"], "partition": "row blocks, %d rank(s)" % world,
+                       "dt": params["dt"], "dt_btp": deck["dt_btp"], "partition": "%s, %d rank(s)" % ("row blocks" if args.partition == "rows" else args.partition, world),
                        "l2_policy": "inputs larger than L2 (>= 60 GB of resident state per job vs 126 MB L2)",
                        "stage_kernel_variant": args.variant, "options": args.opt},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
