@@ -85,6 +85,34 @@ contains
         real(c_double), intent(inout) :: q_df(*), qb_df(*), qprime_df(*)
         if (hnumo_download_state(handle, q_df, qb_df, qprime_df) /= 0) stop "hnumo_download_state failed"
     end subroutine hnumo_b200_sync_host
+
+    ! Resident mode: the numbers print_diagnostics_mlswe prints (src/print_diagnostics.F90:59-128), reduced on the device and
+    ! then over the ranks exactly as the reference reduces them (mass: sum; max/min; Courant numbers: max; dx, dy: min).
+    ! No download of the state is needed on steps that only print this table (mod_time_loop.F90:184,251).
+    subroutine hnumo_b200_diagnostics(mass_conserv, qmax_layers, qmin_layers, qbmax, qbmin, cfl_vector, min_dx_vec)
+        use mpi
+        use mod_input, only: nlayers
+        real(c_double), intent(out) :: mass_conserv(nlayers), qmax_layers(5,nlayers), qmin_layers(5,nlayers)
+        real(c_double), intent(out) :: qbmax(4), qbmin(4), cfl_vector(2), min_dx_vec(2)
+        real(c_double) :: d(11*nlayers + 12), g(11*nlayers + 12)
+        integer :: k, ierr, n
+        n = 11*nlayers + 12
+        if (hnumo_diagnostics(handle, d, int(n, c_int64_t)) /= n) stop "hnumo_diagnostics failed"
+        do k = 1, nlayers
+            call mpi_reduce(d(11*(k-1)+1), g(11*(k-1)+1), 1, MPI_DOUBLE_PRECISION, mpi_sum, 0, mpi_comm_world, ierr)
+            call mpi_reduce(d(11*(k-1)+2), g(11*(k-1)+2), 5, MPI_DOUBLE_PRECISION, mpi_max, 0, mpi_comm_world, ierr)
+            call mpi_reduce(d(11*(k-1)+7), g(11*(k-1)+7), 5, MPI_DOUBLE_PRECISION, mpi_min, 0, mpi_comm_world, ierr)
+            mass_conserv(k) = g(11*(k-1)+1)
+            qmax_layers(:,k) = g(11*(k-1)+2 : 11*(k-1)+6)     ! h, u, v, dp, interface elevation (diagnostics.F90:24-45)
+            qmin_layers(:,k) = g(11*(k-1)+7 : 11*(k-1)+11)
+        end do
+        k = 11*nlayers
+        call mpi_reduce(d(k+1), g(k+1), 4, MPI_DOUBLE_PRECISION, mpi_max, 0, mpi_comm_world, ierr)
+        call mpi_reduce(d(k+5), g(k+5), 4, MPI_DOUBLE_PRECISION, mpi_min, 0, mpi_comm_world, ierr)
+        call mpi_reduce(d(k+9), g(k+9), 2, MPI_DOUBLE_PRECISION, mpi_max, 0, mpi_comm_world, ierr)
+        call mpi_reduce(d(k+11), g(k+11), 2, MPI_DOUBLE_PRECISION, mpi_min, 0, mpi_comm_world, ierr)
+        qbmax = g(k+1:k+4); qbmin = g(k+5:k+8); cfl_vector = g(k+9:k+10); min_dx_vec = g(k+11:k+12)
+    end subroutine hnumo_b200_diagnostics
 end module hnumo_b200_state
 
 subroutine ti_rk_bcl(q_df, qb_df, qprime_df)
