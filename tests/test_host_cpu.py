@@ -254,3 +254,26 @@ def test_fortran_d23_16_formatting(tmp_path):
     _, _, _, c2 = hn.snapshot_read_restart(path, deck)
     for a, b in zip(c2.flat[:2 * npn], coord.flat[:2 * npn]):
         assert a == b or abs(a - b) <= 1e-15 * abs(b)
+
+
+@pytest.mark.parametrize("change,code,text", [
+    (dict(method_visc=1), -3, "method_visc"),                      # quadrature-point viscosity: not implemented
+    (dict(ad_mlswe=1.0e-3), -3, "ad_mlswe"),                       # vertical shear stress: not implemented
+    (dict(nlayers=0), -2, "unsupported sizes"),
+    (dict(kstages=6), -2, "unsupported sizes"),
+    (dict(ngl=12), -2, "unsupported sizes"),
+])
+def test_init_rejects_unsupported_configurations(hn_lib, change, code, text):
+    """argument validation happens before any device work: same answers with and without a GPU"""
+    d = dict(hn.decks.build_deck(dict(hn.decks.SHIPPED["bump"], nelx=2, nely=2)))
+    d.update(change)
+    with pytest.raises(hn.HnumoError) as e:
+        hn.Solver(d)
+    assert "(%d)" % code in str(e.value) and text in str(e.value), str(e.value)
+
+
+def test_null_handle_and_bad_buffers_are_errors(hn_lib):
+    L = hn.load_library()
+    assert L.hnumo_step(None, 1) == -2 and L.hnumo_finalize(None) == -2
+    assert L.hnumo_diagnostics(None, None, 0) == -2
+    assert L.hnumo_snapshot_write(None, 1, 1, 0.0, 0.0, None, None, None, None, None, 9.806) == -2
