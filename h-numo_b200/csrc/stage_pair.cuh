@@ -939,8 +939,18 @@ inline PairDims make_pairdims_t() {
     d.FSIDE = R::FSIDE; d.VSIDE = R::VSIDE; d.ASIDE = R::ASIDE; d.TSIDE = R::TSIDE;
     return d;
 }
-inline bool stage_pair_supported(const Solver& S) { return (S.ngl == 5 && S.nq == 9) || (S.ngl == 4 && S.nq == 7) || (S.ngl == 9 && S.nq == 17); }
-inline PairDims make_pairdims(int G, int Q) { return (G == 9) ? make_pairdims_t<9, 17>() : (G == 5) ? make_pairdims_t<5, 9>() : make_pairdims_t<4, 7>(); }
+// nop 3, 4: warp per element; nop 5..8: block per element (exact integration: nq = 2 nop + 1)
+inline bool stage_pair_supported(const Solver& S) { return S.ngl >= 4 && S.ngl <= 9 && S.nq == 2 * S.ngl - 1; }
+inline PairDims make_pairdims(int G, int Q) {
+    switch (G) {
+        case 4: return make_pairdims_t<4, 7>();
+        case 5: return make_pairdims_t<5, 9>();
+        case 6: return make_pairdims_t<6, 11>();
+        case 7: return make_pairdims_t<7, 13>();
+        case 8: return make_pairdims_t<8, 15>();
+        default: return make_pairdims_t<9, 17>();
+    }
+}
 
 struct PairPackArgs {
     Mesh M;
@@ -1129,6 +1139,9 @@ inline int launch_stage_pair(Solver& S, const PairArgs& a) {
     if (S.ngl == 4 && S.nq == 7) return launch_pair_t<4, 7>(S, a);
     // nop 8: one element per block of 128 threads (81 nodes, 119 pass-2 lines, 68 face points fit; 289 quadrature points in 3 sweeps)
     if (S.ngl == 9 && S.nq == 17) return launch_pair_w<9, 17, 1, 4, true>(S, a);   // (96 threads per element measured slower: 0.41 vs 0.47)
+    if (S.ngl == 8 && S.nq == 15) return launch_pair_w<8, 15, 1, 4, true>(S, a);
+    if (S.ngl == 7 && S.nq == 13) return launch_pair_w<7, 13, 1, 4, true>(S, a);
+    if (S.ngl == 6 && S.nq == 11) return launch_pair_w<6, 11, 1, 4, true>(S, a);
     return -1;
 }
 

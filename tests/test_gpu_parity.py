@@ -33,6 +33,10 @@ DECKS = {
     # SSPRK(3,3) needs a smaller barotropic step than the shipped SSP(5,3) at the same resolution
     "nop8_noslip_drag2": lambda: dict(_nop8_small_step(), x_boundary=(2, 2), botfr=2, cd_mlswe=1e-3, kstages=3),
     "nop8_inviscid": lambda: dict(hn.decks.synthetic_double_gyre(3, 3, nop=8, nlayers=2), visc_mlswe=0.0, botfr=0),
+    # the orders in between run the same block-per-element kernel (6x11, 7x13, 8x15 operators)
+    "nop5": lambda: dict(hn.decks.synthetic_double_gyre(4, 3, nop=5, nlayers=3)),
+    "nop6": lambda: dict(hn.decks.synthetic_double_gyre(3, 4, nop=6, nlayers=2), visc_mlswe=0.0),
+    "nop7": lambda: dict(hn.decks.synthetic_double_gyre(3, 3, nop=7, nlayers=3), x_boundary=(2, 2)),
 }
 VARIANTS = [0, 1, 2, 3, 5]  # 0: element-record kernel (default), 1: simple reference-form kernel, 2/3: record-layout TMA kernels, 5: warp-per-element kernel
 
@@ -118,6 +122,13 @@ def test_phase_parity_high_order(name, variant):
 @pytest.mark.parametrize("name,nsteps", [("nop8", 2), ("nop8_noslip_drag2", 2), ("nop8_inviscid", 2)])
 def test_step_parity_high_order(name, nsteps, variant):
     test_step_parity(name, nsteps, variant)
+
+
+@pytest.mark.parametrize("name", ["nop5", "nop6", "nop7"])
+def test_intermediate_orders(name):
+    """nop 5, 6, 7: element-record kernel in block-per-element form, phase by phase and over whole steps"""
+    test_phase_parity(name, 0)
+    test_step_parity(name, 2, 0)
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
