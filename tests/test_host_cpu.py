@@ -277,3 +277,39 @@ def test_null_handle_and_bad_buffers_are_errors(hn_lib):
     assert L.hnumo_step(None, 1) == -2 and L.hnumo_finalize(None) == -2
     assert L.hnumo_diagnostics(None, None, 0) == -2
     assert L.hnumo_snapshot_write(None, 1, 1, 0.0, 0.0, None, None, None, None, None, 9.806) == -2
+
+
+def test_snapshot_is_readable_by_the_reference_loader(tmp_path):
+    """The reference ships a reader of its snapshot format: Examples/bump/load_data_numo.m (flat list of numbers: nk, npoin, dt,
+    dt_btp, coord(2,npoin), pb, u*pb, v*pb, dp(npoin,nk), u, v, z(npoin,nk+1)).  Restated in numpy and applied to a file
+    written by hnumo_snapshot_write, it must return the state that was written."""
+    deck = hn.decks.build_deck(dict(hn.decks.SHIPPED["bump"], nelx=3, nely=2))
+    q = deck["q_df"].copy(); qb = deck["qb_df"].copy()
+    q[:, :, 1] = 0.01 * q[:, :, 0]; q[:, :, 2] = -0.02 * q[:, :, 0]
+    qb[:, 2] = q[:, :, 1].sum(axis=0); qb[:, 3] = q[:, :, 2].sum(axis=0)
+    path = tmp_path / "mlswe0001"
+    hn.snapshot_write(path, deck, q, qb)
+    temp = np.array([float(t.replace("D", "E")) for t in open(path).read().split()])   # MATLAB: load(file, '-ascii')
+    count = 0
+    nk = int(temp[count]); count += 1
+    npoin = int(temp[count]); count += 1
+    dt = temp[count]; count += 1
+    dt_btp = temp[count]; count += 1
+    coord = temp[count:count + 2 * npoin].reshape(npoin, 2); count += 2 * npoin          # reshape([2,npoin]) column-major
+    pb = temp[count:count + npoin]; count += npoin
+    upb = temp[count:count + npoin]; count += npoin
+    vpb = temp[count:count + npoin]; count += npoin
+    dp = temp[count:count + npoin * nk].reshape(nk, npoin); count += npoin * nk           # reshape([npoin,nk]) column-major
+    u = temp[count:count + npoin * nk].reshape(nk, npoin); count += npoin * nk
+    v = temp[count:count + npoin * nk].reshape(nk, npoin); count += npoin * nk
+    z = temp[count:count + npoin * (nk + 1)].reshape(nk + 1, npoin); count += npoin * (nk + 1)
+    assert count == temp.size and nk == deck["nlayers"] and npoin == deck["npoin"]
+    assert abs(dt - deck["dt"]) <= 1e-15 * dt and abs(dt_btp - deck["dt_btp"]) <= 1e-15 * dt_btp
+    assert np.allclose(coord, deck["coord"], rtol=1e-15, atol=1e-12)
+    assert np.allclose(pb, qb[:, 0], rtol=2e-16 * 8) and np.allclose(upb, qb[:, 2], rtol=2e-15, atol=1e-300) and np.allclose(vpb, qb[:, 3], rtol=2e-15, atol=1e-300)
+    g, al = deck["gravity"], deck["alpha_mlswe"]
+    for k in range(nk):
+        assert np.allclose(dp[k], al[k] / g * q[k, :, 0], rtol=2e-15)      # "dp" of the loader is the thickness h in metres
+        assert np.allclose(u[k], 0.01, rtol=1e-14) and np.allclose(v[k], -0.02, rtol=1e-14)
+    assert np.allclose(z[nk], deck["zbot_df"], rtol=1e-15)
+    assert np.allclose(z[0], deck["zbot_df"] + sum(al[k] / g * q[k, :, 0] for k in range(nk)), rtol=1e-14, atol=1e-12)
