@@ -266,6 +266,29 @@ def snapshot_read_restart(path, deck):
     return q, qb, qp, coord
 
 
+def _fortran_e(x, width, digits):
+    """Fortran Ew.d edit descriptor: 0.ddddE+XX, right-justified"""
+    x = float(x)
+    if x == 0.0:
+        body = "0." + "0" * digits + "E+00"
+    else:
+        m, e = ("%.*e" % (digits - 1, abs(x))).split("e")
+        body = ("-" if x < 0 else "") + "0." + m.replace(".", "") + "E%+03d" % (int(e) + 1)
+    return body.rjust(width)
+
+
+def write_fin(path, diag, mass0):
+    """`mlswe_FIN.txt` as the reference writes it at the end of a run (print_diagnostics.F90:163-184): per layer the relative
+    mass loss |m - m0| / m0 and the max/min of h, u, v, ssh -- from the device-side diagnostics (Solver.diagnostics()) of the
+    final state and the layer masses of the initial state.  The reference's CI compares exactly this file (CI/bump/check.F90)."""
+    with open(path, "w") as f:
+        for k in range(len(diag["mass"])):
+            f.write("Layer = %8d\n" % (k + 1))
+            f.write("Mass Loss  = %s \n" % _fortran_e(abs(diag["mass"][k] - mass0[k]) / mass0[k], 16, 8))
+            for name in ("h", "u", "v", "ssh"):
+                f.write("Fields:   Max/Min = %-3s %s %s \n" % (name, _fortran_e(diag[name][k][0], 24, 12), _fortran_e(diag[name][k][1], 24, 12)))
+
+
 def nccl_unique_id():
     buf = (C.c_char * 128)()
     rc = load_library().hnumo_comm_get_unique_id(buf)

@@ -44,3 +44,24 @@ def compare_extrema(got, ref):
             for a, b in zip(got[layer][f], fields[f]):
                 worst = max(worst, abs(a - b) / scale)
     return worst
+
+
+def ci_check(fin_path, ref_path=None, nlayers=2):
+    """CI/bump/check.F90 restated: the run is rejected when a layer's mass loss exceeds 1e-12 (check.F90:58-62); for the
+    fields of lines 3..5 of each layer block (u, v, ssh) it reports |ref - val| / |ref| of max and min (check.F90:64-80).
+    Returns {(layer, field): (err_max, err_min)}."""
+    ref_path = ref_path or os.path.join(HERE, "golden", "ci_bump_ref_mlswe_FIN.txt")
+    ref = open(ref_path).read().split("\n")
+    fin = open(fin_path).read().split("\n")
+    out = {}
+    for nl in range(1, nlayers + 1):
+        index_layer = 6 * (nl - 1) + 1                      # 1-based line numbers, as in the Fortran
+        mass_loss = float(fin[index_layer + 1 - 1].split("=")[1])
+        assert mass_loss <= 1.0e-12, "Layer %d mass_loss = %g to large" % (nl, mass_loss)
+        for ifield in range(2, 5):
+            index_field = ifield + index_layer
+            r = ref[index_field - 1].split("=")[1].split()
+            v = fin[index_field - 1].split("=")[1].split()
+            assert r[0] == v[0]
+            out[(nl, r[0])] = (abs(float(r[1]) - float(v[1])) / abs(float(r[1])), abs(float(r[2]) - float(v[2])) / abs(float(r[2])))
+    return out

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import oracle_lib
-from golden_util import compare_extrema, read_fin
+from golden_util import ci_check, compare_extrema, read_fin
 from hnumo_loader import hnumo_b200 as hn
 
 
@@ -121,3 +121,29 @@ def test_oracle_rhs_invariants():
     total = float((wj * r2[:, 0]).sum())
     scale = float((wj * np.abs(r2[:, 0])).sum())
     assert scale > 0.0 and abs(total) <= 1e-12 * scale
+
+
+def test_fin_file_passes_the_reference_ci_check(bump108, tmp_path):
+    """The reference's CI (CI/bump/run_check.sh: numo3d, then check.F90 on mlswe_FIN.txt) applied to an mlswe_FIN.txt written by
+    the package from the oracle's diagnostics of the same run: mass loss <= 1e-12 per layer, and the reported relative errors of
+    the extrema of u, v, ssh against CI/bump/ref_mlswe_FIN.txt.  The file format is checked against the golden itself."""
+    o, d0, d = bump108
+    diag = dict(mass=d["mass"])
+    for f in ("h", "u", "v", "ssh"):
+        diag[f] = np.stack([d[f].max(axis=1), d[f].min(axis=1)], axis=1)
+    path = tmp_path / "mlswe_FIN.txt"
+    hn.write_fin(path, diag, d0["mass"])
+    got = open(path).read().split("\n")
+    ref = open(hn.__file__.replace("h-numo_b200/__init__.py", "tests/golden/ci_bump_ref_mlswe_FIN.txt")).read().split("\n")
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        # same columns: identical text up to the digits of the numbers
+        assert len(a.rstrip()) == len(b.rstrip()) and a.split("=")[0] == b.split("=")[0], (a, b)
+        if a.startswith("Fields"):
+            assert a.split()[3] == b.split()[3] and [len(t) for t in a.split()] == [len(t) for t in b.split()], (a, b)
+    errs = ci_check(path)
+    # u, v: 1e-7 of the velocity scale is the conditioning noise floor of this run (test_conditioning_noise_floor); ssh of layer 1
+    # is a 1e-5 m signal on a 20 m thickness
+    for (layer, field), (emax, emin) in errs.items():
+        tol = 1e-4 if field == "ssh" and layer == 1 else 1e-5
+        assert emax < tol and emin < tol, (layer, field, emax, emin)
