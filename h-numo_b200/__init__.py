@@ -273,7 +273,8 @@ def _fortran_e(x, width, digits):
         body = "0." + "0" * digits + "E+00"
     else:
         m, e = ("%.*e" % (digits - 1, abs(x))).split("e")
-        body = ("-" if x < 0 else "") + "0." + m.replace(".", "") + "E%+03d" % (int(e) + 1)
+        ex = int(e) + 1
+        body = ("-" if x < 0 else "") + "0." + m.replace(".", "") + ("E%+03d" % ex if abs(ex) < 100 else "%+04d" % ex)   # three-digit exponents drop the letter
     return body.rjust(width)
 
 
