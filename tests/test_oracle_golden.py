@@ -147,3 +147,30 @@ def test_fin_file_passes_the_reference_ci_check(bump108, tmp_path):
     for (layer, field), (emax, emin) in errs.items():
         tol = 1e-4 if field == "ssh" and layer == 1 else 1e-5
         assert emax < tol and emin < tol, (layer, field, emax, emin)
+
+
+@pytest.mark.parametrize("name", ["bump_4x4", "double_gyre_4x4", "synth3_nop4_4x3", "synth_nop8_5layers_2x2"])
+def test_oracle_matches_committed_fields(name):
+    """Field-level fixtures generated by tests/make_golden.py pin the oracle against accidental change: mass-like fields to
+    1e-12 relative L2, momentum-like fields to 1e-11 of their natural scale c*|dp| (round-off may differ with the number of
+    OpenMP threads; anything larger is a change of the restated algorithm)."""
+    import make_golden
+    import os
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_fields_%s.npz" % name))
+    got = make_golden.run(name)
+    params, _ = make_golden.CASES[name]
+    deck = hn.decks.build_deck(params)
+    nl, npoin = deck["nlayers"], deck["npoin"]
+    c = np.sqrt(deck["gravity"] * float(np.max(-deck["zbot_df"])))
+    q, q0 = got["q_df"].reshape(nl, npoin, 3), ref["q_df"].reshape(nl, npoin, 3)
+    qb, qb0 = got["qb_df"].reshape(npoin, 4), ref["qb_df"].reshape(npoin, 4)
+    qp, qp0 = got["qprime_df"].reshape(nl, npoin, 3), ref["qprime_df"].reshape(nl, npoin, 3)
+    for k in range(nl):
+        dn = np.linalg.norm(q0[k, :, 0])
+        assert np.linalg.norm(q[k, :, 0] - q0[k, :, 0]) <= 1e-12 * dn and np.linalg.norm(qp[k, :, 0] - qp0[k, :, 0]) <= 1e-12 * dn
+        for v in (1, 2):
+            assert np.linalg.norm(q[k, :, v] - q0[k, :, v]) <= 1e-11 * c * dn
+            assert np.linalg.norm(qp[k, :, v] - qp0[k, :, v]) <= 1e-11 * c * np.sqrt(npoin)
+    pn = np.linalg.norm(qb0[:, 0])
+    assert np.linalg.norm(qb[:, :2] - qb0[:, :2]) <= 1e-12 * pn
+    assert np.linalg.norm(qb[:, 2:] - qb0[:, 2:]) <= 1e-11 * c * pn
