@@ -146,7 +146,8 @@ struct MassArgs {
     const double* hq; size_t hstride;
     const double* ave_q[12];
     const double* ave_f[16];
-    double* qdp;          // [nl] nodal planes (in/out): q_df(1,:,k)
+    const double* qdp_in; // [nl] nodal planes: q_df(1,:,k) before the update
+    double* qdp;          // [nl] nodal planes: q_df(1,:,k) after it (may alias qdp_in)
     double* slmf_q[2];
     double* slmf_f[2];
     const double* massinv;
@@ -242,9 +243,9 @@ __global__ void k_layer_mass(MassArgs a) {
                 r += p;
             }
             double dpa = a.massinv[nbase + tid] * r;
-            double* qd = a.qdp + (size_t)k * a.nstride + nbase + tid;
-            double v = *qd + a.dt * dpa;
-            *qd = v;
+            const size_t Iqd = (size_t)k * a.nstride + nbase + tid;
+            double v = a.qdp_in[Iqd] + a.dt * dpa;
+            a.qdp[Iqd] = v;
             if (v < 0.0) *a.flag = 1;
         }
     }
@@ -598,7 +599,8 @@ __global__ void k_mom_volume(MomVolArgs a) {
 struct MomFaceArgs {
     Mesh M;
     const double* qprime;   // [3*nl] input primes (for the traces)
-    double* q;              // [3*nl] in/out: q_df
+    const double* q_in;     // [3*nl] q_df before the step: momentum planes are read here
+    double* q;              // [3*nl] q_df after it: thickness planes are read (already updated), momentum planes written (may alias q_in)
     double* qprime_out;     // [3*nl]
     size_t nstride;
     const double* hq; size_t hstride;
@@ -792,7 +794,7 @@ __global__ void k_mom_faces_update(MomFaceArgs a) {
             r0 = mi * r0 + a.rhs_visc[(size_t)(0 * nl + k) * a.nstride + nbase + tid];
             r1 = mi * r1 + a.rhs_visc[(size_t)(1 * nl + k) * a.nstride + nbase + tid];
             double dpk = a.q[(size_t)(0 * nl + k) * a.nstride + nbase + tid];
-            double mxo = a.q[(size_t)(1 * nl + k) * a.nstride + nbase + tid], myo = a.q[(size_t)(2 * nl + k) * a.nstride + nbase + tid];
+            double mxo = a.q_in[(size_t)(1 * nl + k) * a.nstride + nbase + tid], myo = a.q_in[(size_t)(2 * nl + k) * a.nstride + nbase + tid];
             double t1 = mxo + a.dt * r0, t2 = myo + a.dt * r1;
             double tempu = t1 + f2 * myo, tempv = t2 - f2 * mxo;
             double mxn = ab * tempu + bb * tempv, myn = -bb * tempu + ab * tempv;
@@ -854,9 +856,9 @@ __global__ void k_thickness_finish(const double* qdp, const double* pbprime_df, 
     for (int k = 0; k < nl; ++k) s += qdp[(size_t)k * nstride + I];
     double ope = s / pbprime_df[I];
     for (int k = 0; k < nl; ++k) {
-        double d = qdp[(size_t)k * nstride + I] / ope;
+        const double d = qdp[(size_t)k * nstride + I] / ope, old = qprime_dp[(size_t)k * nstride + I];   // (dpprime2 may alias qprime_dp)
         dpprime2[(size_t)k * nstride + I] = d;
-        qprime2_dp[(size_t)k * nstride + I] = 0.5 * (qprime_dp[(size_t)k * nstride + I] + d);
+        qprime2_dp[(size_t)k * nstride + I] = 0.5 * (old + d);
     }
 }
 

@@ -47,7 +47,6 @@ struct StageArgs {
     double* rhs_out[3];
     double a1, a2, a3, dtt, g, cd, alpha_bot, visc;
     int botfr, has_visc, load_q0, load_q2, store_q0, store_q2, rhs_only;
-    int pf_blocks;    // fused kernel: L2 prefetch distance in thread blocks (0 = off)
     int acc_graduvb;  // 1: accumulate graduvb per stage (reference form); 0: derived after the loop from the nodal velocity sums
 };
 

@@ -16,6 +16,7 @@
 #include <dlfcn.h>
 #include <pthread.h>
 
+#include <condition_variable>
 #include <mutex>
 
 #include "hnumo_dev.cuh"
@@ -43,6 +44,14 @@ __global__ void k_unpack_traces(double* tr, size_t trstride, int nslots, int nha
     if (t >= tot) return;
     int n = t % ngl; size_t r = t / ngl; int v = r % nv; int h = r / nv;
     tr[(size_t)v * trstride + ((size_t)nslots + h) * ngl + n] = recv[t];
+}
+// trace records [slot][tside] (stage_pair.cuh): gather the records of the processor-face slots in exchange order; the
+// receive side needs no unpack -- the halo region of the trace buffer is the receive buffer
+__global__ void k_pack_trace_records(const double* tr, const int* halo_slot, int nhalo, int tside, double* send) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nhalo * tside) return;
+    size_t h = t / tside; int j = (int)(t - h * tside);
+    send[t] = tr[(size_t)halo_slot[h] * tside + j];
 }
 __global__ void k_pack_nodal(const double* planes, size_t stride, const int* halo_slot, int nhalo, int np, int ngl, int npts, double* send) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,14 +104,29 @@ static int nccl_load() {
 static const int NCCL_DOUBLE = 8;  // ncclFloat64
 
 // ---- local (in-process) back end -------------------------------------------------------------------------------
+// Host barrier with an abort flag: a rank that fails (anywhere in its step) aborts the group, which releases every
+// waiter with an error instead of leaving the peers blocked for ever.
 struct LocalGroup {
-    int nranks = 0;
+    int nranks = 0, members = 0;
     std::vector<Solver*> peers;
-    pthread_barrier_t barrier;
-    bool barrier_ok = false;
+    std::mutex m;
+    std::condition_variable cv;
+    int waiting = 0;
+    unsigned long generation = 0;
+    bool aborted = false;
+    int wait() {   // 0 ok, -1 group aborted
+        std::unique_lock<std::mutex> lk(m);
+        if (aborted) return -1;
+        const unsigned long gen = generation;
+        if (++waiting == nranks) { waiting = 0; ++generation; cv.notify_all(); return 0; }
+        cv.wait(lk, [&] { return generation != gen || aborted; });
+        return aborted ? -1 : 0;
+    }
+    void abort() { std::lock_guard<std::mutex> lk(m); aborted = true; cv.notify_all(); }
 };
 static std::mutex g_local_mutex;
 static std::map<int, LocalGroup*> g_local_groups;
+static std::map<LocalGroup*, int> g_local_ids;
 
 inline int halo_get_unique_id(void* id128) {
     if (nccl_load()) return -1;
@@ -118,8 +142,10 @@ inline int halo_comm_init(Solver& S, const void* id128) {
         int gid; memcpy(&gid, c + 8, sizeof(int));
         std::lock_guard<std::mutex> lk(g_local_mutex);
         LocalGroup*& G = g_local_groups[gid];
-        if (!G) { G = new LocalGroup(); G->nranks = S.desc.nranks; G->peers.assign(S.desc.nranks, nullptr); pthread_barrier_init(&G->barrier, nullptr, S.desc.nranks); G->barrier_ok = true; }
-        G->peers[S.desc.rank] = &S;
+        if (G && G->nranks != S.desc.nranks) { set_error("halo", "local group id already in use with another number of ranks"); return -1; }
+        if (!G) { G = new LocalGroup(); G->nranks = S.desc.nranks; G->peers.assign(S.desc.nranks, nullptr); g_local_ids[G] = gid; }
+        if (S.desc.rank < 0 || S.desc.rank >= G->nranks || G->peers[S.desc.rank]) { set_error("halo", "rank out of range or already registered in the local group"); return -1; }
+        G->peers[S.desc.rank] = &S; G->members++;
         S.local_group = G;
         return 0;
     }
@@ -132,8 +158,17 @@ inline int halo_comm_init(Solver& S, const void* id128) {
 }
 inline void halo_comm_destroy(Solver& S) {
     if (S.nccl_comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(S.nccl_comm); S.nccl_comm = nullptr; }
-    S.local_group = nullptr;
+    if (S.local_group) {
+        std::lock_guard<std::mutex> lk(g_local_mutex);
+        LocalGroup* G = (LocalGroup*)S.local_group;
+        G->abort();   // a peer still stepping must not wait for a rank that is gone
+        if (S.desc.rank >= 0 && S.desc.rank < G->nranks && G->peers[S.desc.rank] == &S) { G->peers[S.desc.rank] = nullptr; G->members--; }
+        if (G->members == 0) { g_local_groups.erase(g_local_ids[G]); g_local_ids.erase(G); delete G; }
+        S.local_group = nullptr;
+    }
 }
+// a failing rank releases its peers (no-op for NCCL: a failed NCCL call is fatal for the communicator anyway)
+inline void halo_abort(Solver& S) { if (S.local_group) ((LocalGroup*)S.local_group)->abort(); }
 
 // move S.d_send -> neighbours' S.d_recv ; `per_face` doubles per halo face
 static int halo_sendrecv(Solver& S, size_t per_face, double* recv_base = nullptr, cudaStream_t st = nullptr) {
@@ -153,20 +188,25 @@ static int halo_sendrecv(Solver& S, size_t per_face, double* recv_base = nullptr
     }
     if (S.local_group) {
         LocalGroup* G = (LocalGroup*)S.local_group;
-        if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("halo", "stream sync failed"); return -1; }
-        pthread_barrier_wait(&G->barrier);  // every rank's send buffer is complete
-        for (size_t i = 0; i < S.nbh_rank.size(); ++i) {
+        int err = 0;
+        if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("halo", "stream sync failed"); err = 1; }
+        if (err) G->abort();
+        if (G->wait()) { if (!err) set_error("halo", "a peer rank of the local group failed"); return -1; }   // every rank's send buffer is complete
+        for (size_t i = 0; i < S.nbh_rank.size() && !err; ++i) {
             Solver* P = G->peers[S.nbh_rank[i]];
             // find my block in the peer's neighbour list: the peer lists me with the same number of faces in the same order
             size_t poff = 0; bool found = false;
-            for (size_t j = 0; j < P->nbh_rank.size(); ++j)
+            for (size_t j = 0; P && j < P->nbh_rank.size(); ++j)
                 if (P->nbh_rank[j] == S.desc.rank) { poff = (size_t)P->nbh_offset[j] * per_face; found = true; break; }
-            if (!found) { set_error("halo", "asymmetric neighbour lists"); return -1; }
+            if (!found) { set_error("halo", "asymmetric neighbour lists"); err = 1; break; }
             size_t off = (size_t)S.nbh_offset[i] * per_face, cnt = (size_t)S.nbh_count[i] * per_face;
-            cudaMemcpyAsync(recv_base + off, P->d_send + poff, cnt * sizeof(double), cudaMemcpyDeviceToDevice, st);
+            if (cudaMemcpyAsync(recv_base + off, P->d_send + poff, cnt * sizeof(double), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+                set_error("halo", "peer copy failed"); err = 1;
+            }
         }
-        if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("halo", "copy failed"); return -1; }
-        pthread_barrier_wait(&G->barrier);  // peers may overwrite their send buffers now
+        if (!err && cudaStreamSynchronize(st) != cudaSuccess) { set_error("halo", "copy failed"); err = 1; }
+        if (err) G->abort();
+        if (G->wait()) { if (!err) set_error("halo", "a peer rank of the local group failed"); return -1; }   // peers may overwrite their send buffers now
         return 0;
     }
     set_error("halo", "partition has processor faces but no communicator (call hnumo_comm_init)");

@@ -6,9 +6,6 @@
 #include "bcl_kernels.cuh"
 #include "btp_kernels.cuh"
 #include "halo.cuh"
-#include "stage_fused.cuh"
-#include "stage_tma.cuh"
-#include "stage_rec.cuh"
 #include "stage_pair.cuh"
 #include "diag.cuh"
 
@@ -31,9 +28,9 @@ Planes palloc(Solver& S, int nplanes, size_t stride) {
 void upload_ops(const Ops& ops) { cudaMemcpyToSymbol(c_ops, &ops, sizeof(Ops)); }
 
 // stage kernel variants: 0 element-record kernel (default; falls back to 1 for orders without an instantiation),
-// 1 simple reference-form kernel, 2/3 record-layout TMA kernels, 5 warp-per-element kernel on the plane layout
-static bool use_fused(const Solver& S) { return S.variant == 5 && stage_fused_supported(S); }
-static bool use_pair(const Solver& S) { return (S.variant == 0 || S.variant == 4) && S.p_rec != nullptr; }
+// 1 simple reference-form kernel (any order, reference-form accumulators: the bisecting aid).  The earlier experiments
+// (warp-per-element kernel on planes, record-layout TMA kernels; all measured slower) live in the git history of round 1.
+static bool use_pair(const Solver& S) { return S.variant == 0 && S.p_rec != nullptr; }
 
 // kernels templated on (ngl, nq[, nlayers]): compile-time sizes for the shipped orders, 0 = run-time size
 #define HN_LAUNCH_GQ(kern, S, smem, args)                                                                     \
@@ -212,7 +209,7 @@ static void fill_stage_args(Solver& S, StageArgs& a, Planes& qb, const Planes& q
     for (int v = 0; v < 8; ++v) a.acc_q[v] = S.acc_q[v];
     for (int v = 0; v < 11; ++v) a.acc_f[v] = S.acc_f[v];
     a.g = S.g; a.cd = S.cd; a.alpha_bot = S.alpha[S.nl - 1]; a.visc = S.visc;
-    a.botfr = S.botfr; a.has_visc = S.has_visc; a.acc_graduvb = !use_fused(S); a.pf_blocks = S.pf_blocks;
+    a.botfr = S.botfr; a.has_visc = S.has_visc; a.acc_graduvb = 1;
 }
 
 // run-time-size kernels need the shared-memory opt-in above 48 kB (nop 8: 58 kB for the simple stage kernel)
@@ -222,7 +219,6 @@ static void smem_opt_in(K kern, size_t bytes) {
 }
 
 static int launch_stage(Solver& S, const StageArgs& a) {
-    if (use_fused(S)) return launch_stage_fused(S, a);
     StageSmem L(S.ngl, S.nq);
     smem_opt_in(k_btp_stage_simple, L.total * sizeof(double));
     k_btp_stage_simple<<<S.nelem, threads_for(S), L.total * sizeof(double), S.stream>>>(a);
@@ -241,7 +237,22 @@ static int prime_traces(Solver& S, const double* const* in, int mode, double* tr
     return 0;
 }
 
+static int pair_pack(Solver& S, const Planes& qb, const Planes& qprime, int cur);
+static void fill_pair_args(Solver& S, PairArgs& a);
+static int halo_exchange_trace_records(Solver& S, double* tr, int tside, cudaStream_t st = nullptr);
+// create_rhs_btp (mod_rhs_btp.F90:28-59) of the resident state, evaluated by the stage kernel the solver is configured
+// with (variant 0: element-record kernel in its rhs_only mode; variant 1: simple kernel)
 int rhs_btp_only(Solver& S, Planes& qb, const Planes& qprime, double* d_rhs_out) {
+    if (use_pair(S)) {
+        if (pair_pack(S, qb, qprime, 0)) return -1;
+        PairArgs a; fill_pair_args(S, a);
+        a.a1 = 0.0; a.a2 = 1.0; a.a3 = 0.0; a.dtt = 0.0;
+        a.tr_in = S.p_tr[0]; a.tr_out = S.p_tr[1]; a.part = 0;
+        a.rhs_only = 1; a.rhs_out = d_rhs_out; a.rhs_stride = (size_t)S.npoin;
+        if (launch_stage_pair(S, a)) return -1;
+        HN_CUDA(cudaGetLastError());
+        return 0;
+    }
     const double* in[3] = {qb[0], qb[1], qb[2]};
     prime_traces(S, in, 0, S.trace[0].p);
     if (halo_exchange_traces(S, S.trace[0], S.has_visc ? 7 : 3)) return -1;
@@ -256,12 +267,12 @@ int rhs_btp_only(Solver& S, Planes& qb, const Planes& qprime, double* d_rhs_out)
     return 0;
 }
 
-static int btp_solve_rec(Solver& S, Planes& qb, const Planes& qprime);
-static int btp_solve_pair(Solver& S, Planes& qb, const Planes& qprime);
-// ti_barotropic_ssprk_mlswe (mod_rk_mlswe.F90:19-151)
-int btp_solve(Solver& S, Planes& qb, const Planes& qprime) {
-    if (use_pair(S)) return btp_solve_pair(S, qb, qprime);
-    if ((S.variant == 2 || S.variant == 3) && S.r_geoc) return btp_solve_rec(S, qb, qprime);
+static int btp_solve_pair(Solver& S, const Planes& qb_in, Planes& qb, const Planes& qprime);
+// ti_barotropic_ssprk_mlswe (mod_rk_mlswe.F90:19-151): advances the barotropic state qb_in through N_btp substeps into qb
+// (the two may be the same planes) and leaves the time averages in ave_q / ave_f / ave_n
+int btp_solve(Solver& S, const Planes& qb_in, Planes& qb, const Planes& qprime) {
+    if (use_pair(S)) return btp_solve_pair(S, qb_in, qb, qprime);
+    if (qb_in.p != qb.p) cudaMemcpyAsync(qb.p, qb_in.p, 3 * (size_t)S.npoin * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
     cudaMemsetAsync(S.acc_n.p, 0, S.acc_n.stride * S.acc_n.n * sizeof(double), S.stream);
     cudaMemsetAsync(S.acc_q.p, 0, S.acc_q.stride * S.acc_q.n * sizeof(double), S.stream);
     cudaMemsetAsync(S.acc_f.p, 0, S.acc_f.stride * S.acc_f.n * sizeof(double), S.stream);
@@ -306,7 +317,7 @@ int btp_solve(Solver& S, Planes& qb, const Planes& qprime) {
         for (int v = 0; v < 8; ++v) f.acc_q[v] = S.acc_q[v];
         for (int v = 0; v < 11; ++v) f.acc_f[v] = S.acc_f[v];
         f.tr = S.trace[cur].p; f.tr_vs = S.trace[cur].stride; f.tr_rs = S.ngl;
-        f.en = S.npts; f.eq = S.nq2; f.ef = S.nq; f.derive_graduvb = use_fused(S);
+        f.en = S.npts; f.eq = S.nq2; f.ef = S.nq; f.derive_graduvb = 0;
         for (int v = 0; v < 12; ++v) f.ave_q[v] = S.ave_q[v];
         for (int v = 0; v < 16; ++v) f.ave_f[v] = S.ave_f[v];
         for (int v = 0; v < 7; ++v) f.ave_n[v] = S.ave_n[v];
@@ -334,7 +345,7 @@ int btp_solve(Solver& S, Planes& qb, const Planes& qprime) {
 }
 
 // halo exchange of trace records: gather -> send/recv straight into the halo region of the trace buffer
-static int halo_exchange_trace_records(Solver& S, double* tr, int tside, cudaStream_t st = nullptr) {
+static int halo_exchange_trace_records(Solver& S, double* tr, int tside, cudaStream_t st) {
     if (S.nhalo == 0) return 0;
     if (!st) st = S.stream;
     size_t tot = (size_t)S.nhalo * tside;
@@ -343,140 +354,101 @@ static int halo_exchange_trace_records(Solver& S, double* tr, int tside, cudaStr
     return halo_sendrecv(S, (size_t)tside, tr + (size_t)S.nslots * tside, st);
 }
 
-// ti_barotropic_ssprk_mlswe (mod_rk_mlswe.F90:19-151) on the record layout with the TMA stage kernel
-static int btp_solve_rec(Solver& S, Planes& qb, const Planes& qprime) {
-    const RecDims D = make_recdims(S.ngl, S.nq);
-    const size_t NE = (size_t)S.nelem;
-    const int naccq = (S.botfr == 2) ? 8 : 6;
-    cudaMemsetAsync(S.r_accn, 0, NE * D.ACCN * sizeof(double), S.stream);
-    cudaMemsetAsync(S.r_accq, 0, NE * D.ACCQ * sizeof(double), S.stream);
-    cudaMemsetAsync(S.r_accf, 0, NE * 4 * D.ASIDE * sizeof(double), S.stream);
-    cudaMemsetAsync(S.r_q2, 0, NE * D.QB * sizeof(double), S.stream);
-    int cur = 0;
-    {
-        RecPackArgs p; memset(&p, 0, sizeof(p));
-        p.M = S.mesh; p.D = D;
-        for (int v = 0; v < 3; ++v) p.qb[v] = qb[v];
-        const int bl = S.nl - 1;
-        const double* nstp[14] = {S.pbprime_df, S.massinv, qprime[0 * S.nl + bl], qprime[1 * S.nl + bl], qprime[2 * S.nl + bl], S.pbprime_visc,
-                                  S.btp_dpp_graduv[0], S.btp_dpp_graduv[1], S.btp_dpp_graduv[2], S.btp_dpp_graduv[3],
-                                  S.coriolis_df, S.tauw_df, S.tauw_df + S.npoin, S.zbot_df};
-        for (int v = 0; v < 14; ++v) p.nstp[v] = nstp[v];
-        const double* qstp[5] = {S.oop_q, S.Hbcl, S.Quu, S.Quv, S.Qvv};
-        for (int v = 0; v < 5; ++v) p.qstp[v] = qstp[v];
-        const double* fstp[11] = {S.cL, S.cR, S.cLR, S.lam, S.oop_edge, S.Quu_e, S.Quv_e, S.Qvv_e, S.Hbcl_e, S.pbl, S.pbr};
-        for (int v = 0; v < 11; ++v) p.fstp[v] = fstp[v];
-        for (int v = 0; v < 4; ++v) p.bdg[v] = S.btp_dpp_graduv[v];
-        p.pbv = S.pbprime_visc; p.pbn = S.pbn; p.hstat = S.h_stat.p; p.hstat_stride = S.h_stat.stride;
-        p.r_qb = S.r_qb; p.r_nst = S.r_nst; p.r_qst = S.r_qst; p.r_fst = S.r_fst; p.r_vst = S.r_vst; p.r_tr = S.r_tr[cur];
-        p.has_visc = S.has_visc;
-        k_rec_pack<<<S.nelem, 128, 2 * S.npts * sizeof(double), S.stream>>>(p);
-        S.n_launches++;
-        if (halo_exchange_trace_records(S, S.r_tr[cur], D.TSIDE)) return -1;
-    }
-    cudaEvent_t e_start, e_stop;
-    take_event_pair(S, 0, e_start, e_stop);
-    cudaEventRecord(e_start, S.stream);
-    TmaArgs a; memset(&a, 0, sizeof(a));
-    a.nelem = S.nelem; a.nslots = S.nslots;
-    a.geoc = S.r_geoc; a.nst = S.r_nst; a.qst = S.r_qst; a.fst = S.r_fst; a.vst = S.r_vst;
-    a.qb = S.r_qb; a.q0 = S.r_q0; a.q2 = S.r_q2; a.accn = S.r_accn; a.accq = S.r_accq; a.accf = S.r_accf;
-    a.nbx = (const int4*)S.d_nbx;
-    a.g = S.g; a.cd = S.cd; a.alpha_bot = S.alpha[S.nl - 1]; a.visc = S.visc; a.botfr = S.botfr; a.has_visc = S.has_visc;
-    for (int mstep = 1; mstep <= S.N_btp; ++mstep) {
-        for (int ik = 1; ik <= S.kstages; ++ik) {
-            a.a1 = S.ssprk_a[ik - 1][0]; a.a2 = S.ssprk_a[ik - 1][1]; a.a3 = S.ssprk_a[ik - 1][2];
-            a.dtt = S.dt_btp * S.ssprk_beta[ik - 1];
-            a.load_q0 = (ik > 1 && a.a1 != 0.0);
-            a.load_q2 = (a.a3 != 0.0);
-            a.store_q0 = (ik == 1 && S.kstages > 1);
-            a.store_q2 = (S.kstages == 5 && ik == 2);
-            a.tr_in = S.r_tr[cur]; a.tr_out = S.r_tr[cur ^ 1];
-            if ((S.variant == 3 ? launch_stage_tma(S, a, naccq) : launch_stage_rec(S, a, naccq))) return -1;
-            cur ^= 1;
-            if (halo_exchange_trace_records(S, S.r_tr[cur], D.TSIDE)) return -1;
-        }
-    }
-    cudaEventRecord(e_stop, S.stream);
-    S.n_stages += (long)S.N_btp * S.kstages;
-    // state back to planes, time averages
-    k_rec_unpack_qb<<<nblk(S.npoin), 256, 0, S.stream>>>(S.nelem, D, S.r_qb, qb[0], qb[1], qb[2]);
-    k_rec_sum_traces<<<nblk((size_t)S.nslots * S.ngl), 256, 0, S.stream>>>(S.nelem, D, S.r_accn, S.r_tr[cur]);
-    S.n_launches += 2;
-    if (halo_exchange_trace_records(S, S.r_tr[cur], D.TSIDE)) return -1;
-    FinalizeArgs f; memset(&f, 0, sizeof(f));
-    f.M = S.mesh;
-    for (int v = 0; v < 6; ++v) f.acc_n[v] = S.r_accn + (size_t)v * D.NP;
-    for (int v = 6; v < 10; ++v) f.acc_n[v] = nullptr;
-    for (int v = 0; v < 8; ++v) f.acc_q[v] = S.r_accq + (size_t)v * D.NQ2;
-    for (int v = 0; v < 11; ++v) f.acc_f[v] = S.r_accf + (size_t)v * D.Q;
-    f.en = D.ACCN; f.eq = D.ACCQ; f.ef = D.ASIDE; f.derive_graduvb = 1;
-    f.tr = S.r_tr[cur]; f.tr_vs = D.G; f.tr_rs = D.TSIDE;
-    for (int v = 0; v < 12; ++v) f.ave_q[v] = S.ave_q[v];
-    for (int v = 0; v < 16; ++v) f.ave_f[v] = S.ave_f[v];
-    for (int v = 0; v < 7; ++v) f.ave_n[v] = S.ave_n[v];
-    f.oop_q = S.oop_q; f.Hbcl = S.Hbcl; f.Hbcl_e = S.Hbcl_e; f.cL = S.cL; f.cR = S.cR; f.lam = S.lam; f.pbl = S.pbl; f.pbr = S.pbr;
-    f.qp_dp = qprime[0 * S.nl + S.nl - 1]; f.qp_u = qprime[1 * S.nl + S.nl - 1]; f.qp_v = qprime[2 * S.nl + S.nl - 1];
-    f.S = (double)(S.kstages * S.N_btp); f.N_inv = 1.0 / (double)(S.kstages * S.N_btp); f.cd_over_g = S.cd / S.g;
-    f.botfr = S.botfr;
-    size_t sm = (sops_doubles_host(S.ngl, S.nq) + 8 * S.npts + 6 * S.ngl * S.nq) * sizeof(double);
-    HN_LAUNCH_GQ(k_btp_finalize, S, sm, f);
-    S.n_launches++;
-    // graduvb_face_ave side 2 on processor boundaries = the neighbour's averaged gradient at the face nodes
-    if (S.has_visc && S.nhalo > 0)
-        if (halo_exchange_nodal(S, S.ave_n[3], 4, S.ave_n.stride, S.h_gub)) return -1;
-    HN_CUDA(cudaGetLastError());
-    return 0;
-}
-
-// ti_barotropic_ssprk_mlswe (mod_rk_mlswe.F90:19-151) on per-element records with the element-pair stage kernel
-static int btp_solve_pair(Solver& S, Planes& qb, const Planes& qprime) {
+// planes -> element records (header, state, statics, initial traces; sums zeroed) + exchange of the initial traces
+static int pair_pack(Solver& S, const Planes& qb, const Planes& qprime, int cur) {
     const PairDims D = make_pairdims(S.ngl, S.nq);
-    const size_t NE = (size_t)S.nelem;
-    cudaMemsetAsync(S.p_accf, 0, NE * 4 * D.ASIDE * sizeof(double), S.stream);
-    int cur = 0;
-    {
-        PairPackArgs p; memset(&p, 0, sizeof(p));
-        p.M = S.mesh; p.D = D;
-        for (int v = 0; v < 3; ++v) p.qb[v] = qb[v];
-        const int bl = S.nl - 1;
-        const double* nstp[11] = {S.pbprime_df, S.oop_df, S.massinv, qprime[0 * S.nl + bl], qprime[1 * S.nl + bl], qprime[2 * S.nl + bl],
-                                  S.pbprime_visc, S.btp_dpp_graduv[0], S.btp_dpp_graduv[1], S.btp_dpp_graduv[2], S.btp_dpp_graduv[3]};
-        for (int v = 0; v < 11; ++v) p.nstp[v] = nstp[v];
-        const double* qstp[9] = {S.Hbcl, S.Quu, S.Quv, S.Qvv, S.coriolis_q, S.tauw_q, S.tauw_q + S.npoin_q, S.gradzb_q, S.gradzb_q + S.npoin_q};
-        for (int v = 0; v < 9; ++v) p.qstp[v] = qstp[v];
-        const double* fstp[11] = {S.cL, S.cR, S.cLR, S.lam, S.oop_edge, S.Quu_e, S.Quv_e, S.Qvv_e, S.Hbcl_e, S.pbl, S.pbr};
-        for (int v = 0; v < 11; ++v) p.fstp[v] = fstp[v];
-        for (int v = 0; v < 4; ++v) p.bdg[v] = S.btp_dpp_graduv[v];
-        p.pbv = S.pbprime_visc; p.pbn = S.pbn; p.hstat = S.h_stat.p; p.hstat_stride = S.h_stat.stride;
-        p.rec = S.p_rec; p.tr = S.p_tr[cur];
-        p.has_visc = S.has_visc;
-        k_pair_pack<<<S.nelem, 128, 2 * S.npts * sizeof(double), S.stream>>>(p);
-        S.n_launches++;
-        if (halo_exchange_trace_records(S, S.p_tr[cur], D.TSIDE)) return -1;
-    }
-    cudaEvent_t e_start, e_stop;
-    take_event_pair(S, 0, e_start, e_stop);
-    cudaEventRecord(e_start, S.stream);
-    PairArgs a; memset(&a, 0, sizeof(a));
+    PairPackArgs p; memset(&p, 0, sizeof(p));
+    p.M = S.mesh; p.D = D;
+    for (int v = 0; v < 3; ++v) p.qb[v] = qb[v];
+    const int bl = S.nl - 1;
+    const double* nstp[11] = {S.pbprime_df, S.oop_df, S.massinv, qprime[0 * S.nl + bl], qprime[1 * S.nl + bl], qprime[2 * S.nl + bl],
+                              S.pbprime_visc, S.btp_dpp_graduv[0], S.btp_dpp_graduv[1], S.btp_dpp_graduv[2], S.btp_dpp_graduv[3]};
+    for (int v = 0; v < 11; ++v) p.nstp[v] = nstp[v];
+    const double* qstp[9] = {S.Hbcl, S.Quu, S.Quv, S.Qvv, S.coriolis_q, S.tauw_q, S.tauw_q + S.npoin_q, S.gradzb_q, S.gradzb_q + S.npoin_q};
+    for (int v = 0; v < 9; ++v) p.qstp[v] = qstp[v];
+    const double* fstp[11] = {S.cL, S.cR, S.cLR, S.lam, S.oop_edge, S.Quu_e, S.Quv_e, S.Qvv_e, S.Hbcl_e, S.pbl, S.pbr};
+    for (int v = 0; v < 11; ++v) p.fstp[v] = fstp[v];
+    for (int v = 0; v < 4; ++v) p.bdg[v] = S.btp_dpp_graduv[v];
+    p.pbv = S.pbprime_visc; p.pbn = S.pbn; p.hstat = S.h_stat.p; p.hstat_stride = S.h_stat.stride;
+    p.rec = S.p_rec; p.tr = S.p_tr[cur];
+    p.has_visc = S.has_visc;
+    k_pair_pack<<<S.nelem, 128, 2 * S.npts * sizeof(double), S.stream>>>(p);
+    S.n_launches++;
+    return halo_exchange_trace_records(S, S.p_tr[cur], D.TSIDE);
+}
+static void fill_pair_args(Solver& S, PairArgs& a) {
+    memset(&a, 0, sizeof(a));
     a.nelem = S.nelem; a.nslots = S.nslots;
     a.rec = S.p_rec; a.accf = S.p_accf;
     a.g = S.g; a.cd_g = S.cd / S.g; a.cd_alpha = S.cd / S.alpha[S.nl - 1]; a.visc = S.visc; a.botfr = S.botfr;
     a.prefetch = S.pair_prefetch; a.pf_dist = S.pair_pf_dist;
+}
+
+// ti_barotropic_ssprk_mlswe (mod_rk_mlswe.F90:19-151) on per-element records with the element-pair stage kernel
+static void set_stage_coeffs(const Solver& S, PairArgs& a, int ik) {
+    a.a1 = S.ssprk_a[ik - 1][0]; a.a2 = S.ssprk_a[ik - 1][1]; a.a3 = S.ssprk_a[ik - 1][2];
+    a.dtt = S.dt_btp * S.ssprk_beta[ik - 1];
+    a.load_q0 = (ik > 1 && a.a1 != 0.0);
+    a.load_q2 = (a.a3 != 0.0);
+    a.store_q0 = (ik == 1 && S.kstages > 1);
+    a.store_q2 = (S.kstages == 5 && ik == 2);
+}
+static int btp_solve_pair(Solver& S, const Planes& qb_in, Planes& qb, const Planes& qprime) {
+    const PairDims D = make_pairdims(S.ngl, S.nq);
+    const size_t NE = (size_t)S.nelem;
+    cudaMemsetAsync(S.p_accf, 0, NE * 4 * D.ASIDE * sizeof(double), S.stream);
+    int cur = 0;
+    if (pair_pack(S, qb_in, qprime, cur)) return -1;
+    cudaEvent_t e_start, e_stop;
+    take_event_pair(S, 0, e_start, e_stop);
+    cudaEventRecord(e_start, S.stream);
+    PairArgs a; fill_pair_args(S, a);
     // Overlap: a stage of the elements that own a processor face runs on comm_stream, followed by the pack and
     // the send/recv of their new traces; the stage of every other element runs on `stream` at the same time.  Both need
     // only results of the previous stage: ev_int = "interior stage done" (awaited by the next boundary stage, which reads
     // the traces of interior neighbours), ev_halo = "boundary stage + exchange done" (awaited by the next interior stage).
     const bool overlap = S.overlap && S.nhalo > 0 && S.n_belem > 0;
     if (overlap) { cudaEventRecord(S.ev0, S.stream); cudaEventRecord(S.ev1, S.stream); }
-    for (int mstep = 1; mstep <= S.N_btp; ++mstep) {
+    int mstep = 1;
+    // CUDA graph: without processor faces a substep is kstages back-to-back launches whose arguments repeat
+    // every `cyc` substeps (the trace buffers ping-pong, so an odd kstages needs two substeps to come back).  One cycle is
+    // captured once per solver and replayed: small decks (bump, lake: 9 us of kernel per stage) are launch-bound otherwise.
+    const bool graph = (S.use_graph < 0 ? S.nhalo == 0 : S.use_graph != 0) && S.nhalo == 0;
+    if (graph) {
+        const int cyc = (S.kstages & 1) ? 2 : 1;
+        const int key = S.pair_prefetch * 4096 + S.pair_pf_dist;
+        if (S.N_btp >= 2 * cyc) {
+            if (!S.graph_exec || S.graph_key != key) {
+                if (S.graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)S.graph_exec); S.graph_exec = nullptr; }
+                cudaGraph_t g = nullptr;
+                HN_CUDA(cudaStreamBeginCapture(S.stream, cudaStreamCaptureModeThreadLocal));
+                int c2 = 0, bad = 0;
+                const long l0 = S.n_launches;
+                for (int m = 0; m < cyc && !bad; ++m)
+                    for (int ik = 1; ik <= S.kstages && !bad; ++ik) {
+                        set_stage_coeffs(S, a, ik);
+                        a.tr_in = S.p_tr[c2]; a.tr_out = S.p_tr[c2 ^ 1]; a.part = 0;
+                        bad = launch_stage_pair(S, a);
+                        c2 ^= 1;
+                    }
+                S.n_launches = l0;
+                cudaError_t ce = cudaStreamEndCapture(S.stream, &g);
+                if (bad || ce != cudaSuccess || !g) { set_error("cudaStreamEndCapture", cudaGetErrorString(ce)); if (g) cudaGraphDestroy(g); return -1; }
+                cudaGraphExec_t ge = nullptr;
+                ce = cudaGraphInstantiate(&ge, g, 0);
+                cudaGraphDestroy(g);
+                if (ce != cudaSuccess) { set_error("cudaGraphInstantiate", cudaGetErrorString(ce)); return -1; }
+                S.graph_exec = ge; S.graph_key = key;
+            }
+            for (; mstep + cyc - 1 <= S.N_btp; mstep += cyc) {
+                HN_CUDA(cudaGraphLaunch((cudaGraphExec_t)S.graph_exec, S.stream));
+                S.n_launches += (long)cyc * S.kstages;
+            }
+        }
+    }
+    for (; mstep <= S.N_btp; ++mstep) {
         for (int ik = 1; ik <= S.kstages; ++ik) {
-            a.a1 = S.ssprk_a[ik - 1][0]; a.a2 = S.ssprk_a[ik - 1][1]; a.a3 = S.ssprk_a[ik - 1][2];
-            a.dtt = S.dt_btp * S.ssprk_beta[ik - 1];
-            a.load_q0 = (ik > 1 && a.a1 != 0.0);
-            a.load_q2 = (a.a3 != 0.0);
-            a.store_q0 = (ik == 1 && S.kstages > 1);
-            a.store_q2 = (S.kstages == 5 && ik == 2);
+            set_stage_coeffs(S, a, ik);
             a.tr_in = S.p_tr[cur]; a.tr_out = S.p_tr[cur ^ 1];
             if (!overlap) {
                 a.part = 0;
@@ -554,13 +526,14 @@ int btp_bcl_coeffs(Solver& S, const Planes& qprime, const Planes& dpv) {
     return 0;
 }
 
-static int layer_mass_and_consistency(Solver& S, const Planes& qprime, Planes& q) {
+// q_in: layer state before the step; q_out: receives the new thickness planes (may be the same planes)
+static int layer_mass_and_consistency(Solver& S, const Planes& qprime, const Planes& q_in, Planes& q) {
     // layer_mass_rhs + update of q_df(1) (mod_splitting.F90:58-78 / 217-232)
     MassArgs m; memset(&m, 0, sizeof(m));
     m.M = S.mesh; m.qprime = qprime.p; m.nstride = qprime.stride; m.hq = S.h_q.p; m.hstride = S.h_q.stride;
     for (int v = 0; v < 12; ++v) m.ave_q[v] = S.ave_q[v];
     for (int v = 0; v < 16; ++v) m.ave_f[v] = S.ave_f[v];
-    m.qdp = q[0]; m.slmf_q[0] = S.slmf_q[0]; m.slmf_q[1] = S.slmf_q[1]; m.slmf_f[0] = S.slmf_f[0]; m.slmf_f[1] = S.slmf_f[1];
+    m.qdp_in = q_in[0]; m.qdp = q[0]; m.slmf_q[0] = S.slmf_q[0]; m.slmf_q[1] = S.slmf_q[1]; m.slmf_f[0] = S.slmf_f[0]; m.slmf_f[1] = S.slmf_f[1];
     m.massinv = S.massinv; m.flag = S.d_flag; m.dt = S.dt;
     size_t per = S.ngl * S.nq;
     size_t sm = (sops_doubles_host(S.ngl, S.nq) + 3 * S.npts + 3 * per + 12 * S.ngl + 2 * S.nq2 + 2 * per + S.npts + 4 * S.nq) * sizeof(double);
@@ -582,11 +555,12 @@ static int layer_mass_and_consistency(Solver& S, const Planes& qprime, Planes& q
     return 0;
 }
 
-static int momentum_update(Solver& S, const Planes& qprime_in, Planes& q, Planes& qprime_out, const Planes& qb, int full_prime) {
+// q_in: layer momentum before the step (planes 1,2 are read); q: thickness planes already updated, momentum planes written
+static int momentum_update(Solver& S, const Planes& qprime_in, const Planes& dpv, const Planes& q_in, Planes& q, Planes& qprime_out, const Planes& qb, int full_prime) {
     size_t per = S.ngl * S.nq;
     if (S.has_visc) {
         LapArgs l; memset(&l, 0, sizeof(l));
-        l.M = S.mesh; l.dpv = S.dpv.p; l.dpp_graduv = S.dpp_graduv.p; l.nstride = S.dpv.stride;
+        l.M = S.mesh; l.dpv = dpv.p; l.dpp_graduv = S.dpp_graduv.p; l.nstride = dpv.stride;
         for (int v = 0; v < 4; ++v) l.graduvb[v] = S.ave_n[3 + v];
         l.h_dpv = S.h_dpv.p; l.h_dpg = S.h_dpg.p; l.h_gub = S.h_gub.p; l.hstride = S.h_dpv.stride;
         l.massinv = S.massinv; l.rhs_visc = S.rhs_visc.p; l.visc = S.visc;
@@ -595,7 +569,7 @@ static int momentum_update(Solver& S, const Planes& qprime_in, Planes& q, Planes
         S.n_launches++;
     }
     MomVolArgs v; memset(&v, 0, sizeof(v));
-    v.M = S.mesh; v.qprime = qprime_in.p; v.q = q.p; v.nstride = q.stride;
+    v.M = S.mesh; v.qprime = qprime_in.p; v.q = q_in.p; v.nstride = q.stride;
     for (int i = 0; i < 12; ++i) v.ave_q[i] = S.ave_q[i];
     v.ope2_df = S.ave_n[0]; v.zbot_df = S.zbot_df; v.tauwx_q = S.tauw_q; v.tauwy_q = S.tauw_q + S.npoin_q; v.pbprime_q = S.pbprime_q;
     v.rhs_mom = S.rhs_mom.p;
@@ -605,7 +579,7 @@ static int momentum_update(Solver& S, const Planes& qprime_in, Planes& q, Planes
     HN_LAUNCH_GQL(k_mom_volume, S, sm, v);
     S.n_launches++;
     MomFaceArgs f; memset(&f, 0, sizeof(f));
-    f.M = S.mesh; f.qprime = qprime_in.p; f.q = q.p; f.qprime_out = qprime_out.p; f.nstride = q.stride; f.hq = S.h_q.p; f.hstride = S.h_q.stride;
+    f.M = S.mesh; f.qprime = qprime_in.p; f.q_in = q_in.p; f.q = q.p; f.qprime_out = qprime_out.p; f.nstride = q.stride; f.hq = S.h_q.p; f.hstride = S.h_q.stride;
     for (int i = 0; i < 3; ++i) f.qb[i] = qb[i];
     f.pbprime_df = S.pbprime_df;
     for (int i = 0; i < 16; ++i) f.ave_f[i] = S.ave_f[i];
@@ -623,33 +597,31 @@ static void dcopy(Solver& S, double* dst, const double* src, size_t n) {
     cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
 }
 
-// ti_rk_bcl (ti_rk_bcl.F90:9-87)
+// ti_rk_bcl (ti_rk_bcl.F90:9-87).  The reference works on copies (qb_df_pred, q_df_pred, dpprime_visc ...); here the
+// kernels read one set of planes and write another, so that of the reference's array copies only one remains.
 int bcl_step(Solver& S) {
     const size_t NL3 = (size_t)3 * S.nl * S.npoin, NL1 = (size_t)S.nl * S.npoin;
     cudaEvent_t e_start, e_stop;
     take_event_pair(S, 1, e_start, e_stop);
     cudaEventRecord(e_start, S.stream);
-    // ---- prediction
-    dcopy(S, S.qbp.p, S.qb.p, 3 * (size_t)S.npoin);
-    dcopy(S, S.dpv.p, S.qprime[0], NL1);
-    if (btp_bcl_coeffs(S, S.qprime, S.dpv)) return -1;   // also refreshes the halo copy of qprime traces
-    if (btp_solve(S, S.qbp, S.qprime)) return -1;
-    dcopy(S, S.q2.p, S.q.p, NL3);
-    if (layer_mass_and_consistency(S, S.qprime, S.q2)) return -1;
-    if (momentum_update(S, S.qprime, S.q2, S.qprime2, S.qbp, 1)) return -1;
+    // ---- prediction: qbp <- substeps(qb), q2 <- layer update of q, qprime2 <- new primes
+    Planes dpv1; dpv1.p = S.qprime.p; dpv1.stride = S.qprime.stride; dpv1.n = S.nl;   // dpprime_visc = qprime_df(1,:,:)
+    if (btp_bcl_coeffs(S, S.qprime, dpv1)) return -1;   // also refreshes the halo copy of qprime traces
+    if (btp_solve(S, S.qb, S.qbp, S.qprime)) return -1;
+    if (layer_mass_and_consistency(S, S.qprime, S.q, S.q2)) return -1;
+    if (momentum_update(S, S.qprime, dpv1, S.q, S.q2, S.qprime2, S.qbp, 1)) return -1;
     // ---- correction
     k_average<<<nblk(NL3), 256, 0, S.stream>>>(S.qprime2.p, S.qprime2.p, S.qprime.p, NL3);
     S.n_launches++;
-    dcopy(S, S.dpv.p, S.qprime2[0], NL1);
+    dcopy(S, S.dpv.p, S.qprime2[0], NL1);   // dpprime_visc of the corrector: the averaged thickness, which k_thickness_finish replaces below
     if (btp_bcl_coeffs(S, S.qprime2, S.dpv)) return -1;
-    if (btp_solve(S, S.qb, S.qprime2)) return -1;
-    if (layer_mass_and_consistency(S, S.qprime2, S.q)) return -1;
-    k_thickness_finish<<<nblk(S.npoin), 256, 0, S.stream>>>(S.q[0], S.pbprime_df, S.qprime[0], S.dpprime2.p, S.qprime2[0], S.nl, S.q.stride, S.npoin);
+    if (btp_solve(S, S.qb, S.qb, S.qprime2)) return -1;
+    if (layer_mass_and_consistency(S, S.qprime2, S.q, S.q)) return -1;
+    // dpprime of the new thickness -> qprime (in place); qprime2.dp <- average of old and new
+    k_thickness_finish<<<nblk(S.npoin), 256, 0, S.stream>>>(S.q[0], S.pbprime_df, S.qprime[0], S.qprime[0], S.qprime2[0], S.nl, S.q.stride, S.npoin);
     S.n_launches++;
     if (halo_exchange_nodal(S, S.qprime2.p, 3 * S.nl, S.qprime2.stride, S.h_q)) return -1;
-    if (momentum_update(S, S.qprime2, S.q, S.qprime3, S.qb, 0)) return -1;
-    dcopy(S, S.qprime[0], S.dpprime2.p, NL1);
-    dcopy(S, S.qprime[S.nl], S.qprime3[S.nl], 2 * NL1);
+    if (momentum_update(S, S.qprime2, S.dpv, S.q, S.q, S.qprime, S.qb, 0)) return -1;   // writes u', v' of qprime
     cudaEventRecord(e_stop, S.stream);
     S.n_steps++;
     HN_CUDA(cudaGetLastError());
@@ -674,6 +646,37 @@ using namespace hn;
 
 struct hnumo_handle_s { Solver S; };
 
+// every public entry point runs on the handle's device, whatever the calling thread's current device is
+#define HN_ENTER(h)                                  \
+    if (!(h)) return -2;                             \
+    Solver& S = (h)->S;                              \
+    if (cudaSetDevice(S.device) != cudaSuccess) { set_error("cudaSetDevice", "cannot select the handle's device"); return -1; }
+
+// common teardown of hnumo_finalize and of every failure path of hnumo_init (members are null until created)
+static void destroy_solver(hnumo_handle_s* h) {
+    Solver& S = h->S;
+    cudaSetDevice(S.device);
+    if (S.stream) cudaStreamSynchronize(S.stream);
+    if (S.comm_stream) cudaStreamSynchronize(S.comm_stream);
+    halo_comm_destroy(S);
+    if (S.graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)S.graph_exec);
+    for (void* p : S.allocs) if (p) cudaFree(p);
+    void* extra[] = {S.d_diag_partial, S.d_diag_res, S.d_nbr, S.d_nbslot, S.d_flag, S.d_halo_slot, S.d_belems};
+    for (void* p : extra) if (p) cudaFree(p);
+    for (cudaEvent_t e : S.ev_pool) cudaEventDestroy(e);
+    if (S.ev0) cudaEventDestroy(S.ev0);
+    if (S.ev1) cudaEventDestroy(S.ev1);
+    if (S.stream) cudaStreamDestroy(S.stream);
+    if (S.comm_stream) cudaStreamDestroy(S.comm_stream);
+    delete h;
+}
+// failure inside hnumo_init: release everything acquired so far
+#define HN_INIT_CUDA(call)                                                                   \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess) { hn::set_error(#call, cudaGetErrorString(_e)); destroy_solver(H); return -1; } \
+    } while (0)
+
 extern "C" {
 
 const char* hnumo_last_error(void) { return g_err; }
@@ -692,15 +695,16 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     hnumo_handle_s* H = new hnumo_handle_s();
     Solver& S = H->S;
     S.desc = *d;
+    if (d->device > ndev) { set_error("hnumo_init", "desc.device exceeds the number of CUDA devices"); delete H; return -2; }
     if (d->device > 0) cudaSetDevice(d->device - 1);
     cudaGetDevice(&S.device);
-    HN_CUDA(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+    HN_INIT_CUDA(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
     {   // the boundary/exchange stream overtakes the interior work
         int pr_lo = 0, pr_hi = 0;
         cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi);
-        HN_CUDA(cudaStreamCreateWithPriority(&S.comm_stream, cudaStreamNonBlocking, pr_hi));
+        HN_INIT_CUDA(cudaStreamCreateWithPriority(&S.comm_stream, cudaStreamNonBlocking, pr_hi));
     }
-    cudaEventCreate(&S.ev0); cudaEventCreate(&S.ev1); cudaEventCreate(&S.ev2); cudaEventCreate(&S.ev3);
+    cudaEventCreateWithFlags(&S.ev0, cudaEventDisableTiming); cudaEventCreateWithFlags(&S.ev1, cudaEventDisableTiming);
     S.nelem = d->nelem; S.ngl = d->ngl; S.nq = d->nq; S.npts = d->ngl * d->ngl; S.nq2 = d->nq * d->nq; S.nl = d->nlayers; S.nface = d->nface;
     S.npoin = S.nelem * S.npts; S.npoin_q = S.nelem * S.nq2; S.nslots = S.nelem * 4;
     S.kstages = d->kstages; S.N_btp = d->N_btp; S.botfr = d->botfr; S.dt = d->dt; S.dt_btp = d->dt_btp; S.g = d->gravity; S.cd = d->cd_mlswe;
@@ -724,7 +728,6 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     for (int n = 0; n < S.ngl; ++n)
         for (int k = 0; k < S.ngl; ++k) S.ops.DT[n + S.ngl * k] = S.ops.D[k + S.ngl * n];
     upload_ops(S.ops);
-    upload_fused_ops(S.ops, S.ngl, S.nq);
     // connectivity from face(8,nface)
     std::vector<int> nbr(S.nslots, -99), nbslot(S.nslots, 0);
     std::vector<double> fgeom((size_t)S.nslots * 3, 0.0);
@@ -747,7 +750,7 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     for (int f = 0; f < S.nface; ++f) {
         const int32_t* F = d->face + (size_t)8 * f;
         int ilocl = F[4], ilocr = F[5], el = F[6] - 1, er = F[7];
-        if (ilocl < 3 || ilocl > 6 || el < 0 || el >= S.nelem) { set_error("hnumo_init", "face table: only 2-D xy faces (local face 3..6) are supported"); delete H; return -2; }
+        if (ilocl < 3 || ilocl > 6 || el < 0 || el >= S.nelem) { set_error("hnumo_init", "face table: only 2-D xy faces (local face 3..6) are supported"); destroy_solver(H); return -2; }
         int sl = el * 4 + slot_of(ilocl);
         S.face_owner_slot[f] = sl; S.face_er[f] = er;
         const double* G = d->face_geom + (size_t)3 * f;
@@ -758,18 +761,18 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
             nbr[sl] = er - 1; nbslot[sl] = slot_of(ilocr);
             nbr[sr] = el; nbslot[sr] = slot_of(ilocl);
             fgeom[(size_t)sr * 3 + 0] = G[0]; fgeom[(size_t)sr * 3 + 1] = G[1]; fgeom[(size_t)sr * 3 + 2] = G[2];
-            if (!(el < er - 1)) { set_error("hnumo_init", "face table: left element must have the lower number (p4est.c:1693)"); delete H; return -2; }
+            if (!(el < er - 1)) { set_error("hnumo_init", "face table: left element must have the lower number (p4est.c:1693)"); destroy_solver(H); return -2; }
         } else if (er == 0) {
-            if (halo_of_face[f] < 0) { set_error("hnumo_init", "processor face missing from nbh_send_recv"); delete H; return -2; }
+            if (halo_of_face[f] < 0) { set_error("hnumo_init", "processor face missing from nbh_send_recv"); destroy_solver(H); return -2; }
             nbr[sl] = NBR_HALO; nbslot[sl] = halo_of_face[f];
             S.halo_slot[halo_of_face[f]] = sl;
         } else if (er == -4 || er == -2) {
             nbr[sl] = er;
-        } else { set_error("hnumo_init", "unsupported boundary code in face(8,:) (only -4 free slip, -2 no slip)"); delete H; return -2; }
+        } else { set_error("hnumo_init", "unsupported boundary code in face(8,:) (only -4 free slip, -2 no slip)"); destroy_solver(H); return -2; }
     }
     for (int s = 0; s < S.nslots; ++s)
-        if (nbr[s] == -99) { set_error("hnumo_init", "face table does not cover every element side"); delete H; return -2; }
-    HN_CUDA(cudaMalloc(&S.d_nbr, S.nslots * sizeof(int))); HN_CUDA(cudaMalloc(&S.d_nbslot, S.nslots * sizeof(int)));
+        if (nbr[s] == -99) { set_error("hnumo_init", "face table does not cover every element side"); destroy_solver(H); return -2; }
+    HN_INIT_CUDA(cudaMalloc(&S.d_nbr, S.nslots * sizeof(int))); HN_INIT_CUDA(cudaMalloc(&S.d_nbslot, S.nslots * sizeof(int)));
     cudaMemcpy(S.d_nbr, nbr.data(), S.nslots * sizeof(int), cudaMemcpyHostToDevice);
     cudaMemcpy(S.d_nbslot, nbslot.data(), S.nslots * sizeof(int), cudaMemcpyHostToDevice);
     S.d_fgeom = dalloc(S, (size_t)S.nslots * 3); S.d_em = dalloc(S, (size_t)S.nelem * 5);
@@ -777,14 +780,14 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     cudaMemcpy(S.d_fgeom, fgeom.data(), fgeom.size() * sizeof(double), cudaMemcpyHostToDevice);
     cudaMemcpy(S.d_em, d->elem_metrics, (size_t)S.nelem * 5 * sizeof(double), cudaMemcpyHostToDevice);
     if (S.nhalo > 0) {
-        HN_CUDA(cudaMalloc(&S.d_halo_slot, S.nhalo * sizeof(int)));
+        HN_INIT_CUDA(cudaMalloc(&S.d_halo_slot, S.nhalo * sizeof(int)));
         cudaMemcpy(S.d_halo_slot, S.halo_slot.data(), S.nhalo * sizeof(int), cudaMemcpyHostToDevice);
         // elements that own a processor face, in element order (they advance ahead of the interior, see btp_solve_pair)
         std::vector<int> bel;
         for (int e = 0; e < S.nelem; ++e)
             if (nbr[e * 4] == NBR_HALO || nbr[e * 4 + 1] == NBR_HALO || nbr[e * 4 + 2] == NBR_HALO || nbr[e * 4 + 3] == NBR_HALO) bel.push_back(e);
         S.n_belem = (int)bel.size();
-        HN_CUDA(cudaMalloc(&S.d_belems, std::max<size_t>(bel.size(), 1) * sizeof(int)));
+        HN_INIT_CUDA(cudaMalloc(&S.d_belems, std::max<size_t>(bel.size(), 1) * sizeof(int)));
         cudaMemcpy(S.d_belems, bel.data(), bel.size() * sizeof(int), cudaMemcpyHostToDevice);
     }
     Mesh& M = S.mesh;
@@ -839,7 +842,7 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     S.acc_n = palloc(S, 10, NP); S.acc_q = palloc(S, 8, NQ); S.acc_f = palloc(S, 11, NS);
     S.ave_q = palloc(S, 12, NQ); S.ave_f = palloc(S, 16, NS); S.ave_n = palloc(S, 7, NP);
     S.slmf_q = palloc(S, 2, NQ); S.slmf_f = palloc(S, 2, NS);
-    S.rhs_mom = palloc(S, 2 * nl, NP); S.rhs_visc = palloc(S, 2 * nl, NP);
+    S.rhs_mom = palloc(S, std::max(3, 2 * nl), NP);   // also the 3-plane scratch of hnumo_rhs_btp S.rhs_visc = palloc(S, 2 * nl, NP);
     S.stage_buf = dalloc(S, std::max((size_t)3 * nl * NP, 4 * NP));
     size_t hs = (size_t)std::max(S.nhalo, 1) * S.ngl;
     S.h_q = palloc(S, 3 * nl, hs); S.h_dp = palloc(S, nl, hs); S.h_dpv = palloc(S, nl, hs); S.h_dpg = palloc(S, 4 * nl, hs);
@@ -852,52 +855,39 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     if (const char* ev = getenv("HNUMO_PAIR_NE")) S.pair_ne = atoi(ev);          // tuning overrides (tests, sweeps)
     if (const char* ev = getenv("HNUMO_PAIR_WARPS")) S.pair_warps = atoi(ev);
     if (const char* ev = getenv("HNUMO_PAIR_PREFETCH")) S.pair_prefetch = atoi(ev);
-    if ((S.variant == 0 || S.variant == 4) && stage_pair_supported(S)) {
+    if (S.variant == 0 && stage_pair_supported(S)) {
         const PairDims D = make_pairdims(S.ngl, S.nq);
         const size_t NE = (size_t)S.nelem;
         S.p_rec = dalloc(S, NE * D.REC); S.p_accf = dalloc(S, NE * 4 * D.ASIDE);
         S.p_tr[0] = dalloc(S, (size_t)(S.nslots + S.nhalo) * D.TSIDE); S.p_tr[1] = dalloc(S, (size_t)(S.nslots + S.nhalo) * D.TSIDE);
-    }
-    if ((S.variant == 2 || S.variant == 3) && stage_tma_supported(S)) {
-        const RecDims D = make_recdims(S.ngl, S.nq);
-        const size_t NE = (size_t)S.nelem;
-        S.r_geoc = dalloc(S, NE * D.GEOC); S.r_qb = dalloc(S, NE * D.QB); S.r_q0 = dalloc(S, NE * D.QB); S.r_q2 = dalloc(S, NE * D.QB);
-        S.r_nst = dalloc(S, NE * D.NST); S.r_accn = dalloc(S, NE * D.ACCN); S.r_qst = dalloc(S, NE * D.QST); S.r_accq = dalloc(S, NE * D.ACCQ);
-        S.r_fst = dalloc(S, NE * 4 * D.FSIDE); S.r_accf = dalloc(S, NE * 4 * D.ASIDE); S.r_vst = dalloc(S, NE * 4 * D.VSIDE);
-        S.r_tr[0] = dalloc(S, (size_t)(S.nslots + S.nhalo) * D.TSIDE); S.r_tr[1] = dalloc(S, (size_t)(S.nslots + S.nhalo) * D.TSIDE);
-        HN_CUDA(cudaMalloc(&S.d_nbx, NE * sizeof(int4)));
-        if (S.r_geoc && S.d_nbx) k_rec_static<<<nblk(NE), 256, 0, S.stream>>>(M, D, S.r_geoc, (int4*)S.d_nbx);
+        // per-device function attributes of the stage kernel now (not inside a graph capture, not from a racing thread)
+        PairArgs ca; memset(&ca, 0, sizeof(ca)); ca.configure_only = 1;
+        if (launch_stage_pair(S, ca)) { destroy_solver(H); return -1; }
     }
     S.d_send = dalloc(S, S.halo_capacity); S.d_recv = dalloc(S, S.halo_capacity);
-    HN_CUDA(cudaMalloc(&S.d_flag, sizeof(int)));
+    HN_INIT_CUDA(cudaMalloc(&S.d_flag, sizeof(int)));
     cudaMemsetAsync(S.d_flag, 0, sizeof(int), S.stream);
-    for (void* p : S.allocs) if (!p) { delete H; return -1; }
-    HN_CUDA(cudaStreamSynchronize(S.stream));
-    HN_CUDA(cudaGetLastError());
-    memset(&S.desc.psiq, 0, sizeof(void*));  // host pointers are not retained
+    for (void* p : S.allocs) if (!p) { destroy_solver(H); return -1; }
+    HN_INIT_CUDA(cudaStreamSynchronize(S.stream));
+    HN_INIT_CUDA(cudaGetLastError());
+    // host pointers are not retained: only the scalars of the descriptor stay valid
+    S.desc.psiq = S.desc.dpsiq = S.desc.wnq = S.desc.wgl = S.desc.dpsi = nullptr;
+    S.desc.face = nullptr; S.desc.elem_metrics = S.desc.face_geom = nullptr;
+    S.desc.pbprime_df = S.desc.massinv = S.desc.coriolis_df = S.desc.tau_wind_df = S.desc.zbot_df = nullptr;
+    S.desc.alpha_mlswe = S.desc.ssprk_a = S.desc.ssprk_beta = nullptr;
+    S.desc.nbh_proc = S.desc.num_send_recv = S.desc.nbh_send_recv = nullptr;
     *out = H;
     return 0;
 }
 
 int hnumo_finalize(hnumo_handle_t h) {
     if (!h) return -2;
-    Solver& S = h->S;
-    cudaStreamSynchronize(S.stream);
-    halo_comm_destroy(S);
-    for (void* p : S.allocs) cudaFree(p);
-    if (S.d_nbx) cudaFree(S.d_nbx);
-    if (S.d_diag_partial) cudaFree(S.d_diag_partial);
-    if (S.d_diag_res) cudaFree(S.d_diag_res);
-    cudaFree(S.d_nbr); cudaFree(S.d_nbslot); cudaFree(S.d_flag); if (S.d_halo_slot) cudaFree(S.d_halo_slot); if (S.d_belems) cudaFree(S.d_belems);
-    cudaEventDestroy(S.ev0); cudaEventDestroy(S.ev1); cudaEventDestroy(S.ev2); cudaEventDestroy(S.ev3);
-    cudaStreamDestroy(S.stream); cudaStreamDestroy(S.comm_stream);
-    delete h;
+    destroy_solver(h);
     return 0;
 }
 
 int hnumo_upload_state(hnumo_handle_t h, const double* q_df, const double* qb_df, const double* qprime_df) {
-    if (!h) return -2;
-    Solver& S = h->S;
+    HN_ENTER(h);
     const size_t NP = S.npoin;
     HN_CUDA(cudaMemcpyAsync(S.stage_buf, qb_df, 4 * NP * sizeof(double), cudaMemcpyHostToDevice, S.stream));
     k_aos_to_planes<<<nblk(NP), 256, 0, S.stream>>>(S.stage_buf, S.qb.p, 4, 1, 3, 1, NP, NP);
@@ -911,8 +901,7 @@ int hnumo_upload_state(hnumo_handle_t h, const double* q_df, const double* qb_df
 }
 
 int hnumo_download_state(hnumo_handle_t h, double* q_df, double* qb_df, double* qprime_df) {
-    if (!h) return -2;
-    Solver& S = h->S;
+    HN_ENTER(h);
     const size_t NP = S.npoin;
     k_planes_to_aos<<<nblk(NP), 256, 0, S.stream>>>(S.stage_buf, S.qb.p, 4, 1, 3, 1, NP, NP);
     k_pb_to_aos<<<nblk(NP), 256, 0, S.stream>>>(S.stage_buf, S.qb[0], S.pbprime_df, NP);
@@ -935,10 +924,9 @@ static int check_flag(Solver& S) {
 }
 
 int hnumo_step(hnumo_handle_t h, int32_t nsteps) {
-    if (!h) return -2;
-    Solver& S = h->S;
+    HN_ENTER(h);
     for (int i = 0; i < nsteps; ++i) {
-        if (bcl_step(S)) return -1;
+        if (bcl_step(S)) { halo_abort(S); return -1; }
         if (S.ev_used >= 192) harvest_events(S);  // only between steps: every recorded pair is complete here
     }
     int rc = check_flag(S);
@@ -956,8 +944,7 @@ int hnumo_ti_rk_bcl(hnumo_handle_t h, double* q_df, double* qb_df, double* qprim
 }
 
 int hnumo_btp_bcl_coeffs(hnumo_handle_t h) {
-    if (!h) return -2;
-    Solver& S = h->S;
+    HN_ENTER(h);
     cudaMemcpyAsync(S.dpv.p, S.qprime[0], (size_t)S.nl * S.npoin * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
     if (btp_bcl_coeffs(S, S.qprime, S.dpv)) return -1;
     HN_CUDA(cudaStreamSynchronize(S.stream));
@@ -965,17 +952,15 @@ int hnumo_btp_bcl_coeffs(hnumo_handle_t h) {
 }
 
 int hnumo_btp_substeps(hnumo_handle_t h) {
-    if (!h) return -2;
-    Solver& S = h->S;
-    if (btp_solve(S, S.qb, S.qprime)) return -1;
+    HN_ENTER(h);
+    if (btp_solve(S, S.qb, S.qb, S.qprime)) return -1;
     harvest_events(S);
     HN_CUDA(cudaStreamSynchronize(S.stream));
     return 0;
 }
 
 int hnumo_rhs_btp(hnumo_handle_t h, double* rhs) {
-    if (!h) return -2;
-    Solver& S = h->S;
+    HN_ENTER(h);
     double* d_rhs = S.rhs_mom.p;  // scratch: 3 planes
     if (rhs_btp_only(S, S.qb, S.qprime, d_rhs)) return -1;
     k_planes_to_aos<<<nblk(S.npoin), 256, 0, S.stream>>>(S.stage_buf, d_rhs, 3, 0, 3, 1, S.npoin, S.npoin);
@@ -986,8 +971,7 @@ int hnumo_rhs_btp(hnumo_handle_t h, double* rhs) {
 
 // reference-layout export of work arrays (tests)
 int64_t hnumo_get_array(hnumo_handle_t h, const char* name, double* out, int64_t capacity) {
-    if (!h) return -2;
-    Solver& S = h->S;
+    HN_ENTER(h);
     cudaStreamSynchronize(S.stream);
     const size_t NP = S.npoin, NQ = S.npoin_q;
     std::string nm(name);
@@ -1076,8 +1060,8 @@ int64_t hnumo_get_array(hnumo_handle_t h, const char* name, double* out, int64_t
 
 // device-side diagnostics (diag.cuh): per layer mass, max/min of h u v dp elevation; max/min of qb; Courant numbers
 int64_t hnumo_diagnostics(hnumo_handle_t h, double* out, int64_t capacity) {
-    if (!h || !out) return -2;
-    Solver& S = h->S;
+    if (!out) return -2;
+    HN_ENTER(h);
     const int nvals = S.nl * DIAG_PER_LAYER + 14, nout = S.nl * DIAG_PER_LAYER + DIAG_TAIL;
     if (capacity < nout) { set_error("hnumo_diagnostics", "output buffer too small (need 11*nlayers + 12 doubles)"); return -4; }
     if (!S.d_diag_partial) {
@@ -1108,11 +1092,13 @@ int64_t hnumo_diagnostics(hnumo_handle_t h, double* out, int64_t capacity) {
 }
 
 int hnumo_comm_get_unique_id(void* id128) { return halo_get_unique_id(id128); }
-int hnumo_comm_init(hnumo_handle_t h, const void* id128) { return h ? halo_comm_init(h->S, id128) : -2; }
+int hnumo_comm_init(hnumo_handle_t h, const void* id128) {
+    HN_ENTER(h);
+    return halo_comm_init(S, id128);
+}
 
 int hnumo_timing(hnumo_handle_t h, double* out8, int32_t reset) {
-    if (!h) return -2;
-    Solver& S = h->S;
+    HN_ENTER(h);
     harvest_events(S);
     out8[0] = S.ms_btp; out8[1] = (double)S.n_stages; out8[2] = S.ms_step; out8[3] = (double)S.n_steps; out8[4] = (double)S.n_launches;
     out8[5] = S.ms_btp_last; out8[6] = S.ms_step_last; out8[7] = 0.0;
@@ -1121,12 +1107,9 @@ int hnumo_timing(hnumo_handle_t h, double* out8, int32_t reset) {
 }
 
 int hnumo_set_option(hnumo_handle_t h, const char* key, double value) {
-    if (!h) return -2;
-    Solver& S = h->S;
+    HN_ENTER(h);
     if (!strcmp(key, "stage_kernel_variant")) { S.variant = (int)value; return 0; }
     if (!strcmp(key, "use_graph")) { S.use_graph = (int)value; return 0; }
-    if (!strcmp(key, "prefetch_blocks")) { S.pf_blocks = (int)value; return 0; }
-    if (!strcmp(key, "tma_blocks_per_sm")) { S.tma_blocks_per_sm = (int)value; return 0; }
     if (!strcmp(key, "pair_ne")) { S.pair_ne = (int)value; return 0; }
     if (!strcmp(key, "pair_warps")) { S.pair_warps = (int)value; return 0; }
     if (!strcmp(key, "pair_prefetch")) { S.pair_prefetch = (int)value; return 0; }

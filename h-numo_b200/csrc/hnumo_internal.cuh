@@ -125,16 +125,14 @@ struct Solver {
     size_t halo_capacity = 0;  // doubles per buffer
     void* nccl_comm = nullptr;
     // timing
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // interior stage done / boundary stage + exchange done (btp_solve_pair)
+    void* graph_exec = nullptr;   // CUDA graph of one cycle of the substep loop (see btp_solve_pair)
+    int graph_key = -1, use_graph = -1;   // use_graph: -1 auto (on when the partition has no processor faces), 0 off, 1 on
     std::vector<cudaEvent_t> ev_pool;  // pairs (start, stop) around every barotropic stage loop / whole step
     std::vector<int> ev_kind;          // 0 = barotropic stage loop, 1 = whole step
     size_t ev_used = 0;
     double ms_btp = 0, ms_step = 0, ms_btp_last = 0, ms_step_last = 0;
     long n_stages = 0, n_steps = 0, n_launches = 0;
-    // record layout of the TMA stage kernel (stage_tma.cuh)
-    double *r_geoc = nullptr, *r_qb = nullptr, *r_q0 = nullptr, *r_q2 = nullptr, *r_nst = nullptr, *r_accn = nullptr,
-           *r_qst = nullptr, *r_accq = nullptr, *r_fst = nullptr, *r_accf = nullptr, *r_vst = nullptr, *r_tr[2] = {nullptr, nullptr};
-    void* d_nbx = nullptr;
     // record layout of the element-pair stage kernel (stage_pair.cuh): one record per element, face sums, traces
     double *p_rec = nullptr, *p_accf = nullptr, *p_tr[2] = {nullptr, nullptr};
     int pair_ne = 1, pair_warps = 4, pair_prefetch = 6, pair_pf_dist = 0, pair_units_per_wave = 0;
@@ -143,9 +141,7 @@ struct Solver {
     int* d_belems = nullptr;
     int n_belem = 0, overlap = 1;
     double *d_diag_partial = nullptr, *d_diag_res = nullptr;   // device-side diagnostics (diag.cuh), allocated on first use
-    int num_sms = 148, tma_blocks_per_sm = 0;
-    int use_graph = 0;
-    int pf_blocks = -1;   // L2 prefetch distance of the fused stage kernel, in thread blocks
+    int num_sms = 148;
     std::vector<void*> allocs;
 };
 

@@ -23,6 +23,7 @@
 #pragma once
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "btp_kernels.cuh"
 
@@ -96,6 +97,12 @@ struct PairArgs {
     //   part 2: every element that has no processor face (warps of the others leave once their header has arrived)
     int part, count;
     const int* elist;
+    // rhs_only: evaluate create_rhs_btp of the state in the records (mod_rhs_btp.F90:28-59) into rhs_out[3][npoin] and
+    // change nothing else -- no running sums, no update, no traces (per-phase test entry hnumo_rhs_btp)
+    int rhs_only;
+    double* rhs_out;
+    size_t rhs_stride;
+    int configure_only;   // host: set the per-device function attributes and return (hnumo_init, before any graph capture)
 };
 
 // shared-memory vector of NE doubles
@@ -295,6 +302,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
         rec[c] = a.rec + (size_t)e[c] * R::REC;
     }
     constexpr bool botfr = BOTFR != 0;
+    if (a.rhs_only) { PR_FORC ok[c] = false; }   // ok guards every store and running sum
 
     // ---- 1. nodal loads + nodal sums (mod_rk_mlswe.F90:90-92)
     double pbp[NE], pv[NE], bd[4][NE];   // kept by lane I < NP for the LDG flux variable and the update
@@ -858,6 +866,10 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
         PR_FORC {
             double rr[3] = {mi[c] * r0[c], mi[c] * r1[c], mi[c] * r2[c]};
             if (VISC) { rr[1] = rr[1] + a.visc * mi[c] * l0[c]; rr[2] = rr[2] + a.visc * mi[c] * l1[c]; }
+            if (a.rhs_only && unit * NE + c < a.count) {   // (part 0 only)
+                double* ro = a.rhs_out + (size_t)e[c] * NP + I;
+                ro[0] = rr[0]; ro[a.rhs_stride] = rr[1]; ro[2 * a.rhs_stride] = rr[2];
+            }
             const double q1[3] = {q1a[c], q1b[c], q1c[c]};
             double qn[3];
 #pragma unroll
@@ -1089,21 +1101,32 @@ static int launch_pair_k(Solver& S, const PairArgs& a) {
     using R = PairRec<G, Q>;
     const size_t smem = R::smem_bytes(NE, BLK ? 1 : W);
     auto kern = k_btp_stage_pair<G, Q, NE, W, VISC, BOTFR, BLK>;
-    static bool configured = false;
-    static int units_per_wave = 0;
-    if (!configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            set_error("cudaFuncSetAttribute", "shared memory opt-in failed"); return -1;
+    // function attributes are per device: one configuration record per (instantiation, device), set up under a lock
+    // (several Solvers on different GPUs, or the threaded in-process ranks of the tests, may arrive here together)
+    constexpr int MAXDEV = 64;
+    static std::mutex mtx;
+    static bool configured[MAXDEV] = {};
+    static int upw[MAXDEV] = {};
+    const int dv = (S.device >= 0 && S.device < MAXDEV) ? S.device : 0;
+    int units_per_wave;
+    {
+        std::lock_guard<std::mutex> lk(mtx);
+        if (!configured[dv]) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+                set_error("cudaFuncSetAttribute", "shared memory opt-in failed"); return -1;
+            }
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * W, smem);
+            upw[dv] = nb * (BLK ? 1 : W) * S.num_sms;
+            configured[dv] = true;
+            if (getenv("HNUMO_DEBUG"))
+                fprintf(stderr, "[hnumo] device %d element-record stage kernel G=%d NE=%d W=%d blk=%d visc=%d botfr=%d: %zu B smem/block, %d blocks/SM (%d warps)\n",
+                        dv, G, NE, W, (int)BLK, (int)VISC, BOTFR, smem, nb, nb * W);
         }
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        configured = true;
-        int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * W, smem);
-        units_per_wave = nb * (BLK ? 1 : W) * S.num_sms;
-        if (getenv("HNUMO_DEBUG"))
-            fprintf(stderr, "[hnumo] element-record stage kernel G=%d NE=%d W=%d blk=%d visc=%d botfr=%d: %zu B smem/block, %d blocks/SM (%d warps)\n", G, NE, W,
-                    (int)BLK, (int)VISC, BOTFR, smem, nb, nb * W);
+        units_per_wave = upw[dv];
     }
+    if (a.configure_only) return 0;
     PairArgs b = a;
     // L2 prefetch distance in units (warps, or blocks in block-per-element mode): a quarter / half of the resident wave
     // (measured: 296-1480 units are equivalent at nop 4, 185-370 blocks best at nop 8; profiles/r1_stage_kernel_experiments.md)
@@ -1130,9 +1153,9 @@ static int launch_pair_w(Solver& S, const PairArgs& a) {
 }
 template <int G, int Q>
 static int launch_pair_t(Solver& S, const PairArgs& a) {
-    if (S.pair_ne == 1) return launch_pair_w<G, Q, 1, 4>(S, a);
-    if (S.pair_warps == 3) return launch_pair_w<G, Q, 2, 3>(S, a);
-    return launch_pair_w<G, Q, 2, 4>(S, a);
+    // (NE = 2, two elements per warp with double2 shared-memory words, was measured slower at every size -- half the
+    //  resident warps -- and is no longer instantiated; the kernel source keeps the NE parameter)
+    return launch_pair_w<G, Q, 1, 4>(S, a);
 }
 inline int launch_stage_pair(Solver& S, const PairArgs& a) {
     if (S.ngl == 5 && S.nq == 9) return launch_pair_t<5, 9>(S, a);
