@@ -526,6 +526,7 @@ int btp_bcl_coeffs(Solver& S, const Planes& qprime, const Planes& dpv) {
     return 0;
 }
 
+static int phase_check(Solver& S, const char* phase);
 // q_in: layer state before the step; q_out: receives the new thickness planes (may be the same planes)
 static int layer_mass_and_consistency(Solver& S, const Planes& qprime, const Planes& q_in, Planes& q) {
     // layer_mass_rhs + update of q_df(1) (mod_splitting.F90:58-78 / 217-232)
@@ -567,6 +568,7 @@ static int momentum_update(Solver& S, const Planes& qprime_in, const Planes& dpv
         size_t sm = (sops_doubles_host(S.ngl, S.nq) + 8 * S.npts + 8 * S.ngl) * sizeof(double);
         HN_LAUNCH_GQL(k_bcl_laplacian, S, sm, l);
         S.n_launches++;
+        if (phase_check(S, "k_bcl_laplacian")) return -1;
     }
     MomVolArgs v; memset(&v, 0, sizeof(v));
     v.M = S.mesh; v.qprime = qprime_in.p; v.q = q_in.p; v.nstride = q.stride;
@@ -578,6 +580,7 @@ static int momentum_update(Solver& S, const Planes& qprime_in, const Planes& dpv
     size_t sm = (sops_doubles_host(S.ngl, S.nq) + 5 * S.npts + 6 * per + 6 * S.nq2 + 4 * per + 2 * S.npts) * sizeof(double);
     HN_LAUNCH_GQL(k_mom_volume, S, sm, v);
     S.n_launches++;
+    if (phase_check(S, "k_mom_volume")) return -1;
     MomFaceArgs f; memset(&f, 0, sizeof(f));
     f.M = S.mesh; f.qprime = qprime_in.p; f.q_in = q_in.p; f.q = q.p; f.qprime_out = qprime_out.p; f.nstride = q.stride; f.hq = S.h_q.p; f.hstride = S.h_q.stride;
     for (int i = 0; i < 3; ++i) f.qb[i] = qb[i];
@@ -597,6 +600,18 @@ static void dcopy(Solver& S, double* dst, const double* src, size_t n) {
     cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
 }
 
+// HNUMO_DEBUG_SYNC=1: synchronise after every phase of a step and name the phase that failed (bisecting aid)
+static int phase_check(Solver& S, const char* phase) {
+    static const bool on = getenv("HNUMO_DEBUG_SYNC") != nullptr;
+    if (!on) return 0;
+    cudaError_t e = cudaStreamSynchronize(S.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(S.comm_stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error(phase, cudaGetErrorString(e)); fprintf(stderr, "[hnumo] phase %s: %s\n", phase, cudaGetErrorString(e)); return -1; }
+    return 0;
+}
+#define HN_PHASE(call, name) do { if (call) return -1; if (phase_check(S, name)) return -1; } while (0)
+
 // ti_rk_bcl (ti_rk_bcl.F90:9-87).  The reference works on copies (qb_df_pred, q_df_pred, dpprime_visc ...); here the
 // kernels read one set of planes and write another, so that of the reference's array copies only one remains.
 int bcl_step(Solver& S) {
@@ -606,22 +621,22 @@ int bcl_step(Solver& S) {
     cudaEventRecord(e_start, S.stream);
     // ---- prediction: qbp <- substeps(qb), q2 <- layer update of q, qprime2 <- new primes
     Planes dpv1; dpv1.p = S.qprime.p; dpv1.stride = S.qprime.stride; dpv1.n = S.nl;   // dpprime_visc = qprime_df(1,:,:)
-    if (btp_bcl_coeffs(S, S.qprime, dpv1)) return -1;   // also refreshes the halo copy of qprime traces
-    if (btp_solve(S, S.qb, S.qbp, S.qprime)) return -1;
-    if (layer_mass_and_consistency(S, S.qprime, S.q, S.q2)) return -1;
-    if (momentum_update(S, S.qprime, dpv1, S.q, S.q2, S.qprime2, S.qbp, 1)) return -1;
+    HN_PHASE(btp_bcl_coeffs(S, S.qprime, dpv1), "predictor btp_bcl_coeffs");   // also refreshes the halo copy of qprime traces
+    HN_PHASE(btp_solve(S, S.qb, S.qbp, S.qprime), "predictor btp_solve");
+    HN_PHASE(layer_mass_and_consistency(S, S.qprime, S.q, S.q2), "predictor layer mass + consistency");
+    HN_PHASE(momentum_update(S, S.qprime, dpv1, S.q, S.q2, S.qprime2, S.qbp, 1), "predictor momentum");
     // ---- correction
     k_average<<<nblk(NL3), 256, 0, S.stream>>>(S.qprime2.p, S.qprime2.p, S.qprime.p, NL3);
     S.n_launches++;
     dcopy(S, S.dpv.p, S.qprime2[0], NL1);   // dpprime_visc of the corrector: the averaged thickness, which k_thickness_finish replaces below
-    if (btp_bcl_coeffs(S, S.qprime2, S.dpv)) return -1;
-    if (btp_solve(S, S.qb, S.qb, S.qprime2)) return -1;
-    if (layer_mass_and_consistency(S, S.qprime2, S.q, S.q)) return -1;
+    HN_PHASE(btp_bcl_coeffs(S, S.qprime2, S.dpv), "corrector btp_bcl_coeffs");
+    HN_PHASE(btp_solve(S, S.qb, S.qb, S.qprime2), "corrector btp_solve");
+    HN_PHASE(layer_mass_and_consistency(S, S.qprime2, S.q, S.q), "corrector layer mass + consistency");
     // dpprime of the new thickness -> qprime (in place); qprime2.dp <- average of old and new
     k_thickness_finish<<<nblk(S.npoin), 256, 0, S.stream>>>(S.q[0], S.pbprime_df, S.qprime[0], S.qprime[0], S.qprime2[0], S.nl, S.q.stride, S.npoin);
     S.n_launches++;
-    if (halo_exchange_nodal(S, S.qprime2.p, 3 * S.nl, S.qprime2.stride, S.h_q)) return -1;
-    if (momentum_update(S, S.qprime2, S.dpv, S.q, S.q, S.qprime, S.qb, 0)) return -1;   // writes u', v' of qprime
+    HN_PHASE(halo_exchange_nodal(S, S.qprime2.p, 3 * S.nl, S.qprime2.stride, S.h_q), "corrector thickness");
+    HN_PHASE(momentum_update(S, S.qprime2, S.dpv, S.q, S.q, S.qprime, S.qb, 0), "corrector momentum");   // writes u', v' of qprime
     cudaEventRecord(e_stop, S.stream);
     S.n_steps++;
     HN_CUDA(cudaGetLastError());
@@ -842,7 +857,8 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     S.acc_n = palloc(S, 10, NP); S.acc_q = palloc(S, 8, NQ); S.acc_f = palloc(S, 11, NS);
     S.ave_q = palloc(S, 12, NQ); S.ave_f = palloc(S, 16, NS); S.ave_n = palloc(S, 7, NP);
     S.slmf_q = palloc(S, 2, NQ); S.slmf_f = palloc(S, 2, NS);
-    S.rhs_mom = palloc(S, std::max(3, 2 * nl), NP);   // also the 3-plane scratch of hnumo_rhs_btp S.rhs_visc = palloc(S, 2 * nl, NP);
+    S.rhs_mom = palloc(S, std::max(3, 2 * nl), NP);   // also the 3-plane scratch of hnumo_rhs_btp
+    S.rhs_visc = palloc(S, 2 * nl, NP);
     S.stage_buf = dalloc(S, std::max((size_t)3 * nl * NP, 4 * NP));
     size_t hs = (size_t)std::max(S.nhalo, 1) * S.ngl;
     S.h_q = palloc(S, 3 * nl, hs); S.h_dp = palloc(S, nl, hs); S.h_dpv = palloc(S, nl, hs); S.h_dpg = palloc(S, 4 * nl, hs);
@@ -917,7 +933,8 @@ int hnumo_download_state(hnumo_handle_t h, double* q_df, double* qb_df, double* 
 
 static int check_flag(Solver& S) {
     int flag = 0;
-    if (cudaMemcpyAsync(&flag, S.d_flag, sizeof(int), cudaMemcpyDeviceToHost, S.stream) != cudaSuccess) return -1;
+    { cudaError_t e = cudaMemcpyAsync(&flag, S.d_flag, sizeof(int), cudaMemcpyDeviceToHost, S.stream);
+      if (e != cudaSuccess) { set_error("hnumo_step", cudaGetErrorString(e)); return -1; } }
     if (cudaStreamSynchronize(S.stream) != cudaSuccess) { set_error("hnumo_step", cudaGetErrorString(cudaGetLastError())); return -1; }
     if (flag) { set_error("hnumo_step", "Negative mass in thickness at some points (mod_splitting.F90:74-77)"); return 1; }
     return 0;
