@@ -20,7 +20,7 @@ from . import decks  # noqa: F401
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("HNUMO_LIB_PATH", os.path.join(_HERE, "libhnumo_b200.so"))  # override: instrumented debug builds
-_LIB = None
+_LIBS = {}
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared", "-diag-suppress", "177,550"]
@@ -59,18 +59,20 @@ class Desc(C.Structure):
     ]
 
 
-EXPORTS = ["hnumo_init", "hnumo_finalize", "hnumo_last_error", "hnumo_upload_state", "hnumo_download_state",
+EXPORTS = ["hnumo_init", "hnumo_device_count", "hnumo_finalize", "hnumo_last_error", "hnumo_upload_state", "hnumo_download_state",
            "hnumo_step", "hnumo_ti_rk_bcl", "hnumo_btp_bcl_coeffs", "hnumo_btp_substeps", "hnumo_rhs_btp",
            "hnumo_get_array", "hnumo_diagnostics", "hnumo_snapshot_write", "hnumo_snapshot_info",
            "hnumo_snapshot_read_restart", "hnumo_comm_get_unique_id", "hnumo_comm_init", "hnumo_timing", "hnumo_set_option"]
 
 
-def load_library():
-    global _LIB
-    if _LIB is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError("libhnumo_b200.so is not built (run __graft_entry__.build()); there is no CPU fallback")
-        L = C.CDLL(LIB_PATH)
+def load_library(path=None):
+    """ctypes handle of the library (default: the in-tree build; `path`: another build of the same sources, e.g. the
+    exact-division build profiles/build_exact.sh makes for the parity report)"""
+    path = path or LIB_PATH
+    if path not in _LIBS:
+        if not os.path.exists(path):
+            raise RuntimeError("%s is not built (run __graft_entry__.build()); there is no CPU fallback" % os.path.basename(path))
+        L = C.CDLL(path)
         L.hnumo_last_error.restype = C.c_char_p
         L.hnumo_init.argtypes = [C.POINTER(Desc), C.POINTER(C.c_void_p)]
         L.hnumo_finalize.argtypes = [C.c_void_p]
@@ -94,8 +96,8 @@ def load_library():
         L.hnumo_comm_init.argtypes = [C.c_void_p, C.c_void_p]
         L.hnumo_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.hnumo_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
-        _LIB = L
-    return _LIB
+        _LIBS[path] = L
+    return _LIBS[path]
 
 
 class HnumoError(RuntimeError):
@@ -105,8 +107,8 @@ class HnumoError(RuntimeError):
 class Solver:
     """Device-resident hot path for one partition; mirrors the reference call sequence around ti_rk_bcl."""
 
-    def __init__(self, deck, device=0, variant=0):
-        self.L = load_library()
+    def __init__(self, deck, device=0, variant=0, lib_path=None):
+        self.L = load_library(lib_path)
         self.deck = deck
         self._keep = []
         d = Desc()

@@ -78,7 +78,9 @@ __global__ void k_nodal_to_quad(Mesh M, const double* in, double* out, int mode)
     // A derivative that is pure cancellation noise (flat bottom: |sum| ~ 1e-15 of the sum of |terms|) is the derivative of a
     // constant: store an exact zero, so that the stage kernel's forcing-sparsity flags can skip the field (an element whose
     // grad(z_bot) is round-off otherwise pays two dependent global loads per quadrature point and stage)
+#ifndef HN_NO_GZ_FLUSH   // (the reference-arithmetic build of the parity report keeps the noise: profiles/build_exact.sh)
     if (mode != 0 && fabs(v) <= 1.0e-13 * sabs) v = 0.0;
+#endif
     out[(size_t)e * M.nq2 + tid] = v;
 }
 __global__ void k_recip_guard(const double* in, double* out, size_t n) {
@@ -696,6 +698,12 @@ extern "C" {
 
 const char* hnumo_last_error(void) { return g_err; }
 
+int hnumo_device_count(void) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return ndev;
+}
+
 int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     if (!d || !out) { set_error("hnumo_init", "null argument"); return -2; }
     if (d->abi_version != HNUMO_ABI_VERSION) { set_error("hnumo_init", "ABI version mismatch"); return -2; }
@@ -1127,8 +1135,6 @@ int hnumo_set_option(hnumo_handle_t h, const char* key, double value) {
     HN_ENTER(h);
     if (!strcmp(key, "stage_kernel_variant")) { S.variant = (int)value; return 0; }
     if (!strcmp(key, "use_graph")) { S.use_graph = (int)value; return 0; }
-    if (!strcmp(key, "pair_ne")) { S.pair_ne = (int)value; return 0; }
-    if (!strcmp(key, "pair_warps")) { S.pair_warps = (int)value; return 0; }
     if (!strcmp(key, "pair_prefetch")) { S.pair_prefetch = (int)value; return 0; }
     if (!strcmp(key, "pair_pf_dist")) { S.pair_pf_dist = (int)value; return 0; }
     if (!strcmp(key, "overlap")) { S.overlap = (int)value; return 0; }

@@ -37,6 +37,9 @@ module hnumo_b200_iface
             type(hnumo_desc_t), intent(in) :: desc
             type(c_ptr), intent(out) :: handle
         end function
+        integer(c_int) function hnumo_device_count() bind(C, name="hnumo_device_count")
+            import :: c_int
+        end function
         integer(c_int) function hnumo_finalize(handle) bind(C, name="hnumo_finalize")
             import :: c_int, c_ptr
             type(c_ptr), value :: handle

@@ -22,7 +22,8 @@ contains
 
     subroutine hnumo_b200_setup()
         ! everything ti_rk_bcl reads through `use` (src/ti_rk_bcl.F90:19-28 and the modules below it)
-        use mod_grid, only: nelem, npoin, nface, face
+        use mpi
+        use mod_grid, only: nelem, npoin, nface, face, face_type
         use mod_basis, only: ngl, nq, psiq, dpsiq, wnq, wgl, dpsi
         use mod_input, only: nlayers, kstages, dt, dt_btp, botfr, cd_mlswe, method_visc, visc_mlswe, ad_mlswe
         use mod_constants, only: gravity
@@ -32,10 +33,34 @@ contains
                                N_btp
         use mod_parallel, only: num_nbh, nbh_proc, num_send_recv, nbh_send_recv
         use mod_mpi_utilities, only: irank, numproc
-        type(hnumo_desc_t) :: d
-        integer :: e, f, ierr, ntot
+        integer :: e, f, i, j, iq, ierr, ntot, ndev, local_rank, node_comm
+        integer(c_int) :: rc
+        real(c_double) :: tol, ref
         character(kind=c_char) :: id(128)
-        include 'mpif.h'
+
+        ! The library takes ONE metric set per element and ONE normal / edge Jacobian per face (affine bricks, conforming
+        ! faces; include/hnumo_b200.h).  Refuse anything else instead of integrating it wrongly: curved or gmsh quads have
+        ! per-point metrics, AMR meshes have non-conforming faces (face_type 21/12, src/mod_grid.F90:79).
+        do f = 1, nface
+            if (face_type(f) /= 1 .and. face_type(f) /= 2) stop "hnumo_b200: non-conforming or unknown face_type (only 1, 2)"
+            do iq = 2, nq
+                if (maxval(abs(normal_vector_q(1:2,iq,1,f) - normal_vector_q(1:2,1,1,f))) > 1.0e-12) &
+                    stop "hnumo_b200: face normal varies along a face (curved mesh): not supported"
+                if (abs(jac_faceq(iq,1,f)/wnq(iq) - jac_faceq(1,1,f)/wnq(1)) > 1.0e-10*abs(jac_faceq(1,1,f)/wnq(1))) &
+                    stop "hnumo_b200: edge Jacobian varies along a face (curved mesh): not supported"
+            end do
+        end do
+        do e = 1, nelem
+            ref = abs(ksiq_x(1,1,1,e)) + abs(ksiq_y(1,1,1,e)) + abs(etaq_x(1,1,1,e)) + abs(etaq_y(1,1,1,e))
+            tol = 1.0e-10*ref
+            do j = 1, nq
+                do i = 1, nq
+                    if (abs(ksiq_x(i,j,1,e) - ksiq_x(1,1,1,e)) > tol .or. abs(ksiq_y(i,j,1,e) - ksiq_y(1,1,1,e)) > tol .or. &
+                        abs(etaq_x(i,j,1,e) - etaq_x(1,1,1,e)) > tol .or. abs(etaq_y(i,j,1,e) - etaq_y(1,1,1,e)) > tol) &
+                        stop "hnumo_b200: metric terms vary inside an element (non-affine element): not supported"
+                end do
+            end do
+        end do
 
         allocate(elem_metrics(5,nelem), face_geom(3,nface), face_c(8,nface), ssprk_a_c(kstages,3))
         do e = 1, nelem      ! bricks are affine: one metric set per element (include/hnumo_b200.h, elem_metrics)
@@ -49,29 +74,28 @@ contains
             face_c(:,f) = int(face(:,f), c_int32_t)
         end do
         ssprk_a_c = ssprk_a(1:kstages,1:3)
-
-        d%abi_version = HNUMO_ABI_VERSION
-        d%nelem = nelem; d%ngl = ngl; d%nq = nq; d%nlayers = nlayers; d%nface = nface
-        d%kstages = kstages; d%N_btp = N_btp; d%dt = dt; d%dt_btp = dt_btp
-        d%botfr = botfr; d%method_visc = method_visc
-        d%gravity = gravity; d%cd_mlswe = cd_mlswe; d%visc_mlswe = visc_mlswe; d%ad_mlswe = ad_mlswe
-        d%psiq = c_loc(psiq); d%dpsiq = c_loc(dpsiq); d%wnq = c_loc(wnq); d%wgl = c_loc(wgl); d%dpsi = c_loc(dpsi)
-        d%face = c_loc(face_c); d%elem_metrics = c_loc(elem_metrics); d%face_geom = c_loc(face_geom)
-        d%pbprime_df = c_loc(pbprime_df); d%massinv = c_loc(massinv); d%coriolis_df = c_loc(coriolis_df)
-        d%tau_wind_df = c_loc(tau_wind_df); d%zbot_df = c_loc(zbot_df); d%alpha_mlswe = c_loc(alpha_mlswe)
-        d%ssprk_a = c_loc(ssprk_a_c); d%ssprk_beta = c_loc(ssprk_beta)
-        d%rank = irank; d%nranks = numproc; d%num_nbh = num_nbh
-        d%nbh_proc = c_null_ptr; d%num_send_recv = c_null_ptr; d%nbh_send_recv = c_null_ptr
+        ntot = 0
+        if (num_nbh > 0) ntot = sum(num_send_recv(1:num_nbh))
+        allocate(nbh_proc_c(max(num_nbh,1)), num_send_recv_c(max(num_nbh,1)), nbh_send_recv_c(max(ntot,1)))
         if (num_nbh > 0) then
-            ntot = sum(num_send_recv(1:num_nbh))
-            allocate(nbh_proc_c(num_nbh), num_send_recv_c(num_nbh), nbh_send_recv_c(ntot))
-            nbh_proc_c = nbh_proc(1:num_nbh); num_send_recv_c = num_send_recv(1:num_nbh)
-            nbh_send_recv_c = nbh_send_recv(1:ntot)
-            d%nbh_proc = c_loc(nbh_proc_c); d%num_send_recv = c_loc(num_send_recv_c); d%nbh_send_recv = c_loc(nbh_send_recv_c)
+            nbh_proc_c(1:num_nbh) = nbh_proc(1:num_nbh); num_send_recv_c(1:num_nbh) = num_send_recv(1:num_nbh)
+            nbh_send_recv_c(1:ntot) = nbh_send_recv(1:ntot)
         end if
-        d%device = mod(irank, 8) + 1      ! one MPI rank per GPU of the 8-GPU box
-        d%stage_kernel_variant = 0
-        if (hnumo_init(d, handle) /= 0) stop "hnumo_init failed"
+
+        ! GPU of this rank: node-local rank modulo the number of devices of the node
+        call mpi_comm_split_type(mpi_comm_world, MPI_COMM_TYPE_SHARED, 0, MPI_INFO_NULL, node_comm, ierr)
+        call mpi_comm_rank(node_comm, local_rank, ierr)
+        call mpi_comm_free(node_comm, ierr)
+        ndev = hnumo_device_count()
+        if (ndev < 1) stop "hnumo_b200: no CUDA device on this node (the library has no CPU fallback)"
+
+        ! The reference's module arrays are plain allocatables (no TARGET: src/mod_basis.F90:53-55, src/mod_metrics.F90:40-42,
+        ! src/mod_initial.F90:64-79), so c_loc cannot be applied to them here.  They are passed to a contained procedure whose
+        ! dummies are TARGET assumed-size arrays (sequence association); the addresses are taken there and are used only
+        ! during that call -- hnumo_init copies everything it needs and retains no host pointer.
+        call init_with(psiq, dpsiq, wnq, wgl, dpsi, pbprime_df, massinv, coriolis_df, tau_wind_df, zbot_df, alpha_mlswe, &
+                       ssprk_beta, rc)
+        if (rc /= 0) stop "hnumo_init failed"
         if (numproc > 1) then               ! replaces mod_mpi_communicator_create: NCCL id broadcast over MPI
             if (irank == 0) then
                 if (hnumo_comm_get_unique_id(id) /= 0) stop "hnumo_comm_get_unique_id failed"
@@ -79,6 +103,34 @@ contains
             call mpi_bcast(id, 128, MPI_CHARACTER, 0, mpi_comm_world, ierr)
             if (hnumo_comm_init(handle, id) /= 0) stop "hnumo_comm_init failed"
         end if
+
+    contains
+
+        subroutine init_with(psiq_a, dpsiq_a, wnq_a, wgl_a, dpsi_a, pbprime_a, massinv_a, coriolis_a, tauw_a, zbot_a, &
+                             alpha_a, beta_a, rc_out)
+            real(c_double), target, intent(in) :: psiq_a(*), dpsiq_a(*), wnq_a(*), wgl_a(*), dpsi_a(*), pbprime_a(*), &
+                                                  massinv_a(*), coriolis_a(*), tauw_a(*), zbot_a(*), alpha_a(*), beta_a(*)
+            integer(c_int), intent(out) :: rc_out
+            type(hnumo_desc_t) :: d
+            d%abi_version = HNUMO_ABI_VERSION
+            d%nelem = nelem; d%ngl = ngl; d%nq = nq; d%nlayers = nlayers; d%nface = nface
+            d%kstages = kstages; d%N_btp = N_btp; d%dt = dt; d%dt_btp = dt_btp
+            d%botfr = botfr; d%method_visc = method_visc
+            d%gravity = gravity; d%cd_mlswe = cd_mlswe; d%visc_mlswe = visc_mlswe; d%ad_mlswe = ad_mlswe
+            d%psiq = c_loc(psiq_a); d%dpsiq = c_loc(dpsiq_a); d%wnq = c_loc(wnq_a); d%wgl = c_loc(wgl_a); d%dpsi = c_loc(dpsi_a)
+            d%face = c_loc(face_c); d%elem_metrics = c_loc(elem_metrics); d%face_geom = c_loc(face_geom)
+            d%pbprime_df = c_loc(pbprime_a); d%massinv = c_loc(massinv_a); d%coriolis_df = c_loc(coriolis_a)
+            d%tau_wind_df = c_loc(tauw_a); d%zbot_df = c_loc(zbot_a); d%alpha_mlswe = c_loc(alpha_a)
+            d%ssprk_a = c_loc(ssprk_a_c); d%ssprk_beta = c_loc(beta_a)
+            d%rank = irank; d%nranks = numproc; d%num_nbh = num_nbh
+            d%nbh_proc = c_null_ptr; d%num_send_recv = c_null_ptr; d%nbh_send_recv = c_null_ptr
+            if (num_nbh > 0) then
+                d%nbh_proc = c_loc(nbh_proc_c); d%num_send_recv = c_loc(num_send_recv_c); d%nbh_send_recv = c_loc(nbh_send_recv_c)
+            end if
+            d%device = mod(local_rank, ndev) + 1
+            d%stage_kernel_variant = 0
+            rc_out = hnumo_init(d, handle)
+        end subroutine init_with
     end subroutine hnumo_b200_setup
 
     subroutine hnumo_b200_sync_host(q_df, qb_df, qprime_df)

@@ -87,14 +87,17 @@ typedef struct hnumo_desc {
     const int32_t* nbh_send_recv;
     /* 0 = use the current CUDA device */
     int32_t device;
-    /* tuning: 0 = default (warp-per-element fused stage kernel), 1 = simple reference-form kernel (bisecting aid),
-     * 2 = record layout + TMA staging, one output per thread, 3 = record layout + TMA staging, one line per lane */
+    /* 0 = default: element-record stage kernel (one contiguous record per element; one warp per element at nop 3 and 4, one
+     * block of 128 threads per element at nop 5..8; falls back to 1 for other orders or inexact integration),
+     * 1 = simple reference-form kernel (any order; bisecting aid) */
     int32_t stage_kernel_variant;
 } hnumo_desc_t;
 
 /* ---- life cycle ----------------------------------------------------------------------------- */
 /* replaces: module set-up consumed by ti_rk_bcl through `use` (src/ti_rk_bcl.F90:19-28) */
 int hnumo_init(const hnumo_desc_t* desc, hnumo_handle_t* out);
+/* number of CUDA devices this process can use (0 when there is none: the library has no CPU fallback) */
+int hnumo_device_count(void);
 int hnumo_finalize(hnumo_handle_t h);
 const char* hnumo_last_error(void);
 
@@ -120,7 +123,9 @@ int hnumo_btp_substeps(hnumo_handle_t h);
 int hnumo_rhs_btp(hnumo_handle_t h, double* rhs);
 /* copy a named mod_variables work array to the host in the reference's layout; face arrays are indexed by the
  * face numbers of desc->face.  Names: Q_uu_dp Q_uv_dp Q_vv_dp H_bcl Q_uu_dp_edge Q_uv_dp_edge Q_vv_dp_edge
- * H_bcl_edge ope_ave H_ave Qu_ave Qv_ave Quv_ave ope2_ave btp_mass_flux_ave uvb_ave tau_bot_ave ope2_ave_df
+ * H_bcl_edge grad_zbot_quad (note: entries of grad z_bot that are pure differentiation noise, |sum| <= 1e-13 sum|terms|, i.e. the
+ * derivative of a constant, are stored as exact zeros -- the one deliberate deviation from the reference's set-up arithmetic;
+ * build with -DHN_NO_GZ_FLUSH to keep them) ope_ave H_ave Qu_ave Qv_ave Quv_ave ope2_ave btp_mass_flux_ave uvb_ave tau_bot_ave ope2_ave_df
  * uvb_ave_df graduvb_ave uvb_face_ave btp_mass_flux_face_ave ope_face_ave ope2_face_ave H_face_ave Qu_face_ave
  * Qv_face_ave one_plus_eta_edge_2_ave btp_dpp_graduv pbprime_visc.  Returns the element count or <0. */
 int64_t hnumo_get_array(hnumo_handle_t h, const char* name, double* out, int64_t capacity);
@@ -161,7 +166,12 @@ int hnumo_snapshot_read_restart(const char* path, int32_t nlayers, int64_t npoin
  * out[1] = number of barotropic stages, out[2] = GPU ms in whole steps, out[3] = steps,
  * out[4] = kernel launches issued, out[5..7] reserved.  reset != 0 clears the counters after reading. */
 int hnumo_timing(hnumo_handle_t h, double* out8, int32_t reset);
-/* enable (1) / disable (0) CUDA-graph replay of the barotropic substep loop */
+/* tuning switches, all optional (unknown keys are rejected with -2):
+ *   "use_graph"            -1 auto (default) / 0 off / 1 on: CUDA-graph replay of the barotropic substep loop (only taken on
+ *                          partitions without processor faces; bitwise the same result)
+ *   "overlap"              1 (default) / 0: boundary elements + halo exchange on a second stream, overlapped with the interior
+ *   "stage_kernel_variant" as hnumo_desc_t.stage_kernel_variant (effective if the records were allocated at init)
+ *   "pair_prefetch", "pair_pf_dist"   L2 prefetch bits / distance of the stage kernel (sweeps) */
 int hnumo_set_option(hnumo_handle_t h, const char* key, double value);
 
 #ifdef __cplusplus

@@ -102,6 +102,12 @@ struct Oracle {
     Arr coord;                   // (2,npoin)
     std::vector<int> face;       // (8,nface) Fortran 1-based content kept (face(5..8))
     std::vector<int> fnodeL, fnodeR;  // (ngl,nface) 0-based global node of imapl/imapr
+    // Threading aid (not in the reference): the faces of every element in ascending face number, side 0 = the element is
+    // the face's left element, 1 = right.  The reference scatters face by face into the nodes of both elements; the
+    // threaded loops evaluate the faces in parallel and then gather per element in the same face order, so every node
+    // receives the same additions in the same order -> bit-identical to the serial face loop.
+    std::vector<int> ef_ptr, ef_face, ef_side;
+    void build_elem_faces();
     // metrics
     Arr ksi_x, ksi_y, eta_x, eta_y, jac;         // (npoin)
     Arr ksiq_x, ksiq_y, etaq_x, etaq_y, jacq;    // (npoin_q)

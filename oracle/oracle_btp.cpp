@@ -101,13 +101,36 @@ void Oracle::create_rhs_btp_volume_qdf(Arr& rhs, const Arr& qb, const Arr& qprim
     }
 }
 
-// mod_rhs_btp.F90:211-370
-void Oracle::creat_btp_fluxes_qdf(Arr& rhs, const Arr& qb_df_face) {
-    std::vector<double> quu(nq), quv(nq), qvu(nq), qvv(nq), H_face_temp(nq), flux_edge_x(nq), flux_edge_y(nq);
-    std::vector<double> ul(nq), ur(nq), vl(nq), vr(nq), pbl(nq), pbr(nq), one_plus_eta_edge(nq);
-    Arr qbl, qbr; qbl.alloc(4, nq); qbr.alloc(4, nq);
+void Oracle::build_elem_faces() {
+    ef_ptr.assign(nelem + 1, 0);
     for (int f = 0; f < nface; ++f) {
-        int er = face[8 * f + 7];
+        ef_ptr[face[8 * f + 6]]++;                       // left element (1-based -> slot el+1)
+        if (face[8 * f + 7] > 0) ef_ptr[face[8 * f + 7]]++;
+    }
+    for (int e = 0; e < nelem; ++e) ef_ptr[e + 1] += ef_ptr[e];
+    ef_face.assign(ef_ptr[nelem], 0); ef_side.assign(ef_ptr[nelem], 0);
+    std::vector<int> fill(ef_ptr.begin(), ef_ptr.end() - 1);
+    for (int f = 0; f < nface; ++f) {                     // ascending f: every element's list ends up sorted by face number
+        int el = face[8 * f + 6] - 1, er = face[8 * f + 7];
+        ef_face[fill[el]] = f; ef_side[fill[el]++] = 0;
+        if (er > 0) { ef_face[fill[er - 1]] = f; ef_side[fill[er - 1]++] = 1; }
+    }
+}
+
+// mod_rhs_btp.F90:211-370.  Threaded as: (A) every face evaluated independently (its running sums are per face),
+// (B) scatter of the reference gathered per element in the reference's face order (see ef_ptr in the header).
+void Oracle::creat_btp_fluxes_qdf(Arr& rhs, const Arr& qb_df_face) {
+    if (ef_ptr.empty()) build_elem_faces();
+    static thread_local std::vector<double> quu, quv, qvu, qvv, H_face_temp, flux_edge_x, flux_edge_y, ul, ur, vl, vr, pbl, pbr, one_plus_eta_edge;
+    Arr fl3; fl3.alloc(3, nq, nface);   // flux, H_kx + flux_x, H_ky + flux_y at the face quadrature points
+#pragma omp parallel
+    {
+    quu.assign(nq, 0); quv.assign(nq, 0); qvu.assign(nq, 0); qvv.assign(nq, 0); H_face_temp.assign(nq, 0); flux_edge_x.assign(nq, 0);
+    flux_edge_y.assign(nq, 0); ul.assign(nq, 0); ur.assign(nq, 0); vl.assign(nq, 0); vr.assign(nq, 0); pbl.assign(nq, 0); pbr.assign(nq, 0);
+    one_plus_eta_edge.assign(nq, 0);
+    Arr qbl, qbr; qbl.alloc(4, nq); qbr.alloc(4, nq);
+#pragma omp for schedule(static)
+    for (int f = 0; f < nface; ++f) {
         qbl.zero(); qbr.zero();
         std::fill(pbl.begin(), pbl.end(), 0.0); std::fill(pbr.begin(), pbr.end(), 0.0);
         for (int iq = 0; iq < nq; ++iq) {
@@ -154,7 +177,6 @@ void Oracle::creat_btp_fluxes_qdf(Arr& rhs, const Arr& qb_df_face) {
             uvb_face_ave(1, 0, iq, f) += vl[iq]; uvb_face_ave(1, 1, iq, f) += vr[iq];
         }
         for (int iq = 0; iq < nq; ++iq) {
-            double wq = jac_faceq(iq, f);
             double nxl = normal_vector_q(0, iq, f), nyl = normal_vector_q(1, iq, f);
             double H_kx = nxl * H_face_temp[iq], H_ky = nyl * H_face_temp[iq];
             double lamb = coeff_mass_pbpert_LR(iq, f);
@@ -163,26 +185,39 @@ void Oracle::creat_btp_fluxes_qdf(Arr& rhs, const Arr& qb_df_face) {
             double flux_x = nxl * quu[iq] + nyl * quv[iq] - dispu;
             double flux_y = nxl * qvu[iq] + nyl * qvv[iq] - dispv;
             double flux = nxl * flux_edge_x[iq] + nyl * flux_edge_y[iq];
-            for (int n = 0; n < ngl; ++n) {
-                double hi = psiq(n, iq);
-                int I = fnodeL[(size_t)f * ngl + n];
-                rhs(0, I) = rhs(0, I) - wq * hi * flux;
-                rhs(1, I) = rhs(1, I) - wq * hi * (H_kx + flux_x);
-                rhs(2, I) = rhs(2, I) - wq * hi * (H_ky + flux_y);
-                if (er > 0) {
-                    int Ir = fnodeR[(size_t)f * ngl + n];
-                    rhs(0, Ir) = rhs(0, Ir) + wq * hi * flux;
-                    rhs(1, Ir) = rhs(1, Ir) + wq * hi * (H_kx + flux_x);
-                    rhs(2, Ir) = rhs(2, Ir) + wq * hi * (H_ky + flux_y);
+            fl3(0, iq, f) = flux; fl3(1, iq, f) = H_kx + flux_x; fl3(2, iq, f) = H_ky + flux_y;
+        }
+    }
+    // (B) the reference's scatter `rhs(:,il) -= wq*hi*(...)`, `rhs(:,ir) += ...` (mod_rhs_btp.F90:332-366), per element
+#pragma omp for schedule(static)
+    for (int e = 0; e < nelem; ++e)
+        for (int t = ef_ptr[e]; t < ef_ptr[e + 1]; ++t) {
+            const int f = ef_face[t], side = ef_side[t];
+            const std::vector<int>& fn = side ? fnodeR : fnodeL;
+            for (int iq = 0; iq < nq; ++iq) {
+                double wq = jac_faceq(iq, f);
+                double flux = fl3(0, iq, f), fx = fl3(1, iq, f), fy = fl3(2, iq, f);
+                for (int n = 0; n < ngl; ++n) {
+                    double hi = psiq(n, iq);
+                    int I = fn[(size_t)f * ngl + n];
+                    if (side == 0) {
+                        rhs(0, I) = rhs(0, I) - wq * hi * flux;
+                        rhs(1, I) = rhs(1, I) - wq * hi * fx;
+                        rhs(2, I) = rhs(2, I) - wq * hi * fy;
+                    } else {
+                        rhs(0, I) = rhs(0, I) + wq * hi * flux;
+                        rhs(1, I) = rhs(1, I) + wq * hi * fx;
+                        rhs(2, I) = rhs(2, I) + wq * hi * fy;
+                    }
                 }
             }
         }
-    }
-#pragma omp parallel for schedule(static)
+#pragma omp for schedule(static)
     for (int I = 0; I < npoin; ++I) {
         rhs(0, I) = massinv(I) * rhs(0, I);
         rhs(1, I) = massinv(I) * rhs(1, I);
         rhs(2, I) = massinv(I) * rhs(2, I);
+    }
     }
 }
 
@@ -206,9 +241,13 @@ void Oracle::btp_create_laplacian(Arr& rhs_lap, const Arr& qb) {
     Arr Uk; Uk.alloc(2, npoin);
     Arr graduv; graduv.alloc(4, npoin);
     Arr graduv_face; graduv_face.alloc(4, 2, ngl, nface);
+    if (ef_ptr.empty()) build_elem_faces();
+#pragma omp parallel for schedule(static)
     for (int I = 0; I < npoin; ++I) { Uk(0, I) = qb(2, I) / qb(0, I); Uk(1, I) = qb(3, I) / qb(0, I); }
     compute_gradient_uv(graduv, Uk.data(), 2);
+#pragma omp parallel for schedule(static)
     for (size_t i = 0; i < graduvb_ave.size(); ++i) graduvb_ave.v[i] += graduv.v[i];
+#pragma omp parallel for schedule(static)
     for (int f = 0; f < nface; ++f) {
         int ier = face[8 * f + 7];
         for (int n = 0; n < ngl; ++n) {
@@ -245,11 +284,14 @@ void Oracle::btp_create_laplacian(Arr& rhs_lap, const Arr& qb) {
                 rhs_lap(1, I) = rhs_lap(1, I) - wq * (dpsidx_df(ip, Iq) * qq[2] + dpsidy_df(ip, Iq) * qq[3]);
             }
         }
+#pragma omp parallel for schedule(static)
     for (size_t i = 0; i < graduvb_face_ave.size(); ++i) graduvb_face_ave.v[i] += graduv_face.v[i];
-    // create_rhs_laplacian_flux (as-written flux form, hazard 2)
+    // create_rhs_laplacian_flux (as-written flux form, hazard 2): faces in parallel, then the reference's scatter gathered
+    // per element in the reference's face order
     const double beta = 0.5, alpha = 1.0 - beta;
-    for (int f = 0; f < nface; ++f) {
-        int ier = face[8 * f + 7];
+    Arr lfl; lfl.alloc(2, ngl, nface);
+#pragma omp parallel for schedule(static)
+    for (int f = 0; f < nface; ++f)
         for (int iq = 0; iq < ngl; ++iq) {
             double fv[4][2];
             for (int v = 0; v < 4; ++v) {
@@ -259,22 +301,30 @@ void Oracle::btp_create_laplacian(Arr& rhs_lap, const Arr& qb) {
             double nx = normal_vector(0, iq, f), ny = normal_vector(1, iq, f);
             double qu_mean0 = alpha * fv[0][0] + beta * fv[0][1], qu_mean1 = alpha * fv[1][0] + beta * fv[1][1];
             double qv_mean0 = alpha * fv[2][0] + beta * fv[2][1], qv_mean1 = alpha * fv[3][0] + beta * fv[3][1];
-            double wq = jac_face(iq, f);
-            double flux_qu = (qu_mean0 - fv[0][0] * nx) + (qu_mean1 - fv[1][0] * ny);
-            double flux_qv = (qv_mean0 - fv[2][0] * nx) + (qv_mean1 - fv[3][0] * ny);
-            for (int i = 0; i < ngl; ++i) {
-                double hi = psi(i, iq);
-                int ip = fnodeL[(size_t)f * ngl + i];
-                rhs_lap(0, ip) = rhs_lap(0, ip) + wq * hi * flux_qu;
-                rhs_lap(1, ip) = rhs_lap(1, ip) + wq * hi * flux_qv;
-                if (ier > 0) {
-                    int ipr = fnodeR[(size_t)f * ngl + i];
-                    rhs_lap(0, ipr) = rhs_lap(0, ipr) - wq * hi * flux_qu;
-                    rhs_lap(1, ipr) = rhs_lap(1, ipr) - wq * hi * flux_qv;
+            lfl(0, iq, f) = (qu_mean0 - fv[0][0] * nx) + (qu_mean1 - fv[1][0] * ny);
+            lfl(1, iq, f) = (qv_mean0 - fv[2][0] * nx) + (qv_mean1 - fv[3][0] * ny);
+        }
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < nelem; ++e)
+        for (int t = ef_ptr[e]; t < ef_ptr[e + 1]; ++t) {
+            const int f = ef_face[t], side = ef_side[t];
+            const std::vector<int>& fn = side ? fnodeR : fnodeL;
+            for (int iq = 0; iq < ngl; ++iq) {
+                double wq = jac_face(iq, f), flux_qu = lfl(0, iq, f), flux_qv = lfl(1, iq, f);
+                for (int i = 0; i < ngl; ++i) {
+                    double hi = psi(i, iq);
+                    int ip = fn[(size_t)f * ngl + i];
+                    if (side == 0) {
+                        rhs_lap(0, ip) = rhs_lap(0, ip) + wq * hi * flux_qu;
+                        rhs_lap(1, ip) = rhs_lap(1, ip) + wq * hi * flux_qv;
+                    } else {
+                        rhs_lap(0, ip) = rhs_lap(0, ip) - wq * hi * flux_qu;
+                        rhs_lap(1, ip) = rhs_lap(1, ip) - wq * hi * flux_qv;
+                    }
                 }
             }
         }
-    }
+#pragma omp parallel for schedule(static)
     for (int I = 0; I < npoin; ++I) {
         rhs_lap(0, I) = cfg.visc_mlswe * massinv(I) * rhs_lap(0, I);
         rhs_lap(1, I) = cfg.visc_mlswe * massinv(I) * rhs_lap(1, I);
@@ -289,6 +339,7 @@ void Oracle::create_rhs_btp(Arr& rhs, const Arr& qb, const Arr& qprime) {
     create_rhs_btp_volume_qdf(rhs, qb, qprime);
     creat_btp_fluxes_qdf(rhs, qb_df_face);
     btp_create_laplacian(rhs_visc_btp, qb);  // method_visc != 1
+#pragma omp parallel for schedule(static)
     for (int I = 0; I < npoin; ++I) {
         rhs(1, I) = rhs(1, I) + rhs_visc_btp(0, I);
         rhs(2, I) = rhs(2, I) + rhs_visc_btp(1, I);
@@ -316,6 +367,14 @@ void Oracle::btp_mom_boundary_df(Arr& qb) {
     }
 }
 
+// threaded array assignment (the reference's whole-array `qb1 = qb`)
+static void pcopy(Arr& dst, const Arr& src) {
+    if (dst.size() != src.size()) { dst = src; return; }
+    const size_t n = src.size();
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; ++i) dst.v[i] = src.v[i];
+}
+
 // mod_rk_mlswe.F90:19-151
 void Oracle::ti_barotropic_ssprk_mlswe(Arr& qb, const Arr& qprime) {
     auto t0 = std::chrono::steady_clock::now();
@@ -327,11 +386,12 @@ void Oracle::ti_barotropic_ssprk_mlswe(Arr& qb, const Arr& qprime) {
     graduvb_face_ave.zero(); graduvb_ave.zero();
 
     Arr rhs; rhs.alloc(3, npoin);
-    Arr qb0, qb1, qb2; qb2.alloc(4, npoin);
+    Arr qb0, qb1, qb2; qb2.alloc(4, npoin); qb0.alloc(4, npoin); qb1.alloc(4, npoin);
     for (int mstep = 1; mstep <= N_btp; ++mstep) {
-        qb0 = qb; qb1 = qb;
+        pcopy(qb0, qb); pcopy(qb1, qb);
         for (int ik = 1; ik <= kstages; ++ik) {
             double dtt = dt_btp * ssprk_beta(ik - 1);
+#pragma omp parallel for schedule(static)
             for (int I = 0; I < npoin; ++I) {
                 double t = 1.0 + qb1(1, I) * one_over_pbprime_df(I);
                 ope2_ave_df(I) = ope2_ave_df(I) + t * t;
@@ -349,8 +409,8 @@ void Oracle::ti_barotropic_ssprk_mlswe(Arr& qb, const Arr& qprime) {
                 qb(0, I) = qb(1, I) + pbprime_df(I);
             }
             btp_mom_boundary_df(qb);
-            qb1 = qb;
-            if (kstages == 5 && ik == 2) qb2 = qb;
+            pcopy(qb1, qb);
+            if (kstages == 5 && ik == 2) pcopy(qb2, qb);
         }
         for (size_t i = 0; i < tau_wind_ave.size(); ++i) tau_wind_ave.v[i] += tau_wind.v[i];
     }

@@ -4,6 +4,7 @@
 // cpu_baseline / --impl reference legs; never by the product).
 // ============================================================================
 #include <cstring>
+#include <omp.h>
 
 #include "hnumo_oracle.hpp"
 
@@ -12,6 +13,9 @@ using orc::Oracle;
 
 extern "C" {
 
+// OpenMP team size of every later call (the launcher's OMP_NUM_THREADS is only the default)
+void orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int orc_get_max_threads(void) { return omp_get_max_threads(); }
 void* orc_create(const orc::Config* cfg) { return new Oracle(*cfg); }
 void orc_destroy(void* h) { delete (Oracle*)h; }
 

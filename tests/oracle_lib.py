@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
-_LIB = None
+_LIBS = {}
 
 TEST_CASES = {"bump": 0, "lakeAtrest": 1, "double-gyre": 2, "double-gyre-synth": 3}
 
@@ -31,17 +31,29 @@ class Config(C.Structure):
     ]
 
 
-def build(force=False):
-    so = os.path.join(_ORACLE_DIR, "liboracle.so")
-    if force or not os.path.exists(so):
-        subprocess.check_call(["make", "-C", _ORACLE_DIR, "-B"], stdout=subprocess.DEVNULL)
+def build(force=False, variant=""):
+    """variant "" = the oracle proper; "fma" = the same sources compiled with FP contraction (oracle/Makefile)"""
+    so = os.path.join(_ORACLE_DIR, "liboracle%s.so" % ("_" + variant if variant else ""))
+    srcs = [os.path.join(_ORACLE_DIR, f) for f in os.listdir(_ORACLE_DIR) if f.endswith((".cpp", ".hpp"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in srcs):
+        subprocess.check_call(["make", "-C", _ORACLE_DIR, "-B", os.path.basename(so)], stdout=subprocess.DEVNULL)
     return so
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
-        L = C.CDLL(build())
+def set_threads(n):
+    """OpenMP threads of the oracle from now on (torchrun exports OMP_NUM_THREADS=1; bench.py sets the count explicitly)"""
+    lib().orc_set_threads(int(n))
+
+
+def max_threads():
+    return int(lib().orc_get_max_threads())
+
+
+def lib(variant=""):
+    if variant not in _LIBS:
+        L = C.CDLL(build(variant=variant))
+        L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_get_max_threads.restype = C.c_int
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.POINTER(Config)]
         L.orc_destroy.argtypes = [C.c_void_p]
@@ -57,8 +69,8 @@ def lib():
         L.orc_rhs_btp.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_btp_substeps.argtypes = [C.c_void_p]
         L.orc_diagnostics.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-        _LIB = L
-    return _LIB
+        _LIBS[variant] = L
+    return _LIBS[variant]
 
 
 def make_config(deck):
@@ -88,8 +100,8 @@ def make_config(deck):
 
 
 class Oracle:
-    def __init__(self, deck):
-        self.L = lib()
+    def __init__(self, deck, variant=""):
+        self.L = lib(variant)
         self.cfg = make_config(deck)
         self.h = self.L.orc_create(C.byref(self.cfg))
         info = (C.c_int * 10)()

@@ -313,3 +313,20 @@ def test_snapshot_is_readable_by_the_reference_loader(tmp_path):
         assert np.allclose(u[k], 0.01, rtol=1e-14) and np.allclose(v[k], -0.02, rtol=1e-14)
     assert np.allclose(z[nk], deck["zbot_df"], rtol=1e-15)
     assert np.allclose(z[0], deck["zbot_df"] + sum(al[k] / g * q[k, :, 0] for k in range(nk)), rtol=1e-14, atol=1e-12)
+
+
+def test_c_harness_builds_and_fails_loudly_without_a_gpu(hn, hn_lib, tmp_path):
+    """tests/c_abi_harness.c is a plain-C caller of the C-ABI (no Python, no CUDA headers).  It links against the library and,
+    on a box without a GPU, stops at hnumo_init with the library's own message: there is no CPU fallback behind the boundary."""
+    import subprocess
+    import torch
+    import harness_util
+    exe = harness_util.build_harness()
+    deck = hn.decks.build_deck(dict(hn.decks.SHIPPED["bump"], nelx=3, nely=3))
+    deck_file, out_file = str(tmp_path / "deck.bin"), str(tmp_path / "out.bin")
+    harness_util.write_deck(deck_file, deck)
+    r = subprocess.run([exe, deck_file, out_file, "1"], capture_output=True, text=True, timeout=300)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, (r.stdout, r.stderr)
+    else:
+        assert r.returncode == 3 and "no CUDA device" in r.stderr, (r.returncode, r.stderr)
