@@ -848,17 +848,32 @@ __global__ void k_average(double* out, const double* x, const double* y, size_t 
     if (i < n) out[i] = 0.5 * (x[i] + y[i]);
 }
 // thickness epilogue (mod_splitting.F90:83-87, ti_rk_bcl.F90:78-79): dpprime2 = q_dp/ope ; qprime2.dp = 0.5*(qprime.dp + dpprime2)
-__global__ void k_thickness_finish(const double* qdp, const double* pbprime_df, const double* qprime_dp, double* dpprime2,
-                                   double* qprime2_dp, int nl, size_t nstride, size_t npoin) {
+// (dpprime2 may be the same planes as qprime_dp: every point reads its old value before it writes the new one, and no
+//  point touches another point's entries -- the __restrict__ qualifiers only tell the compiler that the loads of one layer
+//  need not wait for the stores of the previous one)
+__global__ void k_thickness_finish(const double* __restrict__ qdp, const double* __restrict__ pbprime_df, const double* __restrict__ qprime_dp,
+                                   double* __restrict__ dpprime2, double* __restrict__ qprime2_dp, int nl, size_t nstride, size_t npoin) {
     size_t I = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (I >= npoin) return;
     double s = 0.0;
     for (int k = 0; k < nl; ++k) s += qdp[(size_t)k * nstride + I];
     double ope = s / pbprime_df[I];
-    for (int k = 0; k < nl; ++k) {
-        const double d = qdp[(size_t)k * nstride + I] / ope, old = qprime_dp[(size_t)k * nstride + I];   // (dpprime2 may alias qprime_dp)
-        dpprime2[(size_t)k * nstride + I] = d;
-        qprime2_dp[(size_t)k * nstride + I] = 0.5 * (old + d);
+    // four layers at a time: all loads of the group are issued before its first store
+    for (int k0 = 0; k0 < nl; k0 += 4) {
+        double qd[4], old[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = min(k0 + j, nl - 1);
+            qd[j] = qdp[(size_t)k * nstride + I]; old[j] = qprime_dp[(size_t)k * nstride + I];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (k0 + j < nl) {
+                const double d = qd[j] / ope;
+                dpprime2[(size_t)(k0 + j) * nstride + I] = d;
+                qprime2_dp[(size_t)(k0 + j) * nstride + I] = 0.5 * (old[j] + d);
+            }
+        }
     }
 }
 

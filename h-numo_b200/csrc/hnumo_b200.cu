@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "bcl_kernels.cuh"
+#include "layer_warp.cuh"
 #include "btp_kernels.cuh"
 #include "halo.cuh"
 #include "stage_pair.cuh"
@@ -46,6 +47,24 @@ static bool use_pair(const Solver& S) { return S.variant == 0 && S.p_rec != null
         else if ((S).ngl == 5 && (S).nq == 9) kern<5, 9, 0><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args);                \
         else if ((S).ngl == 4 && (S).nq == 7) kern<4, 7, 0><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args);                \
         else { smem_opt_in(kern<0, 0, 0>, smem); kern<0, 0, 0><<<(S).nelem, threads_for(S), smem, (S).stream>>>(args); } \
+    } while (0)
+
+// warp-per-element layer kernels (layer_warp.cuh): nop 3 and 4, layer count compile-time for 2 and 3
+// S.layer_warp is a bit mask: 1 coeffs, 2 layer mass, 4 consistency, 8 laplacian, 16 momentum volume, 32 momentum faces + update
+static bool use_layer_warp(const Solver& S, int bit) { return (S.layer_warp & bit) && ((S.ngl == 5 && S.nq == 9) || (S.ngl == 4 && S.nq == 7)); }
+// SM59 / SM47: dynamic shared memory (bytes) of the (5,9) / (4,7) instantiation
+#define HN_LAUNCH_LW(kern, SM59, SM47, S, args)                                                                              \
+    do {                                                                                                                     \
+        const int _blocks = ((S).nelem + LW_WARPS - 1) / LW_WARPS;                                                           \
+        if ((S).ngl == 5) {                                                                                                  \
+            const size_t _sm = (SM59);                                                                                       \
+            if ((S).nl == 2) { smem_opt_in(kern<5, 9, 2>, _sm); kern<5, 9, 2><<<_blocks, 32 * LW_WARPS, _sm, (S).stream>>>(args); }      \
+            else if ((S).nl == 3) { smem_opt_in(kern<5, 9, 3>, _sm); kern<5, 9, 3><<<_blocks, 32 * LW_WARPS, _sm, (S).stream>>>(args); } \
+            else { smem_opt_in(kern<5, 9, 0>, _sm); kern<5, 9, 0><<<_blocks, 32 * LW_WARPS, _sm, (S).stream>>>(args); }                  \
+        } else {                                                                                                             \
+            const size_t _sm = (SM47);                                                                                       \
+            smem_opt_in(kern<4, 7, 0>, _sm); kern<4, 7, 0><<<_blocks, 32 * LW_WARPS, _sm, (S).stream>>>(args);               \
+        }                                                                                                                    \
     } while (0)
 
 static int threads_for(const Solver& S);
@@ -248,10 +267,13 @@ int rhs_btp_only(Solver& S, Planes& qb, const Planes& qprime, double* d_rhs_out)
     if (use_pair(S)) {
         if (pair_pack(S, qb, qprime, 0)) return -1;
         PairArgs a; fill_pair_args(S, a);
-        a.a1 = 0.0; a.a2 = 1.0; a.a3 = 0.0; a.dtt = 0.0;
+        a.a1 = 0.0; a.a2 = 0.0; a.a3 = 0.0; a.dtt = 1.0;   // new state = 0 + 1 * rhs
         a.tr_in = S.p_tr[0]; a.tr_out = S.p_tr[1]; a.part = 0;
-        a.rhs_only = 1; a.rhs_out = d_rhs_out; a.rhs_stride = (size_t)S.npoin;
+        a.rhs_only = 1;
         if (launch_stage_pair(S, a)) return -1;
+        const PairDims D = make_pairdims(S.ngl, S.nq);
+        k_pair_unpack_qb<<<nblk(S.npoin), 256, 0, S.stream>>>(S.nelem, D, S.p_rec, d_rhs_out, d_rhs_out + S.npoin, d_rhs_out + 2 * (size_t)S.npoin);
+        S.n_launches++;
         HN_CUDA(cudaGetLastError());
         return 0;
     }
@@ -514,7 +536,8 @@ int btp_bcl_coeffs(Solver& S, const Planes& qprime, const Planes& dpv) {
     for (int k = 0; k < S.nl; ++k) a.alpha[k] = S.alpha[k];
     a.has_visc = S.has_visc;
     size_t sm = (sops_doubles_host(S.ngl, S.nq) + 3 * S.npts + 3 * S.ngl * S.nq + 12 * S.ngl) * sizeof(double);
-    HN_LAUNCH_GQL(k_bcl_coeffs, S, sm, a);
+    if (use_layer_warp(S, 1)) HN_LAUNCH_LW(k_bcl_coeffs_w, (lw_coeffs_smem<5, 9>()), (lw_coeffs_smem<4, 7>()), S, a);
+    else HN_LAUNCH_GQL(k_bcl_coeffs, S, sm, a);
     S.n_launches++;
     if (S.has_visc && S.nhalo > 0) {
         // graduv_dpp_face exchange (mod_barotropic_terms.F90:393): per-layer planes and their layer sums
@@ -540,7 +563,8 @@ static int layer_mass_and_consistency(Solver& S, const Planes& qprime, const Pla
     m.massinv = S.massinv; m.flag = S.d_flag; m.dt = S.dt;
     size_t per = S.ngl * S.nq;
     size_t sm = (sops_doubles_host(S.ngl, S.nq) + 3 * S.npts + 3 * per + 12 * S.ngl + 2 * S.nq2 + 2 * per + S.npts + 4 * S.nq) * sizeof(double);
-    HN_LAUNCH_GQL(k_layer_mass, S, sm, m);
+    if (use_layer_warp(S, 2)) HN_LAUNCH_LW(k_layer_mass_w, (lw_mass_smem<5, 9>()), (lw_mass_smem<4, 7>()), S, m);
+    else HN_LAUNCH_GQL(k_layer_mass, S, sm, m);
     S.n_launches++;
     // apply_consistency (mod_splitting.F90:324-366)
     if (halo_exchange_nodal(S, q[0], S.nl, q.stride, S.h_dp)) return -1;
@@ -552,7 +576,8 @@ static int layer_mass_and_consistency(Solver& S, const Planes& qprime, const Pla
     c.slmf_q[0] = S.slmf_q[0]; c.slmf_q[1] = S.slmf_q[1]; c.slmf_f[0] = S.slmf_f[0]; c.slmf_f[1] = S.slmf_f[1];
     c.dt = S.dt;
     sm = (sops_doubles_host(S.ngl, S.nq) + (size_t)S.nl * S.npts + 4 * S.nl * S.ngl + per + 2 * S.nq2 + 2 * per + S.npts + 4 * S.nq) * sizeof(double);
-    HN_LAUNCH_GQL(k_consistency, S, sm, c);
+    if (use_layer_warp(S, 4)) HN_LAUNCH_LW(k_consistency_w, (lw_cons_smem<5, 9>()), (lw_cons_smem<4, 7>()), S, c);
+    else HN_LAUNCH_GQL(k_consistency, S, sm, c);
     S.n_launches++;
     cudaMemcpyAsync(q[0], S.qdp_tmp.p, (size_t)S.nl * q.stride * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
     return 0;
@@ -568,7 +593,8 @@ static int momentum_update(Solver& S, const Planes& qprime_in, const Planes& dpv
         l.h_dpv = S.h_dpv.p; l.h_dpg = S.h_dpg.p; l.h_gub = S.h_gub.p; l.hstride = S.h_dpv.stride;
         l.massinv = S.massinv; l.rhs_visc = S.rhs_visc.p; l.visc = S.visc;
         size_t sm = (sops_doubles_host(S.ngl, S.nq) + 8 * S.npts + 8 * S.ngl) * sizeof(double);
-        HN_LAUNCH_GQL(k_bcl_laplacian, S, sm, l);
+        if (use_layer_warp(S, 8)) HN_LAUNCH_LW(k_bcl_laplacian_w, (lw_lap_smem<5, 9>()), (lw_lap_smem<4, 7>()), S, l);
+        else HN_LAUNCH_GQL(k_bcl_laplacian, S, sm, l);
         S.n_launches++;
         if (phase_check(S, "k_bcl_laplacian")) return -1;
     }
@@ -580,7 +606,9 @@ static int momentum_update(Solver& S, const Planes& qprime_in, const Planes& dpv
     for (int k = 0; k < S.nl; ++k) v.alpha[k] = S.alpha[k];
     v.g = S.g;
     size_t sm = (sops_doubles_host(S.ngl, S.nq) + 5 * S.npts + 6 * per + 6 * S.nq2 + 4 * per + 2 * S.npts) * sizeof(double);
-    HN_LAUNCH_GQL(k_mom_volume, S, sm, v);
+    if (use_layer_warp(S, 16))
+        HN_LAUNCH_LW(k_mom_volume_w, (LW_WARPS * sizeof(double) * lw_mvol_doubles<5, 9>(S.nl)), (LW_WARPS * sizeof(double) * lw_mvol_doubles<4, 7>(S.nl)), S, v);
+    else HN_LAUNCH_GQL(k_mom_volume, S, sm, v);
     S.n_launches++;
     if (phase_check(S, "k_mom_volume")) return -1;
     MomFaceArgs f; memset(&f, 0, sizeof(f));
@@ -593,7 +621,9 @@ static int momentum_update(Solver& S, const Planes& qprime_in, const Planes& dpv
     for (int k = 0; k < S.nl; ++k) f.alpha[k] = S.alpha[k];
     f.g = S.g; f.dt = S.dt; f.full_prime = full_prime;
     sm = (sops_doubles_host(S.ngl, S.nq) + 24 * (size_t)S.nl * S.ngl + 8 * (size_t)S.nl * S.nq) * sizeof(double);
-    HN_LAUNCH_GQL(k_mom_faces_update, S, sm, f);
+    if (use_layer_warp(S, 32))
+        HN_LAUNCH_LW(k_mom_faces_update_w, (LW_WARPS * sizeof(double) * lw_mface_doubles<5, 9>(S.nl)), (LW_WARPS * sizeof(double) * lw_mface_doubles<4, 7>(S.nl)), S, f);
+    else HN_LAUNCH_GQL(k_mom_faces_update, S, sm, f);
     S.n_launches++;
     return 0;
 }
@@ -1135,6 +1165,7 @@ int hnumo_set_option(hnumo_handle_t h, const char* key, double value) {
     HN_ENTER(h);
     if (!strcmp(key, "stage_kernel_variant")) { S.variant = (int)value; return 0; }
     if (!strcmp(key, "use_graph")) { S.use_graph = (int)value; return 0; }
+    if (!strcmp(key, "layer_warp")) { S.layer_warp = (int)value; return 0; }
     if (!strcmp(key, "pair_prefetch")) { S.pair_prefetch = (int)value; return 0; }
     if (!strcmp(key, "pair_pf_dist")) { S.pair_pf_dist = (int)value; return 0; }
     if (!strcmp(key, "overlap")) { S.overlap = (int)value; return 0; }

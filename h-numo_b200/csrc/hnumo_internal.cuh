@@ -142,6 +142,11 @@ struct Solver {
     int n_belem = 0, overlap = 1;
     double *d_diag_partial = nullptr, *d_diag_res = nullptr;   // device-side diagnostics (diag.cuh), allocated on first use
     int num_sms = 148;
+    // warp-per-element layer kernels (layer_warp.cuh) where instantiated, bit per kernel: 1 coeffs, 2 layer mass, 4 consistency,
+    // 8 laplacian, 16 momentum volume, 32 momentum faces + update; 0 = block-per-element kernels (bcl_kernels.cuh).
+    // Default 47: the momentum volume kernel is faster in its block-per-element form (1.37 vs 1.57 ms per launch at 62 500
+    // elements: the warp form interpolates every layer twice), see profiles/r2_layer_kernels.md
+    int layer_warp = 47;
     std::vector<void*> allocs;
 };
 

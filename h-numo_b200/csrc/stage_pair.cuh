@@ -26,10 +26,10 @@
 #include <mutex>
 
 #include "btp_kernels.cuh"
+#include "line_ops.cuh"
 
 namespace hn {
 
-__host__ __device__ constexpr int pr_pad2(int n) { return (n + 1) & ~1; }
 
 // forcing-sparsity flags of an element (header word 22): a zero field is not read
 enum { PF_GZ = 1, PF_TWX = 2, PF_TWY = 4, PF_COR = 8 };
@@ -66,10 +66,9 @@ struct PairRec {
     // shared memory per warp, in units of NE doubles.  The strides SX, ST, TM are padded so that in the line phases
     // (lane = Q*f + i, or lane = G*f + m) the word index is congruent to the lane number modulo 16: no bank conflicts
     // (profiles/smem_conflicts.py).
-    static constexpr int pick(int lo, int mod) { return lo + ((mod - lo) % 16 + 16) % 16; }
-    static constexpr int SX = pick(NQ2, Q);         // stride of the quadrature-point arrays
-    static constexpr int TM = (Q <= 9) ? 11 : Q + 2;   // row stride of the pass-1 arrays T[f][m][i]
-    static constexpr int ST = pick((G - 1) * TM + Q, Q);
+    static constexpr int SX = LineGeom<G, Q>::SX;   // stride of the quadrature-point arrays
+    static constexpr int TM = LineGeom<G, Q>::TM;   // row stride of the pass-1 arrays T[f][m][i]
+    static constexpr int ST = LineGeom<G, Q>::ST;
     static constexpr int S_NOD = 0;                 // 0 dpp 1 mx 2 my 3 pb 4 pp 5 up 6 vp 7 u 8 v ; later 4..7 = LDG flux variable
     static constexpr int S_X = S_NOD + 9 * NP;      // 8 quadrature-point arrays; later rhs, face traces, face fluxes
     static constexpr int X_RHS = 0, X_FL = 3 * NP, X_FR = X_FL + 16 * G, X_LF = X_FR + 16 * G, X_FF = X_LF + 8 * G;
@@ -97,28 +96,13 @@ struct PairArgs {
     //   part 2: every element that has no processor face (warps of the others leave once their header has arrived)
     int part, count;
     const int* elist;
-    // rhs_only: evaluate create_rhs_btp of the state in the records (mod_rhs_btp.F90:28-59) into rhs_out[3][npoin] and
-    // change nothing else -- no running sums, no update, no traces (per-phase test entry hnumo_rhs_btp)
+    // rhs_only (per-phase test entry hnumo_rhs_btp): with a1 = a2 = a3 = 0 and dtt = 1 the "new state" the kernel stores in
+    // the records IS create_rhs_btp of the packed state (mod_rhs_btp.F90:28-59); the flag only switches the wall projection
+    // off.  The caller unpacks the records afterwards; the next solve packs them afresh.
     int rhs_only;
-    double* rhs_out;
-    size_t rhs_stride;
     int configure_only;   // host: set the per-device function attributes and return (hnumo_init, before any graph capture)
 };
 
-// shared-memory vector of NE doubles
-template <int NE> struct PV;
-template <> struct PV<1> {
-    typedef double T;
-    static __device__ __forceinline__ void ld(const T* p, double (&o)[1]) { o[0] = *p; }
-    static __device__ __forceinline__ void st(T* p, const double (&i)[1]) { *p = i[0]; }
-};
-template <> struct PV<2> {
-    typedef double2 T;
-    static __device__ __forceinline__ void ld(const T* p, double (&o)[2]) { double2 t = *p; o[0] = t.x; o[1] = t.y; }
-    static __device__ __forceinline__ void st(T* p, const double (&i)[2]) { *p = make_double2(i[0], i[1]); }
-};
-
-#define PR_FORC _Pragma("unroll") for (int c = 0; c < NE; ++c)
 
 // phase time stamps of a sample of warps (debug builds only: -DHN_PAIR_TIMING)
 #ifdef HN_PAIR_TIMING
@@ -173,62 +157,6 @@ __device__ __forceinline__ double* pr_align16(double* p) { return reinterpret_ca
 
 __device__ __forceinline__ void pr_prefetch_l2(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
-// ---- line contractions on NE elements at once.  The operator entry is a uniform-register operand shared by the NE
-// FMAs.  Loop order: contraction index outside, OUTPUT index inside -- consecutive FMAs belong to independent
-// accumulators (an FP64 FMA has ~8 cycles of dependent-issue latency; the chain-serial order costs 4x the pipe time).
-// out[i] = sum_n M(n,i) in[n], nodes -> quadrature points
-template <int NE, int G, int Q, bool DERIV, int SS, int DS>
-__device__ __forceinline__ void pl_n2q(const typename PV<NE>::T* src, typename PV<NE>::T* dst) {
-    double in[G][NE], s[Q][NE];
-#pragma unroll
-    for (int n = 0; n < G; ++n) PV<NE>::ld(src + n * SS, in[n]);
-#pragma unroll
-    for (int n = 0; n < G; ++n) {
-#pragma unroll
-        for (int i = 0; i < Q; ++i) {
-            const double mv = DERIV ? c_ops.BT[i + Q * n] : c_ops.AT[i + Q * n];
-            if (n == 0) { PR_FORC s[i][c] = mv * in[0][c]; }
-            else { PR_FORC s[i][c] = fma(mv, in[n][c], s[i][c]); }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < Q; ++i) PV<NE>::st(dst + i * DS, s[i]);
-}
-// acc[n] (+)= sum_i M(n,i) in[i], quadrature points -> nodes (weak-form transpose)
-template <int NE, int G, int Q, bool DERIV, int SS, bool FIRST>
-__device__ __forceinline__ void pl_q2n_acc(const typename PV<NE>::T* src, double (&acc)[G][NE]) {
-    double in[Q][NE];
-#pragma unroll
-    for (int i = 0; i < Q; ++i) PV<NE>::ld(src + i * SS, in[i]);
-#pragma unroll
-    for (int i = 0; i < Q; ++i) {
-#pragma unroll
-        for (int n = 0; n < G; ++n) {
-            const double mv = DERIV ? c_ops.B[n + G * i] : c_ops.A[n + G * i];
-            if (FIRST && i == 0) { PR_FORC acc[n][c] = mv * in[0][c]; }
-            else { PR_FORC acc[n][c] = fma(mv, in[i][c], acc[n][c]); }
-        }
-    }
-}
-// collocation derivative along a nodal line (runtime stride): out[n] = sum_k D(k,n) in[k]  or transposed D(n,k)
-template <int NE, int G, bool TRANSP>
-__device__ __forceinline__ void pl_grad(const typename PV<NE>::T* src, typename PV<NE>::T* dst, int stride) {
-    double in[G][NE], s[G][NE];
-#pragma unroll
-    for (int k = 0; k < G; ++k) PV<NE>::ld(src + k * stride, in[k]);
-#pragma unroll
-    for (int k = 0; k < G; ++k) {
-#pragma unroll
-        for (int n = 0; n < G; ++n) {
-            const double mv = TRANSP ? c_ops.D[n + G * k] : c_ops.DT[n + G * k];
-            if (k == 0) { PR_FORC s[n][c] = mv * in[0][c]; }
-            else { PR_FORC s[n][c] = fma(mv, in[k][c], s[n][c]); }
-        }
-    }
-#pragma unroll
-    for (int n = 0; n < G; ++n) PV<NE>::st(dst + n * stride, s[n]);
 }
 
 template <int G>
@@ -302,7 +230,6 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
         rec[c] = a.rec + (size_t)e[c] * R::REC;
     }
     constexpr bool botfr = BOTFR != 0;
-    if (a.rhs_only) { PR_FORC ok[c] = false; }   // ok guards every store and running sum
 
     // ---- 1. nodal loads + nodal sums (mod_rk_mlswe.F90:90-92)
     double pbp[NE], pv[NE], bd[4][NE];   // kept by lane I < NP for the LDG flux variable and the update
@@ -866,10 +793,6 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
         PR_FORC {
             double rr[3] = {mi[c] * r0[c], mi[c] * r1[c], mi[c] * r2[c]};
             if (VISC) { rr[1] = rr[1] + a.visc * mi[c] * l0[c]; rr[2] = rr[2] + a.visc * mi[c] * l1[c]; }
-            if (a.rhs_only && unit * NE + c < a.count) {   // (part 0 only)
-                double* ro = a.rhs_out + (size_t)e[c] * NP + I;
-                ro[0] = rr[0]; ro[a.rhs_stride] = rr[1]; ro[2 * a.rhs_stride] = rr[2];
-            }
             const double q1[3] = {q1a[c], q1b[c], q1c[c]};
             double qn[3];
 #pragma unroll
@@ -883,7 +806,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
             for (int s = 0; s < 4; ++s) {
                 const bool on = (s == 0) ? (m == 0) : (s == 1) ? (m == G - 1) : (s == 2) ? (n == 0) : (n == G - 1);
                 if (!on) continue;
-                const int nb = hi[s];
+                const int nb = a.rhs_only ? 0 : hi[s];
                 if (nb == NBR_FREESLIP) {
                     const double nx = h[6 + s * 3 + 0], ny = h[6 + s * 3 + 1];
                     const double unl = qn[1] * nx + qn[2] * ny;
