@@ -60,7 +60,7 @@ class Desc(C.Structure):
 
 
 EXPORTS = ["hnumo_init", "hnumo_device_count", "hnumo_finalize", "hnumo_last_error", "hnumo_upload_state", "hnumo_download_state",
-           "hnumo_step", "hnumo_ti_rk_bcl", "hnumo_btp_bcl_coeffs", "hnumo_btp_substeps", "hnumo_rhs_btp",
+           "hnumo_step", "hnumo_ti_rk_bcl", "hnumo_btp_bcl_coeffs", "hnumo_btp_substeps", "hnumo_rhs_btp", "hnumo_layer_mass_rhs", "hnumo_layer_momentum_rhs", "hnumo_halo_exchange",
            "hnumo_get_array", "hnumo_diagnostics", "hnumo_snapshot_write", "hnumo_snapshot_info",
            "hnumo_snapshot_read_restart", "hnumo_comm_get_unique_id", "hnumo_comm_init", "hnumo_timing", "hnumo_set_option"]
 
@@ -83,6 +83,10 @@ def load_library(path=None):
         L.hnumo_btp_bcl_coeffs.argtypes = [C.c_void_p]
         L.hnumo_btp_substeps.argtypes = [C.c_void_p]
         L.hnumo_rhs_btp.argtypes = [C.c_void_p, C.c_void_p]
+        L.hnumo_layer_mass_rhs.argtypes = [C.c_void_p, C.c_void_p]
+        L.hnumo_layer_momentum_rhs.argtypes = [C.c_void_p, C.c_void_p]
+        L.hnumo_halo_exchange.restype = C.c_int64
+        L.hnumo_halo_exchange.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.hnumo_get_array.restype = C.c_int64
         L.hnumo_get_array.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
         L.hnumo_snapshot_write.argtypes = [C.c_char_p, C.c_int32, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -191,6 +195,29 @@ class Solver:
         out = np.empty((self.npoin, 3))
         self._check(self.L.hnumo_rhs_btp(self.h, out.ctypes.data), "rhs_btp")
         return out
+
+    def layer_mass_rhs(self):
+        """dp_advec[k, I] of layer_mass_rhs on the resident state (per-phase entry)"""
+        out = np.empty((self.nl, self.npoin))
+        self._check(self.L.hnumo_layer_mass_rhs(self.h, out.ctypes.data), "layer_mass_rhs")
+        return out
+
+    def layer_momentum_rhs(self):
+        """rhs_mom[k, I, 0:2] of layer_momentum_rhs on the resident state (per-phase entry)"""
+        out = np.empty((self.nl, self.npoin, 2))
+        self._check(self.L.hnumo_layer_momentum_rhs(self.h, out.ctypes.data), "layer_momentum_rhs")
+        return out
+
+    def halo_exchange(self, nodal):
+        """nodal[I, v] -> halo[h, n, v]: the neighbour's values at the nodes of this rank's processor faces (collective)"""
+        nodal = np.ascontiguousarray(nodal, dtype=np.float64).reshape(self.npoin, -1)
+        nv = nodal.shape[1]
+        nh = len(self.deck["nbh_send_recv"])
+        out = np.zeros((max(nh, 1), self.deck["ngl"], nv))
+        n = self.L.hnumo_halo_exchange(self.h, nodal.ctypes.data, nv, out.ctypes.data)
+        if n < 0:
+            raise HnumoError("halo_exchange failed (%d): %s" % (n, self.L.hnumo_last_error().decode()))
+        return out[:n]
 
     def get_array(self, name):
         cap = 8 * max(self.deck["nelem"] * self.deck["nq"] ** 2, self.deck["nface"] * self.deck["nq"] * 4)

@@ -584,7 +584,8 @@ static int layer_mass_and_consistency(Solver& S, const Planes& qprime, const Pla
 }
 
 // q_in: layer momentum before the step (planes 1,2 are read); q: thickness planes already updated, momentum planes written
-static int momentum_update(Solver& S, const Planes& qprime_in, const Planes& dpv, const Planes& q_in, Planes& q, Planes& qprime_out, const Planes& qb, int full_prime) {
+static int momentum_update(Solver& S, const Planes& qprime_in, const Planes& dpv, const Planes& q_in, Planes& q, Planes& qprime_out, const Planes& qb, int full_prime,
+                           double* rhs_only_out = nullptr) {
     size_t per = S.ngl * S.nq;
     if (S.has_visc) {
         LapArgs l; memset(&l, 0, sizeof(l));
@@ -620,6 +621,7 @@ static int momentum_update(Solver& S, const Planes& qprime_in, const Planes& dpv
     f.massinv = S.massinv; f.a_bcl = S.a_bcl; f.b_bcl = S.b_bcl; f.fdt2 = S.fdt2;
     for (int k = 0; k < S.nl; ++k) f.alpha[k] = S.alpha[k];
     f.g = S.g; f.dt = S.dt; f.full_prime = full_prime;
+    f.rhs_only = rhs_only_out != nullptr; f.rhs_out = rhs_only_out;
     sm = (sops_doubles_host(S.ngl, S.nq) + 24 * (size_t)S.nl * S.ngl + 8 * (size_t)S.nl * S.nq) * sizeof(double);
     if (use_layer_warp(S, 32))
         HN_LAUNCH_LW(k_mom_faces_update_w, (LW_WARPS * sizeof(double) * lw_mface_doubles<5, 9>(S.nl)), (LW_WARPS * sizeof(double) * lw_mface_doubles<4, 7>(S.nl)), S, f);
@@ -1022,6 +1024,68 @@ int hnumo_rhs_btp(hnumo_handle_t h, double* rhs) {
     HN_CUDA(cudaMemcpyAsync(rhs, S.stage_buf, 3 * (size_t)S.npoin * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
     HN_CUDA(cudaStreamSynchronize(S.stream));
     return 0;
+}
+
+// layer_mass_rhs (mod_create_rhs_mlswe.F90:53-78): with a zero thickness going in and dt = 1 the fused "rhs + update" kernel
+// returns the rhs itself (0 + 1 * dp_advec is exact)
+int hnumo_layer_mass_rhs(hnumo_handle_t h, double* dp_advec) {
+    HN_ENTER(h);
+    const size_t NL1 = (size_t)S.nl * S.npoin;
+    if (halo_exchange_nodal(S, S.qprime.p, 3 * S.nl, S.qprime.stride, S.h_q)) return -1;
+    cudaMemsetAsync(S.qdp_tmp.p, 0, NL1 * sizeof(double), S.stream);
+    MassArgs m; memset(&m, 0, sizeof(m));
+    m.M = S.mesh; m.qprime = S.qprime.p; m.nstride = S.qprime.stride; m.hq = S.h_q.p; m.hstride = S.h_q.stride;
+    for (int v = 0; v < 12; ++v) m.ave_q[v] = S.ave_q[v];
+    for (int v = 0; v < 16; ++v) m.ave_f[v] = S.ave_f[v];
+    m.qdp_in = S.qdp_tmp.p; m.qdp = S.q2[0]; m.slmf_q[0] = S.slmf_q[0]; m.slmf_q[1] = S.slmf_q[1]; m.slmf_f[0] = S.slmf_f[0]; m.slmf_f[1] = S.slmf_f[1];
+    m.massinv = S.massinv; m.flag = S.d_flag; m.dt = 1.0;
+    size_t per = S.ngl * S.nq;
+    size_t sm = (sops_doubles_host(S.ngl, S.nq) + 3 * S.npts + 3 * per + 12 * S.ngl + 2 * S.nq2 + 2 * per + S.npts + 4 * S.nq) * sizeof(double);
+    if (use_layer_warp(S, 2)) HN_LAUNCH_LW(k_layer_mass_w, (lw_mass_smem<5, 9>()), (lw_mass_smem<4, 7>()), S, m);
+    else HN_LAUNCH_GQL(k_layer_mass, S, sm, m);
+    S.n_launches++;
+    cudaMemsetAsync(S.d_flag, 0, sizeof(int), S.stream);   // a negative rhs is not a negative thickness
+    HN_CUDA(cudaMemcpyAsync(dp_advec, S.q2[0], NL1 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+    HN_CUDA(cudaStreamSynchronize(S.stream));
+    return 0;
+}
+
+// layer_momentum_rhs (mod_create_rhs_mlswe.F90:28-51) of the resident q_df, qprime_df with dpprime_visc = qprime_df(1,:,:),
+// the coefficients of the last hnumo_btp_bcl_coeffs and the time averages of the last hnumo_btp_substeps: rhs_mom(2,npoin,nlayers)
+int hnumo_layer_momentum_rhs(hnumo_handle_t h, double* rhs_mom) {
+    HN_ENTER(h);
+    const size_t NP = S.npoin;
+    if (halo_exchange_nodal(S, S.qprime.p, 3 * S.nl, S.qprime.stride, S.h_q)) return -1;
+    Planes dpv1; dpv1.p = S.qprime.p; dpv1.stride = S.qprime.stride; dpv1.n = S.nl;
+    if (momentum_update(S, S.qprime, dpv1, S.q, S.q2, S.qprime2, S.qb, 1, S.rhs_mom.p)) return -1;
+    k_planes_to_aos<<<nblk(NP), 256, 0, S.stream>>>(S.stage_buf, S.rhs_mom.p, 2, 0, 2, S.nl, NP, NP);
+    S.n_launches++;
+    HN_CUDA(cudaMemcpyAsync(rhs_mom, S.stage_buf, 2 * S.nl * NP * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+    HN_CUDA(cudaStreamSynchronize(S.stream));
+    return 0;
+}
+
+// Face-halo exchange of nv nodal fields (the "side 2 := neighbour's side 1" step of create_nbhs_face_df,
+// src/create_rhs_dynamics_flux.F90:104-182): nodal(nv,npoin) from the host, halo(nv,ngl,nhalo) back, processor faces in the
+// order of nbh_send_recv.  Every rank of the partition must call it (collective).  Returns the number of processor faces.
+int64_t hnumo_halo_exchange(hnumo_handle_t h, const double* nodal, int32_t nv, double* halo) {
+    HN_ENTER(h);
+    const size_t NP = S.npoin;
+    if (nv < 1 || nv > 3 * S.nl) { set_error("hnumo_halo_exchange", "nv must be in 1..3*nlayers"); return -2; }
+    HN_CUDA(cudaMemcpyAsync(S.stage_buf, nodal, (size_t)nv * NP * sizeof(double), cudaMemcpyHostToDevice, S.stream));
+    k_aos_to_planes<<<nblk(NP), 256, 0, S.stream>>>(S.stage_buf, S.q2.p, nv, 0, nv, 1, NP, NP);   // planes [v] (scratch)
+    S.n_launches++;
+    if (halo_exchange_nodal(S, S.q2.p, nv, S.q2.stride, S.h_q)) { halo_abort(S); return -1; }
+    if (S.nhalo > 0) {
+        std::vector<double> tmp((size_t)S.nhalo * S.ngl);
+        for (int v = 0; v < nv; ++v) {
+            HN_CUDA(cudaMemcpyAsync(tmp.data(), S.h_q[v], tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+            HN_CUDA(cudaStreamSynchronize(S.stream));
+            for (size_t i = 0; i < tmp.size(); ++i) halo[i * nv + v] = tmp[i];
+        }
+    }
+    HN_CUDA(cudaStreamSynchronize(S.stream));
+    return S.nhalo;
 }
 
 // reference-layout export of work arrays (tests)

@@ -970,6 +970,12 @@ __global__ void __launch_bounds__(32 * LW_WARPS, 3) k_mom_faces_update_w(MomFace
             if (n == G - 1) { r0 += fp[((3 * nl + k) * 2 + 0) * G + m]; r1 += fp[((3 * nl + k) * 2 + 1) * G + m]; }
             r0 = mi * r0 + a.rhs_visc[(size_t)(0 * nl + k) * a.nstride + nbase + tid];
             r1 = mi * r1 + a.rhs_visc[(size_t)(1 * nl + k) * a.nstride + nbase + tid];
+            if (a.rhs_only) {   // per-phase entry hnumo_layer_momentum_rhs: rhs_mom(1:2,I,k) of layer_momentum_rhs, nothing else
+                a.rhs_out[(size_t)(0 * nl + k) * a.nstride + nbase + tid] = r0;
+                a.rhs_out[(size_t)(1 * nl + k) * a.nstride + nbase + tid] = r1;
+                qd[k] = 1.0; qx[k] = 0.0; qy[k] = 0.0;
+                continue;
+            }
             double dpk = a.q[(size_t)(0 * nl + k) * a.nstride + nbase + tid];
             double mxo = a.q_in[(size_t)(1 * nl + k) * a.nstride + nbase + tid], myo = a.q_in[(size_t)(2 * nl + k) * a.nstride + nbase + tid];
             double t1 = mxo + a.dt * r0, t2 = myo + a.dt * r1;
@@ -988,6 +994,7 @@ __global__ void __launch_bounds__(32 * LW_WARPS, 3) k_mom_faces_update_w(MomFace
             }
             qd[k] = dpk; qx[k] = mxn; qy[k] = myn;
         }
+        if (a.rhs_only) return;
         // evaluate_bcl / evaluate_bcl_v1: two passes of extract_velocity
         double pb = a.qb[0][nbase + tid] + a.pbprime_df[nbase + tid];
         double mbx = a.qb[1][nbase + tid], mby = a.qb[2][nbase + tid];

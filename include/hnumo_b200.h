@@ -121,6 +121,19 @@ int hnumo_btp_substeps(hnumo_handle_t h);
 /* create_rhs_btp(rhs, qb_df, qprime_df): rhs(3,npoin) to host (src/mod_rhs_btp.F90:28-59).  The time-average
  * accumulators are not touched. */
 int hnumo_rhs_btp(hnumo_handle_t h, double* rhs);
+/* layer_mass_rhs(dp_advec, qprime_df, qprime_df_face) on the resident qprime_df with the time averages of the last
+ * hnumo_btp_substeps: dp_advec(npoin,nlayers) to host; sum_layer_mass_flux(_face) are refreshed
+ * (src/mod_create_rhs_mlswe.F90:53-78,822-877,922-1034) */
+int hnumo_layer_mass_rhs(hnumo_handle_t h, double* dp_advec);
+/* layer_momentum_rhs(rhs_mom, qprime_df, q_df, qprime_df_face) on the resident state with dpprime_visc = qprime_df(1,:,:), the
+ * coefficients of the last hnumo_btp_bcl_coeffs and the time averages of the last hnumo_btp_substeps: rhs_mom(2,npoin,nlayers)
+ * to host (src/mod_create_rhs_mlswe.F90:28-51,281-820, src/mod_laplacian_quad.F90:227-248) */
+int hnumo_layer_momentum_rhs(hnumo_handle_t h, double* rhs_mom);
+/* face-halo exchange of nv nodal fields, the device replacement of create_nbhs_face_df / send_bound_dg_general_df
+ * (src/create_rhs_dynamics_flux.F90:104-182, src/send_receive_bound.F90:272-327): nodal(nv,npoin) in, halo(nv,ngl,nhalo) out with
+ * the processor faces in the order of nbh_send_recv ("side 2 := the neighbour's side 1").  Collective over the ranks of the
+ * partition.  Returns the number of processor faces of this rank or <0. */
+int64_t hnumo_halo_exchange(hnumo_handle_t h, const double* nodal, int32_t nv, double* halo);
 /* copy a named mod_variables work array to the host in the reference's layout; face arrays are indexed by the
  * face numbers of desc->face.  Names: Q_uu_dp Q_uv_dp Q_vv_dp H_bcl Q_uu_dp_edge Q_uv_dp_edge Q_vv_dp_edge
  * H_bcl_edge grad_zbot_quad (note: entries of grad z_bot that are pure differentiation noise, |sum| <= 1e-13 sum|terms|, i.e. the

@@ -91,6 +91,24 @@ void orc_rhs_btp(void* h, double* rhs_out) {
     o->create_rhs_btp(rhs, o->qb_df, o->qprime_df);
     std::memcpy(rhs_out, rhs.data(), rhs.size() * sizeof(double));
 }
+// phase: layer_mass_rhs (mod_create_rhs_mlswe.F90:53-78) of the current qprime_df with the current time averages: dp_advec(npoin,nl)
+void orc_layer_mass_rhs(void* h, double* out) {
+    Oracle* o = (Oracle*)h;
+    Arr qf; qf.alloc(3, 2, o->ngl, o->nface, o->nl);
+    o->extract_qprime_df_face(qf, o->qprime_df);
+    Arr dp_advec; dp_advec.alloc(o->npoin, o->nl);
+    o->layer_mass_rhs(dp_advec, o->qprime_df, qf);
+    std::memcpy(out, dp_advec.data(), dp_advec.size() * sizeof(double));
+}
+// phase: layer_momentum_rhs (mod_create_rhs_mlswe.F90:28-51) of the current q_df, qprime_df: rhs_mom(2,npoin,nl)
+void orc_layer_momentum_rhs(void* h, double* out) {
+    Oracle* o = (Oracle*)h;
+    Arr qf; qf.alloc(3, 2, o->ngl, o->nface, o->nl);
+    o->extract_qprime_df_face(qf, o->qprime_df);
+    Arr rhs; rhs.alloc(2, o->npoin, o->nl);
+    o->rhs_momentum(rhs, o->qprime_df, o->q_df, qf);
+    std::memcpy(out, rhs.data(), rhs.size() * sizeof(double));
+}
 // phase: full barotropic substep loop on qb_df in place (mod_rk_mlswe.F90:19-151)
 void orc_btp_substeps(void* h) {
     Oracle* o = (Oracle*)h;

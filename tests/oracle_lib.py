@@ -68,6 +68,8 @@ def lib(variant=""):
         L.orc_btp_bcl_coeffs.argtypes = [C.c_void_p]
         L.orc_rhs_btp.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_btp_substeps.argtypes = [C.c_void_p]
+        L.orc_layer_mass_rhs.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_layer_momentum_rhs.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_diagnostics.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _LIBS[variant] = L
     return _LIBS[variant]
@@ -160,6 +162,16 @@ class Oracle:
 
     def btp_substeps(self):
         self.L.orc_btp_substeps(self.h)
+
+    def layer_mass_rhs(self):
+        out = np.empty(self.npoin * self.nl)
+        self.L.orc_layer_mass_rhs(self.h, out.ctypes.data)
+        return out.reshape(self.nl, self.npoin)
+
+    def layer_momentum_rhs(self):
+        out = np.empty(2 * self.npoin * self.nl)
+        self.L.orc_layer_momentum_rhs(self.h, out.ctypes.data)
+        return out.reshape(self.nl, self.npoin, 2)
 
     def diagnostics(self):
         q = np.empty(5 * self.npoin * self.nl)
