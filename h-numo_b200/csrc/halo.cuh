@@ -222,6 +222,39 @@ inline int halo_exchange_traces(Solver& S, const Planes& tr, int nv) {
     S.n_launches += 2;
     return 0;
 }
+// several sets of nodal planes in ONE message per neighbour: send[(h*NPT + p)*ngl + n] with p running over the planes of all
+// segments (NPT in total)
+struct HaloSeg { const double* planes; int np; size_t stride; double* hout; size_t hstride; };
+struct HaloSegs { HaloSeg s[4]; int n, npt; };
+__global__ void k_pack_nodal_multi(HaloSegs g, const int* halo_slot, int nhalo, int ngl, int npts, double* send) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t tot = (size_t)nhalo * g.npt * ngl;
+    if (t >= tot) return;
+    int n = t % ngl; size_t r = t / ngl; int p = r % g.npt; int h = r / g.npt;
+    int slot = halo_slot[h], e = slot >> 2, s = slot & 3, k = 0;
+    while (p >= g.s[k].np) { p -= g.s[k].np; ++k; }
+    send[t] = g.s[k].planes[(size_t)p * g.s[k].stride + (size_t)e * npts + face_node(s, n, ngl)];
+}
+__global__ void k_unpack_nodal_multi(HaloSegs g, int nhalo, int ngl, const double* recv) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t tot = (size_t)nhalo * g.npt * ngl;
+    if (t >= tot) return;
+    int n = t % ngl; size_t r = t / ngl; int p = r % g.npt; int h = r / g.npt, k = 0;
+    while (p >= g.s[k].np) { p -= g.s[k].np; ++k; }
+    g.s[k].hout[(size_t)p * g.s[k].hstride + (size_t)h * ngl + n] = recv[t];
+}
+inline int halo_exchange_nodal_multi(Solver& S, const HaloSeg* seg, int nseg) {
+    if (S.nhalo == 0) return 0;
+    HaloSegs g; g.n = nseg; g.npt = 0;
+    for (int i = 0; i < nseg; ++i) { g.s[i] = seg[i]; g.npt += seg[i].np; }
+    for (int i = nseg; i < 4; ++i) g.s[i] = HaloSeg{nullptr, 1 << 30, 0, nullptr, 0};
+    size_t tot = (size_t)S.nhalo * g.npt * S.ngl;
+    k_pack_nodal_multi<<<(tot + 255) / 256, 256, 0, S.stream>>>(g, S.d_halo_slot, S.nhalo, S.ngl, S.npts, S.d_send);
+    if (halo_sendrecv(S, (size_t)g.npt * S.ngl)) return -1;
+    k_unpack_nodal_multi<<<(tot + 255) / 256, 256, 0, S.stream>>>(g, S.nhalo, S.ngl, S.d_recv);
+    S.n_launches += 2;
+    return 0;
+}
 inline int halo_exchange_nodal(Solver& S, const double* planes, int np, size_t stride, const Planes& hout) {
     if (S.nhalo == 0) return 0;
     size_t tot = (size_t)S.nhalo * np * S.ngl;

@@ -540,12 +540,13 @@ int btp_bcl_coeffs(Solver& S, const Planes& qprime, const Planes& dpv) {
     else HN_LAUNCH_GQL(k_bcl_coeffs, S, sm, a);
     S.n_launches++;
     if (S.has_visc && S.nhalo > 0) {
-        // graduv_dpp_face exchange (mod_barotropic_terms.F90:393): per-layer planes and their layer sums
-        if (halo_exchange_nodal(S, S.dpp_graduv.p, 4 * S.nl, S.dpp_graduv.stride, S.h_dpg)) return -1;
-        if (halo_exchange_nodal(S, dpv.p, S.nl, dpv.stride, S.h_dpv)) return -1;
-        if (halo_exchange_nodal(S, S.btp_dpp_graduv.p, 4, S.btp_dpp_graduv.stride, S.h_stat)) return -1;
-        Planes last; last.p = S.h_stat[4]; last.stride = S.h_stat.stride; last.n = 1;
-        if (halo_exchange_nodal(S, S.pbprime_visc, 1, S.npoin, last)) return -1;
+        // graduv_dpp_face exchange (mod_barotropic_terms.F90:393): per-layer planes and their layer sums -- ONE message per
+        // neighbour for the four arrays (the reference sends them one by one)
+        HaloSeg seg[4] = {{S.dpp_graduv.p, 4 * S.nl, S.dpp_graduv.stride, S.h_dpg.p, S.h_dpg.stride},
+                          {dpv.p, S.nl, dpv.stride, S.h_dpv.p, S.h_dpv.stride},
+                          {S.btp_dpp_graduv.p, 4, S.btp_dpp_graduv.stride, S.h_stat.p, S.h_stat.stride},
+                          {S.pbprime_visc, 1, (size_t)S.npoin, S.h_stat[4], S.h_stat.stride}};
+        if (halo_exchange_nodal_multi(S, seg, 4)) return -1;
     }
     HN_CUDA(cudaGetLastError());
     return 0;
@@ -657,6 +658,11 @@ int bcl_step(Solver& S) {
     Planes dpv1; dpv1.p = S.qprime.p; dpv1.stride = S.qprime.stride; dpv1.n = S.nl;   // dpprime_visc = qprime_df(1,:,:)
     HN_PHASE(btp_bcl_coeffs(S, S.qprime, dpv1), "predictor btp_bcl_coeffs");   // also refreshes the halo copy of qprime traces
     HN_PHASE(btp_solve(S, S.qb, S.qbp, S.qprime), "predictor btp_solve");
+    if (S.pipe_wait_q) {   // pipelined drop-in call: q_df arrives (staged in q2) while the first barotropic solve runs
+        cudaStreamWaitEvent(S.stream, S.ev_pipe[2], 0);
+        k_aos_to_planes<<<nblk(S.npoin), 256, 0, S.stream>>>(S.q2.p, S.q.p, 3, 0, 3, S.nl, (size_t)S.npoin, (size_t)S.npoin);
+        S.n_launches++; S.pipe_wait_q = 0;
+    }
     HN_PHASE(layer_mass_and_consistency(S, S.qprime, S.q, S.q2), "predictor layer mass + consistency");
     HN_PHASE(momentum_update(S, S.qprime, dpv1, S.q, S.q2, S.qprime2, S.qbp, 1), "predictor momentum");
     // ---- correction
@@ -665,6 +671,15 @@ int bcl_step(Solver& S) {
     dcopy(S, S.dpv.p, S.qprime2[0], NL1);   // dpprime_visc of the corrector: the averaged thickness, which k_thickness_finish replaces below
     HN_PHASE(btp_bcl_coeffs(S, S.qprime2, S.dpv), "corrector btp_bcl_coeffs");
     HN_PHASE(btp_solve(S, S.qb, S.qb, S.qprime2), "corrector btp_solve");
+    if (S.pipe_qb_host) {   // pipelined drop-in call: qb_df is final here; it leaves while the layer kernels run
+        const size_t NP = S.npoin;
+        cudaEventRecord(S.ev_pipe[3], S.stream);
+        cudaStreamWaitEvent(S.copy_stream, S.ev_pipe[3], 0);
+        k_planes_to_aos<<<nblk(NP), 256, 0, S.copy_stream>>>(S.stage_buf, S.qb.p, 4, 1, 3, 1, NP, NP);
+        k_pb_to_aos<<<nblk(NP), 256, 0, S.copy_stream>>>(S.stage_buf, S.qb[0], S.pbprime_df, NP);
+        cudaMemcpyAsync(S.pipe_qb_host, S.stage_buf, 4 * NP * sizeof(double), cudaMemcpyDeviceToHost, S.copy_stream);
+        S.n_launches += 2; S.pipe_qb_host = nullptr;
+    }
     HN_PHASE(layer_mass_and_consistency(S, S.qprime2, S.q, S.q), "corrector layer mass + consistency");
     // dpprime of the new thickness -> qprime (in place); qprime2.dp <- average of old and new
     k_thickness_finish<<<nblk(S.npoin), 256, 0, S.stream>>>(S.q[0], S.pbprime_df, S.qprime[0], S.qprime[0], S.qprime2[0], S.nl, S.q.stride, S.npoin);
@@ -709,6 +724,9 @@ static void destroy_solver(hnumo_handle_s* h) {
     if (S.comm_stream) cudaStreamSynchronize(S.comm_stream);
     halo_comm_destroy(S);
     if (S.graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)S.graph_exec);
+    if (S.copy_stream) { cudaStreamSynchronize(S.copy_stream); cudaStreamDestroy(S.copy_stream); }
+    for (cudaEvent_t e : S.ev_pipe) if (e) cudaEventDestroy(e);
+    for (auto& e : S.pinned_host) cudaHostUnregister(e.first);
     for (void* p : S.allocs) if (p) cudaFree(p);
     void* extra[] = {S.d_diag_partial, S.d_diag_res, S.d_nbr, S.d_nbslot, S.d_flag, S.d_halo_slot, S.d_belems};
     for (void* p : extra) if (p) cudaFree(p);
@@ -903,7 +921,7 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     size_t hs = (size_t)std::max(S.nhalo, 1) * S.ngl;
     S.h_q = palloc(S, 3 * nl, hs); S.h_dp = palloc(S, nl, hs); S.h_dpv = palloc(S, nl, hs); S.h_dpg = palloc(S, 4 * nl, hs);
     S.h_gub = palloc(S, 4, hs); S.h_stat = palloc(S, 5, hs);
-    S.halo_capacity = (size_t)std::max(8, 4 * nl) * hs;
+    S.halo_capacity = (size_t)std::max(8, 5 * nl + 5) * hs;   // largest message: the merged viscosity exchange, 5 nl + 5 planes
     {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, S.device) == cudaSuccess) S.num_sms = prop.multiProcessorCount;
@@ -991,13 +1009,61 @@ int hnumo_step(hnumo_handle_t h, int32_t nsteps) {
     return rc;
 }
 
+// page-lock a caller array once (Fortran allocatables and numpy arrays are pageable: a pageable copy runs at a fraction of
+// the link's rate and cannot overlap with kernels).  Already pinned memory (cudaHostAlloc, torch pin_memory) is left alone.
+static void pin_host(Solver& S, void* p, size_t bytes) {
+    if (bytes < ((size_t)4 << 20)) return;   // small arrays: the pageable path costs nothing, and short-lived buffers should not stay registered
+    for (auto& e : S.pinned_host) if (e.first == p && e.second >= bytes) return;
+    if (S.pinned_host.size() >= 16) { cudaHostUnregister(S.pinned_host.front().first); cudaGetLastError(); S.pinned_host.erase(S.pinned_host.begin()); }
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) { cudaGetLastError(); return; }
+    cudaGetLastError();
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) S.pinned_host.push_back({p, bytes});
+    else cudaGetLastError();   // not fatal: the copies fall back to the pageable path
+}
+
+// Drop-in call with the reference's signature (src/ti_rk_bcl.F90:9,32-34): host arrays in, host arrays out.  The copies are
+// pipelined with the step: qprime_df (needed first, by btp_bcl_coeffs) and qb_df go up, the first barotropic solve starts, q_df
+// follows behind it; qb_df comes back while the corrector's layer kernels run; q_df and qprime_df (final only after the last
+// kernel) come back with the transpose of the second overlapping the copy of the first.  Staging uses work planes that are idle
+// at those moments (q2, qprime3, stage_buf): no extra device memory.
 int hnumo_ti_rk_bcl(hnumo_handle_t h, double* q_df, double* qb_df, double* qprime_df) {
-    int rc = hnumo_upload_state(h, q_df, qb_df, qprime_df);
-    if (rc) return rc;
-    rc = hnumo_step(h, 1);
-    if (rc < 0) return rc;
-    int rc2 = hnumo_download_state(h, q_df, qb_df, qprime_df);
-    return rc2 ? rc2 : rc;
+    HN_ENTER(h);
+    const size_t NP = S.npoin, NL3 = 3 * (size_t)S.nl * NP;
+    if (!S.copy_stream) {
+        HN_CUDA(cudaStreamCreateWithFlags(&S.copy_stream, cudaStreamNonBlocking));
+        for (auto& e : S.ev_pipe) HN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    pin_host(S, q_df, NL3 * sizeof(double)); pin_host(S, qb_df, 4 * NP * sizeof(double)); pin_host(S, qprime_df, NL3 * sizeof(double));
+    // ---- in
+    HN_CUDA(cudaMemcpyAsync(S.qprime3.p, qprime_df, NL3 * sizeof(double), cudaMemcpyHostToDevice, S.copy_stream));
+    cudaEventRecord(S.ev_pipe[0], S.copy_stream);
+    HN_CUDA(cudaMemcpyAsync(S.stage_buf, qb_df, 4 * NP * sizeof(double), cudaMemcpyHostToDevice, S.copy_stream));
+    cudaEventRecord(S.ev_pipe[1], S.copy_stream);
+    HN_CUDA(cudaMemcpyAsync(S.q2.p, q_df, NL3 * sizeof(double), cudaMemcpyHostToDevice, S.copy_stream));
+    cudaEventRecord(S.ev_pipe[2], S.copy_stream);
+    cudaStreamWaitEvent(S.stream, S.ev_pipe[0], 0);
+    k_aos_to_planes<<<nblk(NP), 256, 0, S.stream>>>(S.qprime3.p, S.qprime.p, 3, 0, 3, S.nl, NP, NP);
+    cudaStreamWaitEvent(S.stream, S.ev_pipe[1], 0);
+    k_aos_to_planes<<<nblk(NP), 256, 0, S.stream>>>(S.stage_buf, S.qb.p, 4, 1, 3, 1, NP, NP);
+    S.n_launches += 2;
+    // ---- the step; bcl_step picks q_df up before the first layer kernel and sends qb_df off after the second solve
+    S.pipe_wait_q = 1; S.pipe_qb_host = qb_df;
+    if (bcl_step(S)) { halo_abort(S); S.pipe_wait_q = 0; S.pipe_qb_host = nullptr; return -1; }
+    // ---- out
+    k_planes_to_aos<<<nblk(NP), 256, 0, S.stream>>>(S.q2.p, S.q.p, 3, 0, 3, S.nl, NP, NP);
+    cudaEventRecord(S.ev_pipe[4], S.stream);
+    k_planes_to_aos<<<nblk(NP), 256, 0, S.stream>>>(S.qprime3.p, S.qprime.p, 3, 0, 3, S.nl, NP, NP);
+    cudaEventRecord(S.ev_pipe[5], S.stream);
+    S.n_launches += 2;
+    cudaStreamWaitEvent(S.copy_stream, S.ev_pipe[4], 0);
+    HN_CUDA(cudaMemcpyAsync(q_df, S.q2.p, NL3 * sizeof(double), cudaMemcpyDeviceToHost, S.copy_stream));
+    cudaStreamWaitEvent(S.copy_stream, S.ev_pipe[5], 0);
+    HN_CUDA(cudaMemcpyAsync(qprime_df, S.qprime3.p, NL3 * sizeof(double), cudaMemcpyDeviceToHost, S.copy_stream));
+    int rc = check_flag(S);             // synchronises the compute stream
+    HN_CUDA(cudaStreamSynchronize(S.copy_stream));
+    harvest_events(S);
+    return rc;
 }
 
 int hnumo_btp_bcl_coeffs(hnumo_handle_t h) {

@@ -126,6 +126,12 @@ struct Solver {
     void* nccl_comm = nullptr;
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // interior stage done / boundary stage + exchange done (btp_solve_pair)
+    // pipelined drop-in call (hnumo_ti_rk_bcl): host<->device copies on copy_stream overlapped with the step
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_pipe[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int pipe_wait_q = 0;               // bcl_step: q_df is still on its way (staged in q2), transpose it before the first layer kernel
+    double* pipe_qb_host = nullptr;    // bcl_step: download qb_df as soon as the corrector's barotropic solve is done
+    std::vector<std::pair<void*, size_t>> pinned_host;   // caller arrays page-locked by the library (cudaHostRegister)
     void* graph_exec = nullptr;   // CUDA graph of one cycle of the substep loop (see btp_solve_pair)
     int graph_key = -1, use_graph = -1;   // use_graph: -1 auto (on when the partition has no processor faces), 0 off, 1 on
     std::vector<cudaEvent_t> ev_pool;  // pairs (start, stop) around every barotropic stage loop / whole step

@@ -42,8 +42,31 @@ template <> struct PV<2> {
 // FMAs.  Loop order: contraction index outside, OUTPUT index inside -- consecutive FMAs belong to independent
 // accumulators (an FP64 FMA has ~8 cycles of dependent-issue latency; the chain-serial order costs 4x the pipe time).
 // out[i] = sum_n M(n,i) in[n], nodes -> quadrature points
+// High orders (nop 7, 8: 8x15 and 9x17 operators): the fully unrolled contraction of one line is 150 FMAs with as many
+// constant operands, and a stage kernel has a dozen of them inlined -- more code than the instruction cache holds (ncu, round 1:
+// 1.07 issue slots per instruction lost to no_instruction).  There the contraction index is a real loop: the line value is
+// loaded inside it and the operator row is addressed with the (warp-uniform) loop counter.
+#ifndef HN_ROLL_FROM_G
+#define HN_ROLL_FROM_G 99   // measured SLOWER at nop 8 (stage 5.70 vs 4.89 ms at 250 000 elements): kept for experiments only
+#endif
 template <int NE, int G, int Q, bool DERIV, int SS, int DS>
 __device__ __forceinline__ void pl_n2q(const typename PV<NE>::T* src, typename PV<NE>::T* dst) {
+    if constexpr (G >= HN_ROLL_FROM_G) {
+        double s[Q][NE];
+#pragma unroll
+        for (int i = 0; i < Q; ++i) { PR_FORC s[i][c] = 0.0; }
+        const double* op = DERIV ? c_ops.BT : c_ops.AT;
+#pragma unroll 1
+        for (int n = 0; n < G; ++n) {
+            double v[NE];
+            PV<NE>::ld(src + n * SS, v);
+#pragma unroll
+            for (int i = 0; i < Q; ++i) { PR_FORC s[i][c] = fma(op[i + Q * n], v[c], s[i][c]); }
+        }
+#pragma unroll
+        for (int i = 0; i < Q; ++i) PV<NE>::st(dst + i * DS, s[i]);
+        return;
+    }
     double in[G][NE], s[Q][NE];
 #pragma unroll
     for (int n = 0; n < G; ++n) PV<NE>::ld(src + n * SS, in[n]);
@@ -62,6 +85,21 @@ __device__ __forceinline__ void pl_n2q(const typename PV<NE>::T* src, typename P
 // acc[n] (+)= sum_i M(n,i) in[i], quadrature points -> nodes (weak-form transpose)
 template <int NE, int G, int Q, bool DERIV, int SS, bool FIRST>
 __device__ __forceinline__ void pl_q2n_acc(const typename PV<NE>::T* src, double (&acc)[G][NE]) {
+    if constexpr (G >= HN_ROLL_FROM_G) {
+        if (FIRST) {
+#pragma unroll
+            for (int n = 0; n < G; ++n) { PR_FORC acc[n][c] = 0.0; }
+        }
+        const double* op = DERIV ? c_ops.B : c_ops.A;
+#pragma unroll 1
+        for (int i = 0; i < Q; ++i) {
+            double v[NE];
+            PV<NE>::ld(src + i * SS, v);
+#pragma unroll
+            for (int n = 0; n < G; ++n) { PR_FORC acc[n][c] = fma(op[n + G * i], v[c], acc[n][c]); }
+        }
+        return;
+    }
     double in[Q][NE];
 #pragma unroll
     for (int i = 0; i < Q; ++i) PV<NE>::ld(src + i * SS, in[i]);
