@@ -62,7 +62,7 @@ class Desc(C.Structure):
 EXPORTS = ["hnumo_init", "hnumo_device_count", "hnumo_finalize", "hnumo_last_error", "hnumo_upload_state", "hnumo_download_state",
            "hnumo_step", "hnumo_ti_rk_bcl", "hnumo_btp_bcl_coeffs", "hnumo_btp_substeps", "hnumo_rhs_btp", "hnumo_layer_mass_rhs", "hnumo_layer_momentum_rhs", "hnumo_halo_exchange",
            "hnumo_get_array", "hnumo_diagnostics", "hnumo_snapshot_write", "hnumo_snapshot_info",
-           "hnumo_snapshot_read_restart", "hnumo_comm_get_unique_id", "hnumo_comm_init", "hnumo_timing", "hnumo_set_option"]
+           "hnumo_snapshot_read_restart", "hnumo_snapshot_write_nc", "hnumo_snapshot_read_nc_restart", "hnumo_comm_get_unique_id", "hnumo_comm_init", "hnumo_timing", "hnumo_set_option"]
 
 
 def load_library(path=None):
@@ -94,6 +94,10 @@ def load_library(path=None):
         L.hnumo_snapshot_info.argtypes = [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.hnumo_snapshot_read_restart.argtypes = [C.c_char_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                                                   C.c_void_p, C.c_void_p]
+        L.hnumo_snapshot_write_nc.argtypes = [C.c_char_p, C.c_int32, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+        L.hnumo_snapshot_read_nc_restart.argtypes = [C.c_char_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                                     C.c_void_p, C.c_void_p]
         L.hnumo_diagnostics.restype = C.c_int64
         L.hnumo_diagnostics.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.hnumo_comm_get_unique_id.argtypes = [C.c_void_p]
@@ -272,6 +276,31 @@ def snapshot_write(path, deck, q_df, qb_df):
                                 _ptr(zb), _ptr(al), deck["gravity"])
     if rc != 0:
         raise HnumoError("snapshot_write failed (%d): %s" % (rc, L.hnumo_last_error().decode()))
+
+
+def snapshot_write_nc(path, deck, q_df, qb_df):
+    """NetCDF snapshot `mlswe####.nc` with the layout of the reference's diagnostics_nc (src/diagnostics_nc.F90:98-165)."""
+    L = load_library()
+    q = np.ascontiguousarray(q_df, dtype=np.float64); qb = np.ascontiguousarray(qb_df, dtype=np.float64)
+    coord = np.ascontiguousarray(deck["coord"], dtype=np.float64)
+    zb = np.ascontiguousarray(deck["zbot_df"], dtype=np.float64); al = np.ascontiguousarray(deck["alpha_mlswe"], dtype=np.float64)
+    pbp = np.ascontiguousarray(deck["pbprime_df"], dtype=np.float64)
+    rc = L.hnumo_snapshot_write_nc(str(path).encode(), deck["nlayers"], deck["npoin"], deck["dt"], deck["dt_btp"], _ptr(coord), _ptr(q), _ptr(qb),
+                                   _ptr(zb), _ptr(al), _ptr(pbp), deck["gravity"])
+    if rc != 0:
+        raise HnumoError("snapshot_write_nc failed (%d): %s" % (rc, L.hnumo_last_error().decode()))
+
+
+def snapshot_read_nc_restart(path, deck):
+    """(q_df, qb_df, qprime_df, coord) rebuilt from a NetCDF snapshot, as restart_mlswe rebuilds them from the text one."""
+    L = load_library()
+    nl, npn = deck["nlayers"], deck["npoin"]
+    q = np.zeros((nl, npn, 3)); qb = np.zeros((npn, 4)); qp = np.zeros((nl, npn, 3)); coord = np.zeros((npn, 2))
+    pbp = np.ascontiguousarray(deck["pbprime_df"], dtype=np.float64); al = np.ascontiguousarray(deck["alpha_mlswe"], dtype=np.float64)
+    rc = L.hnumo_snapshot_read_nc_restart(str(path).encode(), nl, npn, _ptr(pbp), _ptr(al), deck["gravity"], _ptr(q), _ptr(qb), _ptr(qp), _ptr(coord))
+    if rc != 0:
+        raise HnumoError("snapshot_read_nc_restart failed (%d): %s" % (rc, L.hnumo_last_error().decode()))
+    return q, qb, qp, coord
 
 
 def snapshot_info(path):

@@ -174,6 +174,17 @@ int hnumo_snapshot_info(const char* path, int32_t* nlayers, int64_t* npoin, doub
 int hnumo_snapshot_read_restart(const char* path, int32_t nlayers, int64_t npoin, const double* pbprime_df, const double* alpha_mlswe,
                                 double gravity, double* q_df, double* qb_df, double* qprime_df, double* coord_out);
 
+/* NetCDF snapshots (classic 64-bit-offset format, written and read without a NetCDF library): the file of
+ * src/diagnostics_nc.F90:98-165 -- dimensions time (unlimited), npoin, nlayers, zi; variables dt, dt_btp (time), x, y, pb, pbub, pbvb
+ * (npoin), h, u, v (nlayers, npoin), eta (zi, npoin) with the reference's names and attributes.  pbprime_df(npoin) gives
+ * eta(:,1) = pb / pbprime - 1.  hnumo_snapshot_read_nc_restart rebuilds q_df, qb_df, qprime_df from such a file the way restart_mlswe
+ * does from the text snapshot.  Same return codes as the text functions. */
+int hnumo_snapshot_write_nc(const char* path, int32_t nlayers, int64_t npoin, double dt, double dt_btp, const double* coord,
+                            const double* q_df, const double* qb_df, const double* zbot_df, const double* alpha_mlswe,
+                            const double* pbprime_df, double gravity);
+int hnumo_snapshot_read_nc_restart(const char* path, int32_t nlayers, int64_t npoin, const double* pbprime_df, const double* alpha_mlswe,
+                                   double gravity, double* q_df, double* qb_df, double* qprime_df, double* coord_out);
+
 /* ---- measurement ------------------------------------------------------------------------------ */
 /* out[0] = GPU ms spent in barotropic stages since the last reset (CUDA events on the compute stream),
  * out[1] = number of barotropic stages, out[2] = GPU ms in whole steps, out[3] = steps,

@@ -235,6 +235,77 @@ def test_snapshot_roundtrip_and_restart(tmp_path):
         hn.snapshot_info(tmp_path / "missing")
 
 
+def test_netcdf_snapshot_layout_and_restart(tmp_path):
+    """SURVEY 8(f) rank 3, NetCDF layout: hnumo_snapshot_write_nc writes the file of src/diagnostics_nc.F90:98-165 (classic format with
+    64-bit offsets, no NetCDF library); an independent reader (scipy.io.netcdf_file) must see the reference's dimensions, variable
+    names, attributes and values, and hnumo_snapshot_read_nc_restart must rebuild the state like restart_mlswe does."""
+    import numpy as np
+    from scipy.io import netcdf_file
+
+    p = hn.decks.synthetic_double_gyre(3, 2, nop=4, nlayers=3)
+    deck = hn.decks.build_deck(p)
+    rng = np.random.default_rng(11)
+    q = deck["q_df"].copy(); qb = deck["qb_df"].copy()
+    for k in range(3):
+        q[k, :, 0] *= 1.0 + 1e-3 * rng.normal(0.0, 1.0, deck["npoin"])
+        q[k, :, 1] = q[k, :, 0] * rng.normal(0.0, 0.3, deck["npoin"])
+        q[k, :, 2] = q[k, :, 0] * rng.normal(0.0, 0.3, deck["npoin"])
+    qb[:, 0] = q[:, :, 0].sum(axis=0); qb[:, 1] = qb[:, 0] - deck["pbprime_df"]
+    qb[:, 2] = q[:, :, 1].sum(axis=0); qb[:, 3] = q[:, :, 2].sum(axis=0)
+    path = tmp_path / "mlswe0003.nc"
+    hn.snapshot_write_nc(path, deck, q, qb)
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"CDF\x02"                                   # nf90_64bit_offset
+    npn, nl, g, al = deck["npoin"], 3, deck["gravity"], deck["alpha_mlswe"]
+    f = netcdf_file(str(path), "r", mmap=False)
+    try:
+        assert list(f.dimensions.keys()) == ["time", "npoin", "nlayers", "zi"]
+        assert f.dimensions["time"] is None and f.dimensions["npoin"] == npn and f.dimensions["nlayers"] == nl and f.dimensions["zi"] == nl + 1
+        assert f.filename if hasattr(f, "filename") else True
+        assert f._attributes["filename"] == b"mlswe0003.nc" and f._attributes["zi"] == b"Number of interfaces"
+        assert list(f.variables.keys()) == ["dt", "dt_btp", "x", "y", "pb", "pbub", "pbvb", "h", "u", "v", "eta"]
+        v = f.variables
+        assert v["dt"].dimensions == ("time",) and v["h"].dimensions == ("nlayers", "npoin") and v["eta"].dimensions == ("zi", "npoin")
+        assert v["dt"].units == b"seconds" and v["h"].name == b"Layer thickness" and v["x"].axis == b"X"
+        assert v["pb"].units == "N/m\u00b2".encode() and v["pbub"].units == "kg\u00b7m/s".encode()
+        assert v["dt"][:].shape == (1,) and v["dt"][0] == deck["dt"] and v["dt_btp"][0] == deck["dt_btp"]
+        assert np.array_equal(v["x"][:], deck["coord"][:, 0]) and np.array_equal(v["y"][:], deck["coord"][:, 1])
+        assert np.array_equal(v["pb"][:], qb[:, 0]) and np.array_equal(v["pbub"][:], qb[:, 2]) and np.array_equal(v["pbvb"][:], qb[:, 3])
+        h = np.stack([(al[k] / g) * q[k, :, 0] for k in range(nl)])
+        assert np.array_equal(v["h"][:], h)
+        assert np.array_equal(v["u"][:], q[:, :, 1] / q[:, :, 0]) and np.array_equal(v["v"][:], q[:, :, 2] / q[:, :, 0])
+        eta = v["eta"][:]
+        assert np.array_equal(eta[nl], deck["zbot_df"])
+        z = deck["zbot_df"].copy()
+        for k in range(nl - 1, 0, -1):                               # mslwe_elevation, diagnostics_nc.F90:59-63
+            z = z + h[k]
+            assert np.array_equal(eta[k], z)
+        assert np.allclose(eta[0], qb[:, 0] / deck["pbprime_df"] - 1.0, rtol=0, atol=4e-16)
+    finally:
+        f.close()
+    q2, qb2, qp2, coord = hn.snapshot_read_nc_restart(path, deck)
+    assert np.array_equal(coord, deck["coord"]) and np.array_equal(qb2[:, [0, 2, 3]], qb[:, [0, 2, 3]])
+    assert np.array_equal(qb2[:, 1], qb2[:, 0] - deck["pbprime_df"])
+    assert np.allclose(q2, q, rtol=4e-16, atol=0)                    # binary doubles: only the h <-> dp scaling rounds
+    ope = q2[:, :, 0].sum(axis=0) / deck["pbprime_df"]
+    for k in range(nl):
+        assert np.allclose(qp2[k, :, 0], q2[k, :, 0] / ope, rtol=1e-15)
+        assert np.allclose(qp2[k, :, 2], q2[k, :, 2] / q2[k, :, 0] - qb2[:, 3] / qb2[:, 0], rtol=1e-13, atol=1e-15)
+    # the text and the NetCDF snapshots hold the same fields
+    tpath = tmp_path / "mlswe0003"
+    hn.snapshot_write(tpath, deck, q, qb)
+    q3, qb3, _, _ = hn.snapshot_read_restart(tpath, deck)
+    assert np.allclose(q3, q2, rtol=4e-15, atol=1e-12) and np.allclose(qb3, qb2, rtol=4e-15, atol=1e-6)
+    # error behaviour
+    other = hn.decks.build_deck(hn.decks.synthetic_double_gyre(2, 2, nop=4, nlayers=3))
+    with pytest.raises(hn.HnumoError, match="-8"):
+        hn.snapshot_read_nc_restart(path, other)
+    with pytest.raises(hn.HnumoError, match="-7"):
+        hn.snapshot_read_nc_restart(tpath, deck)
+    with pytest.raises(hn.HnumoError, match="-6"):
+        hn.snapshot_read_nc_restart(tmp_path / "missing.nc", deck)
+
+
 def test_fortran_d23_16_formatting(tmp_path):
     """corner cases of the d23.16 writer / reader: zero, negative, tiny, huge (three-digit exponents drop the letter)"""
     import numpy as np
