@@ -26,19 +26,30 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-shared", "-diag-suppress", "177,550"]
 
 
-def build_library(force=False, verbose=False):
-    """nvcc cross-compile of the single translation unit into h-numo_b200/libhnumo_b200.so (in-tree)."""
+EXACT_LIB_PATH = os.path.join(_HERE, "libhnumo_b200_exact.so")
+
+
+def build_library(force=False, verbose=False, exact=False):
+    """nvcc cross-compile of the single translation unit into h-numo_b200/libhnumo_b200.so (in-tree).
+
+    exact=True builds the measurement aid libhnumo_b200_exact.so instead: the same sources with the two deliberate arithmetic
+    deviations of the stage kernel switched off (-DHN_EXACT_DIV: IEEE division instead of rcp.approx + 2 Newton steps;
+    -DHN_NO_GZ_FLUSH: grad(z_bot) kept as computed).  tests/test_gpu_acceptance.py loads it next to the default build."""
     src = os.path.join(_HERE, "csrc", "hnumo_b200.cu")
+    out = EXACT_LIB_PATH if exact else LIB_PATH
     deps = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))]
     deps.append(os.path.join(_ROOT, "include", "hnumo_b200.h"))
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
-        return LIB_PATH
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, src, "-lpthread", "-ldl"]
+    cmd = [nvcc] + NVCC_FLAGS + (["-DHN_EXACT_DIV", "-DHN_NO_GZ_FLUSH"] if exact else []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, src, "-lpthread", "-ldl"]
     env = dict(os.environ)
     env.pop("CXX", None); env.pop("CC", None)
-    subprocess.check_call(cmd, env=env)
-    return LIB_PATH
+    r = subprocess.run(cmd, env=env, stderr=None if verbose else subprocess.PIPE, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stderr or "")
+        raise subprocess.CalledProcessError(r.returncode, cmd)
+    return out
 
 
 class Desc(C.Structure):
@@ -56,11 +67,12 @@ class Desc(C.Structure):
         ("rank", C.c_int32), ("nranks", C.c_int32), ("num_nbh", C.c_int32),
         ("nbh_proc", C.c_void_p), ("num_send_recv", C.c_void_p), ("nbh_send_recv", C.c_void_p),
         ("device", C.c_int32), ("stage_kernel_variant", C.c_int32),
+        ("max_shear_dz", C.c_double),
     ]
 
 
 EXPORTS = ["hnumo_init", "hnumo_device_count", "hnumo_finalize", "hnumo_last_error", "hnumo_upload_state", "hnumo_download_state",
-           "hnumo_step", "hnumo_ti_rk_bcl", "hnumo_btp_bcl_coeffs", "hnumo_btp_substeps", "hnumo_rhs_btp", "hnumo_layer_mass_rhs", "hnumo_layer_momentum_rhs", "hnumo_halo_exchange",
+           "hnumo_step", "hnumo_ti_rk_bcl", "hnumo_btp_bcl_coeffs", "hnumo_btp_substeps", "hnumo_rhs_btp", "hnumo_layer_mass_rhs", "hnumo_layer_momentum_rhs", "hnumo_layer_shear_stress", "hnumo_halo_exchange",
            "hnumo_get_array", "hnumo_diagnostics", "hnumo_snapshot_write", "hnumo_snapshot_info",
            "hnumo_snapshot_read_restart", "hnumo_snapshot_write_nc", "hnumo_snapshot_read_nc_restart", "hnumo_comm_get_unique_id", "hnumo_comm_init", "hnumo_timing", "hnumo_set_option"]
 
@@ -85,6 +97,7 @@ def load_library(path=None):
         L.hnumo_rhs_btp.argtypes = [C.c_void_p, C.c_void_p]
         L.hnumo_layer_mass_rhs.argtypes = [C.c_void_p, C.c_void_p]
         L.hnumo_layer_momentum_rhs.argtypes = [C.c_void_p, C.c_void_p]
+        L.hnumo_layer_shear_stress.argtypes = [C.c_void_p, C.c_void_p]
         L.hnumo_halo_exchange.restype = C.c_int64
         L.hnumo_halo_exchange.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.hnumo_get_array.restype = C.c_int64
@@ -120,7 +133,7 @@ class Solver:
         self.deck = deck
         self._keep = []
         d = Desc()
-        d.abi_version = 1
+        d.abi_version = 2
         for k in ("nelem", "ngl", "nq", "nlayers", "nface", "kstages", "N_btp", "botfr", "method_visc", "rank", "nranks"):
             setattr(d, k, int(deck[k]))
         for k in ("dt", "dt_btp", "gravity", "cd_mlswe", "visc_mlswe", "ad_mlswe"):
@@ -146,6 +159,7 @@ class Solver:
         d.nbh_send_recv = ptr(deck["nbh_send_recv"], np.int32) if d.num_nbh else None
         d.device = device
         d.stage_kernel_variant = variant
+        d.max_shear_dz = float(deck.get("max_shear_dz", 0.0))
         self.h = C.c_void_p()
         rc = self.L.hnumo_init(C.byref(d), C.byref(self.h))
         if rc != 0:
@@ -210,6 +224,12 @@ class Solver:
         """rhs_mom[k, I, 0:2] of layer_momentum_rhs on the resident state (per-phase entry)"""
         out = np.empty((self.nl, self.npoin, 2))
         self._check(self.L.hnumo_layer_momentum_rhs(self.h, out.ctypes.data), "layer_momentum_rhs")
+        return out
+
+    def layer_shear_stress(self):
+        """rhs_stress[k, I, 0:2] of rhs_layer_shear_stress on the resident q_df (per-phase entry, ad_mlswe > 0)"""
+        out = np.empty((self.nl, self.npoin, 2))
+        self._check(self.L.hnumo_layer_shear_stress(self.h, out.ctypes.data), "layer_shear_stress")
         return out
 
     def halo_exchange(self, nodal):

@@ -850,6 +850,188 @@ __global__ void k_mom_faces_update(MomFaceArgs a) {
 }
 
 // --------------------------------------------------------------------------------------------------------------
+// Vertical shear stress between the layers (ad_mlswe > 0) + the momentum update it sits in
+// (mod_splitting.F90:139-179 / 247-286, mod_create_rhs_mlswe.F90:146-279, mod_layer_terms.F90:139-196).
+// Runs instead of the update epilogue of k_mom_faces_update (which is launched with rhs_only = 1 and leaves the complete
+// rhs_mom in `rhs`): per element
+//   A. nodes:  q_df_temp = q + dt rhs_mom; q_df3 = Coriolis rotation of it; velocity_df (velocities reconciled with the
+//              barotropic velocity, momentum rebuilt);
+//   B. quadrature points: dp, udp, vdp of every layer interpolated; the tridiagonal system of the implicit shear stress
+//              as written (sub-diagonal -coeff, super-diagonal -coeff1, right-hand side u = udp/dp); tau at the interfaces;
+//   C. nodes:  rhs_stress = sum_q wq psi tau_q (no mass matrix inside), q_df_temp += dt massinv rhs_stress, then the
+//              rotation, the wall projection and evaluate_bcl(_v1) exactly like the epilogue of k_mom_faces_update.
+// Two values the reference leaves undefined are set to the evident intent (parity hazards 2 and 3): the stress
+// through the bottom interface tau(nlayers+1) = 0, and the corrector (`momentum`) uses q_df3 like the predictor does.
+// One block per element, run-time sizes (optional physics: not on the benchmark path).
+struct ShearArgs {
+    Mesh M;
+    const double* q_in;     // [3*nl] q_df before the step: momentum planes are read
+    double* q;              // [3*nl] thickness planes read (already updated), momentum planes written (may alias q_in)
+    double* qprime_out;     // [3*nl]
+    size_t nstride;
+    const double* qb[3];    // pbpert, mx, my of the barotropic state
+    const double* pbprime_df;
+    const double* rhs;      // [2*nl] rhs_mom = massinv (volume + faces) + rhs_visc
+    const double *massinv, *a_bcl, *b_bcl, *fdt2, *coriolis_q;
+    double alpha0, g, dt, ad, max_shear_dz;
+    int full_prime;
+    // per-phase entry hnumo_layer_shear_stress: rhs_layer_shear_stress of q itself -> stress_out [2*nl], nothing else
+    int stress_only;
+    double* stress_out;
+};
+__global__ void k_shear_update(ShearArgs a) {
+    extern __shared__ double sm[];
+    const int ngl = a.M.ngl, nq = a.M.nq, npts = ngl * ngl, nq2 = nq * nq, nl = a.M.nl;
+    constexpr int LMAX = HN_MAXL;
+    const int e = blockIdx.x, tid = threadIdx.x;
+    SOps o = load_sops(sm, ngl, nq);
+    double* s3 = sm + sops_doubles(ngl, nq);   // [3][nl][npts]: dp, udp, vdp of q_df3 after velocity_df
+    double* st = s3 + 3 * nl * npts;           // [2][nl][npts]: q_df_temp
+    double* tq = st + 2 * nl * npts;           // [2][nl][nq2]: wq * gravity * (tau(k) - tau(k+1))
+    const size_t nbase = (size_t)e * npts, qbase = (size_t)e * nq2;
+    const double J = a.M.em[e * 5 + 4];
+    __syncthreads();
+    if (a.stress_only) {
+        for (int t = tid; t < 3 * nl * npts; t += blockDim.x) { const int vk = t / npts; s3[t] = a.q[(size_t)vk * a.nstride + nbase + (t - vk * npts)]; }
+    } else
+    for (int t = tid; t < npts; t += blockDim.x) {
+        const double f2 = a.fdt2[nbase + t], ab = a.a_bcl[nbase + t], bb = a.b_bcl[nbase + t];
+        const double pb = a.qb[0][nbase + t] + a.pbprime_df[nbase + t];
+        const double mbx = a.qb[1][nbase + t], mby = a.qb[2][nbase + t];
+        double dpk[LMAX], uk[LMAX], vk[LMAX];
+        double ubar = 0.0, vbar = 0.0;
+        for (int k = 0; k < nl; ++k) {
+            const double mxo = a.q_in[(size_t)(1 * nl + k) * a.nstride + nbase + t], myo = a.q_in[(size_t)(2 * nl + k) * a.nstride + nbase + t];
+            const double t1 = mxo + a.dt * a.rhs[(size_t)(0 * nl + k) * a.nstride + nbase + t];
+            const double t2 = myo + a.dt * a.rhs[(size_t)(1 * nl + k) * a.nstride + nbase + t];
+            st[(0 * nl + k) * npts + t] = t1; st[(1 * nl + k) * npts + t] = t2;
+            const double tempu = t1 + f2 * myo, tempv = t2 - f2 * mxo;
+            const double m3x = ab * tempu + bb * tempv, m3y = -bb * tempu + ab * tempv;
+            dpk[k] = a.q[(size_t)(0 * nl + k) * a.nstride + nbase + t];
+            uk[k] = m3x / dpk[k]; vk[k] = m3y / dpk[k];
+        }
+        for (int k = 0; k < nl; ++k) { ubar = ubar + uk[k] * dpk[k]; vbar = vbar + vk[k] * dpk[k]; }
+        if (pb > 0.0) {
+            ubar = ubar / pb; vbar = vbar / pb;
+            for (int k = 0; k < nl; ++k) { uk[k] = uk[k] - ubar + mbx / pb; vk[k] = vk[k] - vbar + mby / pb; }
+        } else {
+            for (int k = 0; k < nl; ++k) { uk[k] = 0.0; vk[k] = 0.0; }
+        }
+        for (int k = 0; k < nl; ++k) {
+            s3[(0 * nl + k) * npts + t] = dpk[k]; s3[(1 * nl + k) * npts + t] = uk[k] * dpk[k]; s3[(2 * nl + k) * npts + t] = vk[k] * dpk[k];
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < nq2; t += blockDim.x) {
+        const int j = t / nq, i = t - j * nq;
+        double dp[LMAX], u[LMAX], v[LMAX], b[LMAX], tu[LMAX + 1], tv[LMAX + 1];
+        for (int k = 0; k < nl; ++k) {
+            double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+            for (int m = 0; m < ngl; ++m)
+                for (int n = 0; n < ngl; ++n) {
+                    const double hi = o.A[n + ngl * i] * o.A[m + ngl * j];
+                    d0 = d0 + hi * s3[(0 * nl + k) * npts + m * ngl + n];
+                    d1 = d1 + hi * s3[(1 * nl + k) * npts + m * ngl + n];
+                    d2 = d2 + hi * s3[(2 * nl + k) * npts + m * ngl + n];
+                }
+            dp[k] = d0; u[k] = d1 / d0; v[k] = d2 / d0;
+        }
+        const double coeff = fmax(sqrt(0.5 * a.coriolis_q[qbase + t] * a.ad) / a.alpha0, a.ad / (a.alpha0 * a.max_shear_dz));
+        const double coeff1 = a.g * a.dt * coeff;
+        // a(k) = -coeff (k > 1), c(k) = -coeff1 (k < nl), b(k) = dp(k) + 2 coeff1, b(1) and b(nl) = dp + coeff1
+        for (int k = 0; k < nl; ++k) b[k] = dp[k] + 2.0 * coeff1;
+        b[0] = dp[0] + coeff1;
+        b[nl - 1] = dp[nl - 1] + coeff1;
+        for (int k = 1; k < nl; ++k) {
+            const double mult = -coeff / b[k - 1];
+            const double ckm = (k - 1 == nl - 1) ? 0.0 : -coeff1;
+            b[k] = b[k] - mult * ckm;
+            u[k] = u[k] - mult * u[k - 1];
+            v[k] = v[k] - mult * v[k - 1];
+        }
+        u[nl - 1] = u[nl - 1] / b[nl - 1];
+        v[nl - 1] = v[nl - 1] / b[nl - 1];
+        for (int k = nl - 2; k >= 0; --k) {
+            u[k] = (u[k] - (-coeff1) * u[k + 1]) / b[k];
+            v[k] = (v[k] - (-coeff1) * v[k + 1]) / b[k];
+        }
+        tu[0] = 0.0; tv[0] = 0.0;
+        for (int k = 1; k < nl; ++k) { tu[k] = coeff * (u[k - 1] - u[k]); tv[k] = coeff * (v[k - 1] - v[k]); }
+        tu[nl] = 0.0; tv[nl] = 0.0;
+        const double wq = o.wq[i] * o.wq[j] * J;
+        for (int k = 0; k < nl; ++k) {
+            tq[(0 * nl + k) * nq2 + t] = wq * (a.g * (tu[k] - tu[k + 1]));
+            tq[(1 * nl + k) * nq2 + t] = wq * (a.g * (tv[k] - tv[k + 1]));
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < npts; t += blockDim.x) {
+        const int m = t / ngl, n = t - m * ngl;
+        const double mi = a.massinv[nbase + t];
+        const double f2 = a.fdt2[nbase + t], ab = a.a_bcl[nbase + t], bb = a.b_bcl[nbase + t];
+        double qd[LMAX], qx[LMAX], qy[LMAX];
+        for (int k = 0; k < nl; ++k) {
+            double r0 = 0.0, r1 = 0.0;
+            for (int j = 0; j < nq; ++j)
+                for (int i = 0; i < nq; ++i) {
+                    const double hi = o.A[n + ngl * i] * o.A[m + ngl * j];
+                    r0 = r0 + hi * tq[(0 * nl + k) * nq2 + j * nq + i];
+                    r1 = r1 + hi * tq[(1 * nl + k) * nq2 + j * nq + i];
+                }
+            if (a.stress_only) {
+                a.stress_out[(size_t)(0 * nl + k) * a.nstride + nbase + t] = r0;
+                a.stress_out[(size_t)(1 * nl + k) * a.nstride + nbase + t] = r1;
+                qd[k] = 1.0; qx[k] = 0.0; qy[k] = 0.0;
+                continue;
+            }
+            const double t1 = st[(0 * nl + k) * npts + t] + a.dt * (mi * r0);
+            const double t2 = st[(1 * nl + k) * npts + t] + a.dt * (mi * r1);
+            const double mxo = a.q_in[(size_t)(1 * nl + k) * a.nstride + nbase + t], myo = a.q_in[(size_t)(2 * nl + k) * a.nstride + nbase + t];
+            const double tempu = t1 + f2 * myo, tempv = t2 - f2 * mxo;
+            double mxn = ab * tempu + bb * tempv, myn = -bb * tempu + ab * tempv;
+            for (int s = 0; s < 4; ++s) {   // wall projection (layer_mom_boundary_df)
+                const bool on = (s == 0) ? (m == 0) : (s == 1) ? (m == ngl - 1) : (s == 2) ? (n == 0) : (n == ngl - 1);
+                if (!on) continue;
+                const int slot = e * 4 + s, nb = a.M.nbr[slot];
+                if (nb == NBR_FREESLIP) {
+                    const double nx = a.M.fgeom[slot * 3], ny = a.M.fgeom[slot * 3 + 1];
+                    const double up = mxn * nx + myn * ny;
+                    mxn = mxn - up * nx; myn = myn - up * ny;
+                } else if (nb == NBR_NOSLIP) { mxn = 0.0; myn = 0.0; }
+            }
+            qd[k] = s3[(0 * nl + k) * npts + t]; qx[k] = mxn; qy[k] = myn;
+        }
+        if (a.stress_only) continue;
+        // evaluate_bcl / evaluate_bcl_v1: two passes of extract_velocity
+        const double pb = a.qb[0][nbase + t] + a.pbprime_df[nbase + t];
+        const double mbx = a.qb[1][nbase + t], mby = a.qb[2][nbase + t];
+        double uk[LMAX], vk[LMAX];
+        for (int pass = 0; pass < 2; ++pass) {
+            double ubar = 0.0, vbar = 0.0;
+            for (int k = 0; k < nl; ++k) { uk[k] = qx[k] / qd[k]; vk[k] = qy[k] / qd[k]; }
+            for (int k = 0; k < nl; ++k) { ubar = ubar + uk[k] * qd[k]; vbar = vbar + vk[k] * qd[k]; }
+            if (pb > 0.0) {
+                ubar = ubar / pb; vbar = vbar / pb;
+                for (int k = 0; k < nl; ++k) { uk[k] = uk[k] - ubar + mbx / pb; vk[k] = vk[k] - vbar + mby / pb; }
+            } else {
+                for (int k = 0; k < nl; ++k) { uk[k] = 0.0; vk[k] = 0.0; }
+            }
+            if (pass == 0) for (int k = 0; k < nl; ++k) { qx[k] = uk[k] * qd[k]; qy[k] = vk[k] * qd[k]; }
+        }
+        double ope = 0.0;
+        for (int k = 0; k < nl; ++k) ope = ope + qd[k];
+        ope = ope / a.pbprime_df[nbase + t];
+        for (int k = 0; k < nl; ++k) {
+            a.q[(size_t)(1 * nl + k) * a.nstride + nbase + t] = qx[k];
+            a.q[(size_t)(2 * nl + k) * a.nstride + nbase + t] = qy[k];
+            if (a.full_prime) a.qprime_out[(size_t)(0 * nl + k) * a.nstride + nbase + t] = qd[k] / ope;
+            a.qprime_out[(size_t)(1 * nl + k) * a.nstride + nbase + t] = uk[k] - mbx / pb;
+            a.qprime_out[(size_t)(2 * nl + k) * a.nstride + nbase + t] = vk[k] - mby / pb;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------
 // small pointwise kernels
 // out = 0.5*(x + y)   (ti_rk_bcl.F90:64-66)
 __global__ void k_average(double* out, const double* x, const double* y, size_t n) {

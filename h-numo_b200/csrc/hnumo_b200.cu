@@ -623,11 +623,26 @@ static int momentum_update(Solver& S, const Planes& qprime_in, const Planes& dpv
     for (int k = 0; k < S.nl; ++k) f.alpha[k] = S.alpha[k];
     f.g = S.g; f.dt = S.dt; f.full_prime = full_prime;
     f.rhs_only = rhs_only_out != nullptr; f.rhs_out = rhs_only_out;
+    const bool shear = S.ad > 0.0 && rhs_only_out == nullptr;   // vertical shear stress: the update moves to k_shear_update
+    if (shear) { f.rhs_only = 1; f.rhs_out = S.rhs_full.p; }
     sm = (sops_doubles_host(S.ngl, S.nq) + 24 * (size_t)S.nl * S.ngl + 8 * (size_t)S.nl * S.nq) * sizeof(double);
     if (use_layer_warp(S, 32))
         HN_LAUNCH_LW(k_mom_faces_update_w, (LW_WARPS * sizeof(double) * lw_mface_doubles<5, 9>(S.nl)), (LW_WARPS * sizeof(double) * lw_mface_doubles<4, 7>(S.nl)), S, f);
     else HN_LAUNCH_GQL(k_mom_faces_update, S, sm, f);
     S.n_launches++;
+    if (shear) {
+        if (phase_check(S, "k_mom_faces_update (rhs)")) return -1;
+        ShearArgs h; memset(&h, 0, sizeof(h));
+        h.M = S.mesh; h.q_in = q_in.p; h.q = q.p; h.qprime_out = qprime_out.p; h.nstride = q.stride;
+        for (int i = 0; i < 3; ++i) h.qb[i] = qb[i];
+        h.pbprime_df = S.pbprime_df; h.rhs = S.rhs_full.p; h.massinv = S.massinv; h.a_bcl = S.a_bcl; h.b_bcl = S.b_bcl; h.fdt2 = S.fdt2;
+        h.coriolis_q = S.coriolis_q; h.alpha0 = S.alpha[0]; h.g = S.g; h.dt = S.dt; h.ad = S.ad; h.max_shear_dz = S.max_shear_dz;
+        h.full_prime = full_prime;
+        const size_t smh = (sops_doubles_host(S.ngl, S.nq) + 5 * (size_t)S.nl * S.npts + 2 * (size_t)S.nl * S.nq2) * sizeof(double);
+        smem_opt_in(k_shear_update, smh);
+        k_shear_update<<<S.nelem, threads_for(S), smh, S.stream>>>(h);
+        S.n_launches++;
+    }
     return 0;
 }
 
@@ -760,8 +775,12 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     if (d->ngl < 2 || d->ngl > HN_MAXNGL || d->nq > HN_MAXNQ || d->nlayers < 1 || d->nlayers > HN_MAXL || d->kstages < 1 || d->kstages > 5) {
         set_error("hnumo_init", "unsupported sizes (ngl<=9, nq<=17, nlayers<=20, kstages<=5)"); return -2;
     }
-    if (d->method_visc == 1 || d->ad_mlswe > 0.0) {
-        set_error("hnumo_init", "method_visc==1 and ad_mlswe>0 are not implemented (SURVEY 8(f) rank 4)"); return -3;
+    if (d->method_visc == 1) {
+        set_error("hnumo_init", "method_visc==1 (quadrature-point viscosity) is not implemented (SURVEY 8(f) rank 4)"); return -3;
+    }
+    if (d->ad_mlswe > 0.0 && !(d->max_shear_dz > 0.0)) {
+        // mod_create_rhs_mlswe.F90:204-205 divides by max_shear_dz (namelist default 0): the reference would work with an infinite coefficient
+        set_error("hnumo_init", "ad_mlswe > 0 needs max_shear_dz > 0"); return -2;
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("hnumo_init", "no CUDA device: this library has no CPU fallback"); return -1; }
@@ -782,6 +801,7 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     S.npoin = S.nelem * S.npts; S.npoin_q = S.nelem * S.nq2; S.nslots = S.nelem * 4;
     S.kstages = d->kstages; S.N_btp = d->N_btp; S.botfr = d->botfr; S.dt = d->dt; S.dt_btp = d->dt_btp; S.g = d->gravity; S.cd = d->cd_mlswe;
     S.visc = d->visc_mlswe; S.has_visc = (d->visc_mlswe != 0.0);
+    S.ad = d->ad_mlswe > 0.0 ? d->ad_mlswe : 0.0; S.max_shear_dz = d->max_shear_dz;
     if (getenv("HNUMO_FORCE_VISC")) S.has_visc = 1;   // debugging aid: run the LDG code path with visc == 0
     S.variant = d->stage_kernel_variant;
     for (int k = 0; k < S.nl; ++k) S.alpha[k] = d->alpha_mlswe[k];
@@ -917,6 +937,7 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     S.slmf_q = palloc(S, 2, NQ); S.slmf_f = palloc(S, 2, NS);
     S.rhs_mom = palloc(S, std::max(3, 2 * nl), NP);   // also the 3-plane scratch of hnumo_rhs_btp
     S.rhs_visc = palloc(S, 2 * nl, NP);
+    if (S.ad > 0.0) S.rhs_full = palloc(S, 2 * nl, NP);   // complete rhs_mom, handed from k_mom_faces_update to k_shear_update
     S.stage_buf = dalloc(S, std::max((size_t)3 * nl * NP, 4 * NP));
     size_t hs = (size_t)std::max(S.nhalo, 1) * S.ngl;
     S.h_q = palloc(S, 3 * nl, hs); S.h_dp = palloc(S, nl, hs); S.h_dpv = palloc(S, nl, hs); S.h_dpg = palloc(S, 4 * nl, hs);
@@ -1127,6 +1148,28 @@ int hnumo_layer_momentum_rhs(hnumo_handle_t h, double* rhs_mom) {
     k_planes_to_aos<<<nblk(NP), 256, 0, S.stream>>>(S.stage_buf, S.rhs_mom.p, 2, 0, 2, S.nl, NP, NP);
     S.n_launches++;
     HN_CUDA(cudaMemcpyAsync(rhs_mom, S.stage_buf, 2 * S.nl * NP * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+    HN_CUDA(cudaStreamSynchronize(S.stream));
+    return 0;
+}
+
+// rhs_layer_shear_stress(rhs_stress, q_df) of the resident q_df (mod_create_rhs_mlswe.F90:146-279): rhs_stress(2,npoin,nlayers),
+// without the inverse mass matrix, as the reference routine returns it
+int hnumo_layer_shear_stress(hnumo_handle_t h, double* rhs_stress) {
+    HN_ENTER(h);
+    if (!rhs_stress) return -2;
+    if (!(S.ad > 0.0)) { set_error("hnumo_layer_shear_stress", "ad_mlswe is 0"); return -2; }
+    const size_t NP = S.npoin;
+    ShearArgs a; memset(&a, 0, sizeof(a));
+    a.M = S.mesh; a.q_in = S.q.p; a.q = S.q.p; a.nstride = S.q.stride; a.coriolis_q = S.coriolis_q; a.massinv = S.massinv;
+    a.alpha0 = S.alpha[0]; a.g = S.g; a.dt = S.dt; a.ad = S.ad; a.max_shear_dz = S.max_shear_dz;
+    a.stress_only = 1; a.stress_out = S.rhs_full.p;
+    const size_t sm = (sops_doubles_host(S.ngl, S.nq) + 5 * (size_t)S.nl * S.npts + 2 * (size_t)S.nl * S.nq2) * sizeof(double);
+    smem_opt_in(k_shear_update, sm);
+    k_shear_update<<<S.nelem, threads_for(S), sm, S.stream>>>(a);
+    S.n_launches++;
+    k_planes_to_aos<<<nblk(NP), 256, 0, S.stream>>>(S.stage_buf, S.rhs_full.p, 2, 0, 2, S.nl, NP, NP);
+    S.n_launches++;
+    HN_CUDA(cudaMemcpyAsync(rhs_stress, S.stage_buf, 2 * S.nl * NP * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
     HN_CUDA(cudaStreamSynchronize(S.stream));
     return 0;
 }

@@ -69,6 +69,7 @@ struct Solver {
     int nelem, ngl, nq, npts, nq2, nl, nface, npoin, npoin_q, nslots;
     int kstages, N_btp, botfr, has_visc;
     double dt, dt_btp, g, cd, visc;
+    double ad = 0.0, max_shear_dz = 0.0;   // vertical shear stress between the layers (0 = off)
     double ssprk_a[5][3], ssprk_beta[5], alpha[HN_MAXL];
     int variant = 0;
     // host copies of the face table (for reference-layout output) : face f -> owner slot, right slot (or -1)
@@ -111,6 +112,7 @@ struct Solver {
     Planes slmf_q;  // 2 quad: sum_layer_mass_flux
     Planes slmf_f;  // 2 slot: sum_layer_mass_flux_face
     Planes rhs_mom, rhs_visc;  // 2*nl nodal planes each
+    Planes rhs_full;           // 2*nl, only when ad > 0
     double* stage_buf = nullptr;  // AoS staging for upload/download
     // halo copies of neighbour nodal traces on processor faces: [plane][nhalo*ngl]
     Planes h_q, h_dp, h_dpv, h_dpg, h_gub, h_stat;

@@ -371,7 +371,7 @@ def build_deck(params, rank=0, nranks=1):
     deck = dict(
         nelem=nelem, ngl=ngl, nq=nq, nlayers=nl, nface=nface, kstages=ks, N_btp=N_btp, dt=float(p["dt"]), dt_btp=dt_btp,
         botfr=p.get("botfr", 0), method_visc=p.get("method_visc", 0), gravity=g, cd_mlswe=p.get("cd_mlswe", 0.0),
-        visc_mlswe=p.get("visc_mlswe", 0.0), ad_mlswe=0.0,
+        visc_mlswe=p.get("visc_mlswe", 0.0), ad_mlswe=p.get("ad_mlswe", 0.0), max_shear_dz=p.get("max_shear_dz", 0.0),
         psiq=np.asfortranarray(B["psiq"]), dpsiq=np.asfortranarray(B["dpsiq"]), wnq=B["wnq"], wgl=B["wgl"],
         dpsi=np.asfortranarray(B["dpsi"]),
         face=face, elem_metrics=em, face_geom=fg,

@@ -9,7 +9,7 @@ module hnumo_b200_iface
     use iso_c_binding
     implicit none
 
-    integer(c_int32_t), parameter :: HNUMO_ABI_VERSION = 1
+    integer(c_int32_t), parameter :: HNUMO_ABI_VERSION = 2
 
     ! mirrors hnumo_desc_t field by field
     type, bind(C) :: hnumo_desc_t
@@ -29,6 +29,7 @@ module hnumo_b200_iface
         type(c_ptr) :: nbh_proc, num_send_recv, nbh_send_recv
         integer(c_int32_t) :: device
         integer(c_int32_t) :: stage_kernel_variant
+        real(c_double)     :: max_shear_dz
     end type hnumo_desc_t
 
     interface

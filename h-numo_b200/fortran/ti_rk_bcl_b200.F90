@@ -25,7 +25,7 @@ contains
         use mpi
         use mod_grid, only: nelem, npoin, nface, face, face_type
         use mod_basis, only: ngl, nq, psiq, dpsiq, wnq, wgl, dpsi
-        use mod_input, only: nlayers, kstages, dt, dt_btp, botfr, cd_mlswe, method_visc, visc_mlswe, ad_mlswe
+        use mod_input, only: nlayers, kstages, dt, dt_btp, botfr, cd_mlswe, method_visc, visc_mlswe, ad_mlswe, max_shear_dz
         use mod_constants, only: gravity
         use mod_metrics, only: ksiq_x, ksiq_y, etaq_x, etaq_y, jacq, massinv
         use mod_face, only: normal_vector_q, jac_faceq
@@ -129,6 +129,7 @@ contains
             end if
             d%device = mod(local_rank, ndev) + 1
             d%stage_kernel_variant = 0
+            d%max_shear_dz = max_shear_dz
             rc_out = hnumo_init(d, handle)
         end subroutine init_with
     end subroutine hnumo_b200_setup

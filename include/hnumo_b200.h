@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define HNUMO_ABI_VERSION 1
+#define HNUMO_ABI_VERSION 2
 #define HNUMO_MAX_LAYERS 20 /* lakeAtrest supports 2..20 layers, src/initial_conditions.F90:130-169 */
 #define HNUMO_MAX_NGL 9     /* nop <= 8 (BASELINE config 5) */
 
@@ -49,7 +49,8 @@ typedef struct hnumo_desc {
     int32_t kstages, N_btp;
     double dt, dt_btp;
     /* physics switches: mod_input botfr, cd_mlswe, method_visc, visc_mlswe, ad_mlswe; gravity as reset by the
-     * test case (9.806, src/initial_conditions.F90:97). method_visc==1 and ad_mlswe>0 are rejected (-3). */
+     * test case (9.806, src/initial_conditions.F90:97). method_visc==1 is rejected (-3).  ad_mlswe > 0 switches the vertical
+     * shear stress between the layers on (src/mod_create_rhs_mlswe.F90:146-279) and needs max_shear_dz > 0 (last member). */
     int32_t botfr, method_visc;
     double gravity, cd_mlswe, visc_mlswe, ad_mlswe;
     /* 1-D operators of mod_basis (src/mod_basis.F90:157-160): psiq(ngl,nq), dpsiq(ngl,nq), wnq(nq), wgl(ngl),
@@ -91,6 +92,9 @@ typedef struct hnumo_desc {
      * block of 128 threads per element at nop 5..8; falls back to 1 for other orders or inexact integration),
      * 1 = simple reference-form kernel (any order; bisecting aid) */
     int32_t stage_kernel_variant;
+    /* mod_input max_shear_dz: upper bound of the shear-layer thickness of the vertical shear stress (only read when ad_mlswe > 0;
+     * added with ABI version 2) */
+    double max_shear_dz;
 } hnumo_desc_t;
 
 /* ---- life cycle ----------------------------------------------------------------------------- */
@@ -129,6 +133,9 @@ int hnumo_layer_mass_rhs(hnumo_handle_t h, double* dp_advec);
  * coefficients of the last hnumo_btp_bcl_coeffs and the time averages of the last hnumo_btp_substeps: rhs_mom(2,npoin,nlayers)
  * to host (src/mod_create_rhs_mlswe.F90:28-51,281-820, src/mod_laplacian_quad.F90:227-248) */
 int hnumo_layer_momentum_rhs(hnumo_handle_t h, double* rhs_mom);
+/* rhs_layer_shear_stress(rhs_stress, q_df) on the resident q_df (needs ad_mlswe > 0): rhs_stress(2,npoin,nlayers) to host, without
+ * the inverse mass matrix, as the reference routine returns it (src/mod_create_rhs_mlswe.F90:146-279) */
+int hnumo_layer_shear_stress(hnumo_handle_t h, double* rhs_stress);
 /* face-halo exchange of nv nodal fields, the device replacement of create_nbhs_face_df / send_bound_dg_general_df
  * (src/create_rhs_dynamics_flux.F90:104-182, src/send_receive_bound.F90:272-327): nodal(nv,npoin) in, halo(nv,ngl,nhalo) out with
  * the processor faces in the order of nbh_send_recv ("side 2 := the neighbour's side 1").  Collective over the ranks of the

@@ -87,6 +87,8 @@ struct Config {
     // point to point, exactly like the reference's metrics.F90) by their per-element / per-face constant values
     // (first quadrature point), i.e. the affine-brick geometry the CUDA library is given.  0 = as the reference.
     int affine_metrics;
+    // vertical shear stress between the layers (mod_input ad_mlswe, max_shear_dz; mod_create_rhs_mlswe.F90:146-279); 0 = off
+    double ad_mlswe, max_shear_dz;
 };
 
 struct Oracle {
@@ -173,6 +175,18 @@ struct Oracle {
     void layer_momentum_volume(Arr& rhs_mom, const Arr& qprime, const Arr& q);
     void apply_layers_fluxes(Arr& rhs_mom, const Arr& qprime_df_face);
     void layer_mom_boundary_df(Arr& q);
+    // method_visc == 1 (oracle_visc_q.cpp)
+    Arr dpprime_visc_q;   // (npoin_q, nl)
+    void interpolate_dpp();
+    void compute_gradient_uv_q(Arr& grad_uv, const Arr& uv);
+    void visc_flux_faces(Arr& ff, const Arr& flux);
+    void compute_laplacian_quad(Arr& lap_q, const Arr& grad_dpuvp);
+    void create_rhs_laplacian_flux_quad(Arr& rhs, const Arr& gradq_face);
+    void btp_create_laplacian_v2(Arr& rhs_lap, const Arr& qprime, const Arr& qb);
+    void bcl_create_laplacian_v2(Arr& rhs_lap, const Arr& qprime);
+    void rhs_layer_shear_stress(Arr& rhs_stress, const Arr& q);
+    void velocity_df(Arr& q, const Arr& qb);
+    void add_shear_stress(Arr& q_df_temp, const Arr& q, const Arr& qb);
     void extract_velocity(Arr& uv, const Arr& q, const Arr& qb);
     void evaluate_bcl(Arr& qprime_df_face, Arr& q, Arr& qprime, const Arr& qb);
     void evaluate_bcl_v1(Arr& q, Arr& qprime, const Arr& qb);

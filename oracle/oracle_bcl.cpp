@@ -532,7 +532,8 @@ void Oracle::apply_layers_fluxes(Arr& rhs_mom, const Arr& qf) {
 // mod_splitting.F90:289-322 + mod_create_rhs_mlswe.F90:28-51
 void Oracle::rhs_momentum(Arr& rhs_mom, const Arr& qprime, const Arr& q, const Arr& qf) {
     Arr rhs_visc_bcl; rhs_visc_bcl.alloc(2, npoin, nl);
-    bcl_create_laplacian(rhs_visc_bcl);
+    if (cfg.method_visc == 1) bcl_create_laplacian_v2(rhs_visc_bcl, qprime);
+    else bcl_create_laplacian(rhs_visc_bcl);
     layer_momentum_volume(rhs_mom, qprime, q);
     apply_layers_fluxes(rhs_mom, qf);
     for (int k = 0; k < nl; ++k)
@@ -621,7 +622,120 @@ void Oracle::evaluate_bcl_v1(Arr& q, Arr& qprime, const Arr& qb) {
         }
 }
 
-// mod_splitting.F90:182-287 (ad_mlswe == 0)
+// mod_layer_terms.F90:139-196: velocities reconciled with the barotropic velocity, momentum rebuilt from them
+void Oracle::velocity_df(Arr& q, const Arr& qb) {
+    Arr uv; uv.alloc(2, npoin, nl);
+    for (int k = 0; k < nl; ++k)
+        for (int I = 0; I < npoin; ++I) { uv(0, I, k) = q(1, I, k) / q(0, I, k); uv(1, I, k) = q(2, I, k) / q(0, I, k); }
+    for (int I = 0; I < npoin; ++I) {
+        double ubar = 0.0, vbar = 0.0;
+        for (int k = 0; k < nl; ++k) { ubar = ubar + uv(0, I, k) * q(0, I, k); vbar = vbar + uv(1, I, k) * q(0, I, k); }
+        if (qb(0, I) > 0.0) {
+            ubar = ubar / qb(0, I); vbar = vbar / qb(0, I);
+            for (int k = 0; k < nl; ++k) {
+                uv(0, I, k) = uv(0, I, k) - ubar + qb(2, I) / qb(0, I);
+                uv(1, I, k) = uv(1, I, k) - vbar + qb(3, I) / qb(0, I);
+            }
+        } else {
+            for (int k = 0; k < nl; ++k) { uv(0, I, k) = 0.0; uv(1, I, k) = 0.0; }
+        }
+    }
+    for (int k = 0; k < nl; ++k)
+        for (int I = 0; I < npoin; ++I) { q(1, I, k) = uv(0, I, k) * q(0, I, k); q(2, I, k) = uv(1, I, k) * q(0, I, k); }
+}
+
+// mod_create_rhs_mlswe.F90:146-279: implicit vertical shear stress between the layers, one tridiagonal system per quadrature
+// point; rhs_stress(2,npoin,nl) WITHOUT the inverse mass matrix (the caller applies it, mod_splitting.F90:160-163).
+// Statement by statement as written (sub-diagonal -coeff, super-diagonal -coeff1, right-hand side u = udp/dp), except for one
+// value the reference never defines: tau_u(nlayers+1), tau_v(nlayers+1) are read at :253-254 but never assigned
+// (parity hazard 2): the evident intent -- no shear stress through the bottom, which the bottom drag handles -- is 0.
+void Oracle::rhs_layer_shear_stress(Arr& rhs_stress, const Arr& q) {
+    rhs_stress.zero();
+    const int nq2 = nq * nq;
+    const double ad = cfg.ad_mlswe;
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < nelem; ++e) {
+        std::vector<double> tau_u(nl + 1), tau_v(nl + 1), a(nl), b(nl), c(nl), dp(nl), udp(nl), vdp(nl), r1(nl), r2(nl), u(nl), v(nl);
+        for (int Iq = e * nq2; Iq < (e + 1) * nq2; ++Iq) {
+            std::fill(dp.begin(), dp.end(), 0.0); std::fill(udp.begin(), udp.end(), 0.0); std::fill(vdp.begin(), vdp.end(), 0.0);
+            for (int ip = 0; ip < npts; ++ip) {
+                int I = indexq[(size_t)Iq * npts + ip];
+                double hi = psih(ip, Iq);
+                for (int k = 0; k < nl; ++k) {
+                    dp[k] = dp[k] + hi * q(0, I, k);
+                    udp[k] = udp[k] + hi * q(1, I, k);
+                    vdp[k] = vdp[k] + hi * q(2, I, k);
+                }
+            }
+            double coeff = std::fmax(std::sqrt(0.5 * coriolis_quad(Iq) * ad) / alpha_mlswe(0), ad / (alpha_mlswe(0) * cfg.max_shear_dz));
+            double coeff1 = gravity * dt * coeff;
+            for (int k = 0; k < nl; ++k) {
+                a[k] = -coeff;
+                b[k] = dp[k] + 2.0 * coeff1;
+                c[k] = -coeff1;
+                r1[k] = udp[k] / dp[k];
+                r2[k] = vdp[k] / dp[k];
+            }
+            b[0] = dp[0] + coeff1;
+            b[nl - 1] = dp[nl - 1] + coeff1;
+            a[0] = 0.0;
+            c[nl - 1] = 0.0;
+            for (int k = 1; k < nl; ++k) {
+                double mult = a[k] / b[k - 1];
+                b[k] = b[k] - mult * c[k - 1];
+                r1[k] = r1[k] - mult * r1[k - 1];
+                r2[k] = r2[k] - mult * r2[k - 1];
+            }
+            r1[nl - 1] = r1[nl - 1] / b[nl - 1];
+            r2[nl - 1] = r2[nl - 1] / b[nl - 1];
+            u[nl - 1] = r1[nl - 1]; v[nl - 1] = r2[nl - 1];
+            for (int k = nl - 2; k >= 0; --k) {
+                r1[k] = (r1[k] - c[k] * r1[k + 1]) / b[k];
+                r2[k] = (r2[k] - c[k] * r2[k + 1]) / b[k];
+                u[k] = r1[k]; v[k] = r2[k];
+            }
+            tau_u[0] = 0.0; tau_v[0] = 0.0;
+            for (int k = 1; k < nl; ++k) { tau_u[k] = coeff * (u[k - 1] - u[k]); tau_v[k] = coeff * (v[k - 1] - v[k]); }
+            tau_u[nl] = 0.0; tau_v[nl] = 0.0;   // hazard 2: undefined in the reference
+            double wq = wjac(Iq);
+            for (int k = 0; k < nl; ++k) {
+                double tau_u_q = gravity * (tau_u[k] - tau_u[k + 1]);
+                double tau_v_q = gravity * (tau_v[k] - tau_v[k + 1]);
+                for (int ip = 0; ip < npts; ++ip) {
+                    int I = indexq[(size_t)Iq * npts + ip];
+                    double hi = psih(ip, Iq);
+                    rhs_stress(0, I, k) = rhs_stress(0, I, k) + wq * hi * tau_u_q;
+                    rhs_stress(1, I, k) = rhs_stress(1, I, k) + wq * hi * tau_v_q;
+                }
+            }
+        }
+    }
+}
+
+// mod_splitting.F90:139-164 / 247-271: the shear-stress block of momentum / momentum_mass.  q_df_temp(2,npoin,nl) holds
+// q_df(2:3) + dt*rhs_mom on entry.  In `momentum` the reference passes an unset local (`uv`, of another shape) to
+// rhs_layer_shear_stress (:158) where `momentum_mass` passes q_df3 (:265): parity hazard 3; q_df3 -- the evident intent -- is used in both.
+void Oracle::add_shear_stress(Arr& q_df_temp, const Arr& q, const Arr& qb) {
+    Arr q3; q3.alloc(3, npoin, nl);
+    for (int k = 0; k < nl; ++k)
+        for (int I = 0; I < npoin; ++I) {
+            double tempu = q_df_temp(0, I, k) + fdt2_bcl(I) * q(2, I, k);
+            double tempv = q_df_temp(1, I, k) - fdt2_bcl(I) * q(1, I, k);
+            q3(1, I, k) = a_bcl(I) * tempu + b_bcl(I) * tempv;
+            q3(2, I, k) = -b_bcl(I) * tempu + a_bcl(I) * tempv;
+            q3(0, I, k) = q(0, I, k);
+        }
+    velocity_df(q3, qb);
+    Arr rhs_stress; rhs_stress.alloc(2, npoin, nl);
+    rhs_layer_shear_stress(rhs_stress, q3);
+    for (int k = 0; k < nl; ++k)
+        for (int I = 0; I < npoin; ++I) {
+            q_df_temp(0, I, k) = q_df_temp(0, I, k) + dt * (massinv(I) * rhs_stress(0, I, k));
+            q_df_temp(1, I, k) = q_df_temp(1, I, k) + dt * (massinv(I) * rhs_stress(1, I, k));
+        }
+}
+
+// mod_splitting.F90:182-287
 void Oracle::momentum_mass(Arr& q, Arr& qf, Arr& qprime, const Arr& qb) {
     Arr dp_advec; dp_advec.alloc(npoin, nl);
     Arr rhs_mom; rhs_mom.alloc(2, npoin, nl);
@@ -633,12 +747,17 @@ void Oracle::momentum_mass(Arr& q, Arr& qf, Arr& qprime, const Arr& qb) {
         }
     apply_consistency(q);
     rhs_momentum(rhs_mom, qprime, q, qf);
+    Arr q_df_temp; q_df_temp.alloc(2, npoin, nl);
     for (int k = 0; k < nl; ++k)
         for (int I = 0; I < npoin; ++I) {
-            double t1 = q(1, I, k) + dt * rhs_mom(0, I, k);
-            double t2 = q(2, I, k) + dt * rhs_mom(1, I, k);
-            double tempu = t1 + fdt2_bcl(I) * q(2, I, k);
-            double tempv = t2 - fdt2_bcl(I) * q(1, I, k);
+            q_df_temp(0, I, k) = q(1, I, k) + dt * rhs_mom(0, I, k);
+            q_df_temp(1, I, k) = q(2, I, k) + dt * rhs_mom(1, I, k);
+        }
+    if (cfg.ad_mlswe > 0.0) add_shear_stress(q_df_temp, q, qb);
+    for (int k = 0; k < nl; ++k)
+        for (int I = 0; I < npoin; ++I) {
+            double tempu = q_df_temp(0, I, k) + fdt2_bcl(I) * q(2, I, k);
+            double tempv = q_df_temp(1, I, k) - fdt2_bcl(I) * q(1, I, k);
             q(1, I, k) = a_bcl(I) * tempu + b_bcl(I) * tempv;
             q(2, I, k) = -b_bcl(I) * tempu + a_bcl(I) * tempv;
         }
@@ -666,16 +785,21 @@ void Oracle::thickness(Arr& qprime, Arr& q, const Arr& qb, Arr& qf) {
     extract_dprime_df_face(qf, qprime);
 }
 
-// mod_splitting.F90:94-180 (ad_mlswe == 0)
+// mod_splitting.F90:94-180
 void Oracle::momentum(Arr& q, Arr& qprime, const Arr& qb, const Arr& qf) {
     Arr rhs_mom; rhs_mom.alloc(2, npoin, nl);
     rhs_momentum(rhs_mom, qprime, q, qf);
+    Arr q_df_temp; q_df_temp.alloc(2, npoin, nl);
     for (int k = 0; k < nl; ++k)
         for (int I = 0; I < npoin; ++I) {
-            double t1 = q(1, I, k) + dt * rhs_mom(0, I, k);
-            double t2 = q(2, I, k) + dt * rhs_mom(1, I, k);
-            double tempu = t1 + fdt2_bcl(I) * q(2, I, k);
-            double tempv = t2 - fdt2_bcl(I) * q(1, I, k);
+            q_df_temp(0, I, k) = q(1, I, k) + dt * rhs_mom(0, I, k);
+            q_df_temp(1, I, k) = q(2, I, k) + dt * rhs_mom(1, I, k);
+        }
+    if (cfg.ad_mlswe > 0.0) add_shear_stress(q_df_temp, q, qb);
+    for (int k = 0; k < nl; ++k)
+        for (int I = 0; I < npoin; ++I) {
+            double tempu = q_df_temp(0, I, k) + fdt2_bcl(I) * q(2, I, k);
+            double tempv = q_df_temp(1, I, k) - fdt2_bcl(I) * q(1, I, k);
             q(1, I, k) = a_bcl(I) * tempu + b_bcl(I) * tempv;
             q(2, I, k) = -b_bcl(I) * tempu + a_bcl(I) * tempv;
         }
@@ -692,6 +816,7 @@ void Oracle::ti_rk_bcl() {
     qbp = qb_df;
     for (int k = 0; k < nl; ++k)
         for (int I = 0; I < npoin; ++I) dpprime_visc(I, k) = qprime_df(0, I, k);
+    if (cfg.method_visc == 1) interpolate_dpp();
     btp_bcl_coeffs_qdf(qf, qprime_df);
     ti_barotropic_ssprk_mlswe(qbp, qprime_df);
     q2 = q_df; qprime2 = qprime_df; qf2 = qf;
@@ -701,6 +826,7 @@ void Oracle::ti_rk_bcl() {
     for (size_t i = 0; i < qf2.size(); ++i) qf2.v[i] = 0.5 * (qf.v[i] + qf2.v[i]);
     for (int k = 0; k < nl; ++k)
         for (int I = 0; I < npoin; ++I) dpprime_visc(I, k) = qprime2(0, I, k);
+    if (cfg.method_visc == 1) interpolate_dpp();
     btp_bcl_coeffs_qdf(qf2, qprime2);
     ti_barotropic_ssprk_mlswe(qb_df, qprime2);
     thickness(qprime2, q_df, qb_df, qf2);

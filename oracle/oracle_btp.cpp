@@ -338,7 +338,8 @@ void Oracle::create_rhs_btp(Arr& rhs, const Arr& qb, const Arr& qprime) {
     btp_extract_df(qb_df_face, qb);
     create_rhs_btp_volume_qdf(rhs, qb, qprime);
     creat_btp_fluxes_qdf(rhs, qb_df_face);
-    btp_create_laplacian(rhs_visc_btp, qb);  // method_visc != 1
+    if (cfg.method_visc == 1) btp_create_laplacian_v2(rhs_visc_btp, qprime, qb);
+    else btp_create_laplacian(rhs_visc_btp, qb);
 #pragma omp parallel for schedule(static)
     for (int I = 0; I < npoin; ++I) {
         rhs(1, I) = rhs(1, I) + rhs_visc_btp(0, I);

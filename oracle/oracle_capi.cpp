@@ -82,6 +82,7 @@ void orc_btp_bcl_coeffs(void* h) {
     o->extract_qprime_df_face(qf, o->qprime_df);
     for (int k = 0; k < o->nl; ++k)
         for (int I = 0; I < o->npoin; ++I) o->dpprime_visc(I, k) = o->qprime_df(0, I, k);
+    if (o->cfg.method_visc == 1) o->interpolate_dpp();
     o->btp_bcl_coeffs_qdf(qf, o->qprime_df);
 }
 // phase: one barotropic RHS evaluation on the current qb_df (mod_rhs_btp.F90:28-59); accumulators are updated
@@ -108,6 +109,13 @@ void orc_layer_momentum_rhs(void* h, double* out) {
     Arr rhs; rhs.alloc(2, o->npoin, o->nl);
     o->rhs_momentum(rhs, o->qprime_df, o->q_df, qf);
     std::memcpy(out, rhs.data(), rhs.size() * sizeof(double));
+}
+// phase: rhs_layer_shear_stress of the current q_df (mod_create_rhs_mlswe.F90:146-279): rhs_stress(2,npoin,nl), no mass matrix
+void orc_shear_stress(void* h, double* out) {
+    Oracle* o = (Oracle*)h;
+    Arr rs; rs.alloc(2, o->npoin, o->nl);
+    o->rhs_layer_shear_stress(rs, o->q_df);
+    std::memcpy(out, rs.data(), rs.size() * sizeof(double));
 }
 // phase: full barotropic substep loop on qb_df in place (mod_rk_mlswe.F90:19-151)
 void orc_btp_substeps(void* h) {

@@ -608,7 +608,7 @@ void Oracle::allocate_variables() {
     H_face_ave.alloc(nq, nface); Qu_face_ave.alloc(2, nq, nface); Qv_face_ave.alloc(2, nq, nface);
     Quv_face_ave.alloc(2, nq, nface); tau_wind_ave.alloc(2, npoin_q); tau_bot_ave.alloc(2, npoin_q);
     one_plus_eta_edge_2_ave.alloc(nq, nface); uvb_ave_df.alloc(2, npoin); ope2_face_ave.alloc(2, nq, nface);
-    dpprime_visc.alloc(npoin, nl); pbprime_visc.alloc(npoin); btp_dpp_graduv.alloc(4, npoin);
+    dpprime_visc.alloc(npoin, nl); dpprime_visc_q.alloc(npoin_q, nl); pbprime_visc.alloc(npoin); btp_dpp_graduv.alloc(4, npoin);
     dpp_graduv.alloc(4, npoin, nl); graduv_dpp_face.alloc(5, 2, ngl, nface, nl); btp_graduv_dpp_face.alloc(5, 2, ngl, nface);
     graduvb_face_ave.alloc(4, 2, ngl, nface); graduvb_ave.alloc(4, npoin);
     sum_layer_mass_flux.alloc(2, npoin_q); sum_layer_mass_flux_face.alloc(2, nq, nface);
@@ -663,7 +663,7 @@ Oracle::Oracle(const Config& c) : cfg(c) {
     REG(ope_ave); REG(H_ave); REG(Qu_ave); REG(Qv_ave); REG(Quv_ave); REG(ope2_ave); REG(btp_mass_flux_ave); REG(uvb_ave);
     REG(ope2_ave_df); REG(uvb_face_ave); REG(btp_mass_flux_face_ave); REG(ope_face_ave); REG(H_face_ave); REG(Qu_face_ave);
     REG(Qv_face_ave); REG(Quv_face_ave); REG(tau_wind_ave); REG(tau_bot_ave); REG(one_plus_eta_edge_2_ave); REG(uvb_ave_df);
-    REG(ope2_face_ave); REG(dpprime_visc); REG(pbprime_visc); REG(btp_dpp_graduv); REG(dpp_graduv); REG(graduv_dpp_face);
+    REG(ope2_face_ave); REG(dpprime_visc); REG(dpprime_visc_q); REG(pbprime_visc); REG(btp_dpp_graduv); REG(dpp_graduv); REG(graduv_dpp_face);
     REG(btp_graduv_dpp_face); REG(graduvb_face_ave); REG(graduvb_ave); REG(sum_layer_mass_flux); REG(sum_layer_mass_flux_face);
 #undef REG
 }

@@ -29,15 +29,15 @@ int main(int argc, char** argv) {
     FILE* f = fopen(argv[1], "rb");
     if (!f) { perror("deck"); return 2; }
     int32_t h[16];
-    double sc[6];
-    if (fread(h, sizeof(int32_t), 16, f) != 16 || h[0] != 0x484e554d || fread(sc, sizeof(double), 6, f) != 6) { fprintf(stderr, "harness: bad deck header\n"); return 2; }
+    double sc[7];
+    if (fread(h, sizeof(int32_t), 16, f) != 16 || h[0] != 0x484e554d || fread(sc, sizeof(double), 7, f) != 7) { fprintf(stderr, "harness: bad deck header\n"); return 2; }
     hnumo_desc_t d;
     memset(&d, 0, sizeof(d));
     d.abi_version = HNUMO_ABI_VERSION;
     d.nelem = h[1]; d.ngl = h[2]; d.nq = h[3]; d.nlayers = h[4]; d.nface = h[5]; d.kstages = h[6]; d.N_btp = h[7];
     d.botfr = h[8]; d.method_visc = h[9]; d.rank = h[10]; d.nranks = h[11]; d.num_nbh = h[12];
     const int nsr = h[13];
-    d.dt = sc[0]; d.dt_btp = sc[1]; d.gravity = sc[2]; d.cd_mlswe = sc[3]; d.visc_mlswe = sc[4]; d.ad_mlswe = sc[5];
+    d.dt = sc[0]; d.dt_btp = sc[1]; d.gravity = sc[2]; d.cd_mlswe = sc[3]; d.visc_mlswe = sc[4]; d.ad_mlswe = sc[5]; d.max_shear_dz = sc[6];
     const size_t npoin = (size_t)d.nelem * d.ngl * d.ngl, D = sizeof(double), I = sizeof(int32_t);
     d.psiq = rd(f, D * d.ngl * d.nq); d.dpsiq = rd(f, D * d.ngl * d.nq); d.wnq = rd(f, D * d.nq); d.wgl = rd(f, D * d.ngl);
     d.dpsi = rd(f, D * d.ngl * d.ngl);

@@ -28,7 +28,7 @@ def write_deck(path, deck):
            deck["method_visc"], deck["rank"], deck["nranks"], len(deck["nbh_proc"]), nsr, 0, 0]
     with open(path, "wb") as f:
         f.write(struct.pack("16i", *[int(x) for x in hdr]))
-        f.write(struct.pack("6d", deck["dt"], deck["dt_btp"], deck["gravity"], deck["cd_mlswe"], deck["visc_mlswe"], deck["ad_mlswe"]))
+        f.write(struct.pack("7d", deck["dt"], deck["dt_btp"], deck["gravity"], deck["cd_mlswe"], deck["visc_mlswe"], deck["ad_mlswe"], deck.get("max_shear_dz", 0.0)))
         for k in ("psiq", "dpsiq"):
             f.write(f64(deck[k], "F"))          # (ngl,nq) column-major
         f.write(f64(deck["wnq"])); f.write(f64(deck["wgl"])); f.write(f64(deck["dpsi"], "F"))

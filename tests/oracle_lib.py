@@ -28,6 +28,7 @@ class Config(C.Structure):
         ("test_case", C.c_int), ("dg_integ_exact", C.c_int),
         ("synth_z", C.c_double * 33), ("synth_alpha", C.c_double * 32), ("synth_perturb", C.c_double),
         ("affine_metrics", C.c_int),
+        ("ad_mlswe", C.c_double), ("max_shear_dz", C.c_double),
     ]
 
 
@@ -70,6 +71,7 @@ def lib(variant=""):
         L.orc_btp_substeps.argtypes = [C.c_void_p]
         L.orc_layer_mass_rhs.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_layer_momentum_rhs.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_shear_stress.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_diagnostics.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _LIBS[variant] = L
     return _LIBS[variant]
@@ -98,6 +100,7 @@ def make_config(deck):
         c.synth_alpha[i] = a
     c.synth_perturb = deck.get("synth_perturb", 0.0)
     c.affine_metrics = 1 if deck.get("affine_metrics", False) else 0
+    c.ad_mlswe, c.max_shear_dz = deck.get("ad_mlswe", 0.0), deck.get("max_shear_dz", 0.0)
     return c
 
 
@@ -171,6 +174,11 @@ class Oracle:
     def layer_momentum_rhs(self):
         out = np.empty(2 * self.npoin * self.nl)
         self.L.orc_layer_momentum_rhs(self.h, out.ctypes.data)
+        return out.reshape(self.nl, self.npoin, 2)
+
+    def shear_stress(self):
+        out = np.empty(2 * self.npoin * self.nl)
+        self.L.orc_shear_stress(self.h, out.ctypes.data)
         return out.reshape(self.nl, self.npoin, 2)
 
     def diagnostics(self):

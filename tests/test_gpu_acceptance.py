@@ -111,7 +111,9 @@ def test_exact_division_build_differs_by_round_off(name):
     floor of each field, and is no closer to the oracle."""
     path = os.path.join(HERE, "golden", "acceptance_%s.npz" % name)
     if not os.path.exists(path) or not os.path.exists(EXACT_LIB):
-        pytest.skip("needs the fixture and h-numo_b200/libhnumo_b200_exact.so (profiles/build_exact.sh)")
+        pytest.skip("needs the fixture and h-numo_b200/libhnumo_b200_exact.so (build(): build_library(exact=True))")
+    if os.path.getmtime(EXACT_LIB) + 600 < os.path.getmtime(hn.LIB_PATH):
+        pytest.skip("libhnumo_b200_exact.so is older than the library: rebuild it (build_library(exact=True))")
     fx = np.load(path)
     params, spin, stride = mag.cases()[name]
     deck, a, _, _ = _run_gpu(params, fx)

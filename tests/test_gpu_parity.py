@@ -146,6 +146,41 @@ def test_step_parity(name, nsteps, variant):
     S.close()
 
 
+SHEAR_DECKS = {
+    # ad_mlswe is taken large so that the term is visible next to the momentum (as written, the implicit system solves for
+    # u = udp/dp against a diagonal of size dp, so the stress is ~1e-7 of what a dimensionally consistent system would give)
+    "double_gyre": lambda: dict(hn.decks.SHIPPED["double_gyre"], nelx=6, nely=6, ad_mlswe=1.0e6, max_shear_dz=2.0),
+    "synth3": lambda: dict(hn.decks.synthetic_double_gyre(6, 5, nop=4, nlayers=3), ad_mlswe=1.0e6, max_shear_dz=5.0),
+    "bump": lambda: dict(hn.decks.SHIPPED["bump"], nelx=6, nely=6, ad_mlswe=1.0e4, max_shear_dz=0.5),     # f = 0: coeff = ad / (alpha dz)
+    "nop8_5layers": lambda: dict(hn.decks.synthetic_double_gyre(3, 3, nop=8, nlayers=5), ad_mlswe=1.0e6, max_shear_dz=2.0),
+}
+
+
+@pytest.mark.parametrize("name", list(SHEAR_DECKS))
+def test_vertical_shear_stress(name):
+    """ad_mlswe > 0 (rhs_layer_shear_stress, mod_create_rhs_mlswe.F90:146-279, call sites
+    mod_splitting.F90:139-164,247-271) against the oracle over whole steps, and the term really acts: the run differs from
+    the run without it by far more than the tolerance."""
+    p = SHEAR_DECKS[name]()
+    deck, S, O = make_pair(p)
+    n = 4
+    assert S.step(n) == 0 and O.step(n) == 0
+    e = natural_errors(S, O, deck)
+    assert e["mass"] < 1e-10 and e["mom"] < 1e-11, e
+    # the term by itself, on the same developed state: rhs_layer_shear_stress(q_df)
+    sync_state_from_oracle(S, O)
+    rs_o, rs_g = O.shear_stress(), S.layer_shear_stress()
+    assert np.abs(rs_o).max() > 0.0
+    assert rel_l2(rs_g, rs_o) < 1e-11, rel_l2(rs_g, rs_o)
+    O0 = oracle_lib.Oracle(dict(p, ad_mlswe=0.0, affine_metrics=True))
+    assert O0.step(n) == 0
+    c = np.sqrt(deck["gravity"] * float(np.max(-deck["zbot_df"])))
+    qa = O.get("q_df").reshape(deck["nlayers"], -1, 3); q0 = O0.get("q_df").reshape(deck["nlayers"], -1, 3)
+    effect = max(np.linalg.norm(qa[k, :, v] - q0[k, :, v]) / np.linalg.norm(qa[k, :, v]) for k in range(deck["nlayers"]) for v in (1, 2))
+    assert effect > 1e-8, effect      # relative change of the layer momentum by the stress (small: see the note at SHEAR_DECKS)
+    S.close()
+
+
 def test_high_order_many_layers():
     """BASELINE config 5 in small: nop=8 (ngl=9, nq=17), 10 layers -- orders without a compile-time instantiation run the
     run-time-size kernels; nl > 3 uses the intent semantics of SURVEY 8 hazard 1 in both the oracle and the library"""

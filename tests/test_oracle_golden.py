@@ -174,3 +174,20 @@ def test_oracle_matches_committed_fields(name):
     pn = np.linalg.norm(qb0[:, 0])
     assert np.linalg.norm(qb[:, :2] - qb0[:, :2]) <= 1e-12 * pn
     assert np.linalg.norm(qb[:, 2:] - qb0[:, 2:]) <= 1e-11 * c * pn
+
+
+def test_oracle_shear_stress_properties():
+    """rhs_layer_shear_stress (mod_create_rhs_mlswe.F90:146-279) as restated: the interface stresses telescope, so the stress
+    tendencies of the layers sum to zero at every node (no stress through the surface, and -- parity hazard 2 -- none through the
+    bottom); with one layer there is no interface at all; and ad_mlswe = 0 leaves the step untouched."""
+    p = dict(hn.decks.synthetic_double_gyre(3, 3, nop=4, nlayers=3), ad_mlswe=1.0e6, max_shear_dz=2.0)
+    O = oracle_lib.Oracle(p)
+    assert O.step(2) == 0
+    rs = O.shear_stress()
+    assert np.abs(rs).max() > 0.0
+    assert np.abs(rs.sum(axis=0)).max() <= 1e-12 * np.abs(rs).max()
+    p0 = dict(p, ad_mlswe=0.0)
+    A, B = oracle_lib.Oracle(p0), oracle_lib.Oracle(dict(p0, max_shear_dz=0.0))
+    A.step(1); B.step(1)
+    assert np.array_equal(A.get("q_df"), B.get("q_df"))
+    assert not np.array_equal(A.get("q_df"), O.get("q_df"))
