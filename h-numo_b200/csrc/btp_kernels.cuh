@@ -19,6 +19,7 @@
 // k_btp_finalize from nodal sums (SURVEY.md section 7 "accumulator diet").
 #pragma once
 #include "hnumo_dev.cuh"
+#include "visc_q.cuh"
 
 namespace hn {
 
@@ -48,6 +49,13 @@ struct StageArgs {
     double a1, a2, a3, dtt, g, cd, alpha_bot, visc;
     int botfr, has_visc, load_q0, load_q2, store_q0, store_q2, rhs_only;
     int acc_graduvb;  // 1: accumulate graduvb per stage (reference form); 0: derived after the loop from the nodal velocity sums
+    // method_visc == 1 (visc_q.cuh): flux variable at the quadrature points F = S + P grad(ub,vb), face values in slot planes
+    int visc_q;
+    const double* vqP;
+    const double* vqS[4];
+    const double* trq_in;
+    double* trq_out;
+    size_t trq_stride;
 };
 
 // value of trace variable v at face node n of (e,s) as seen from the neighbour's side ("side 2" of
@@ -82,7 +90,7 @@ __device__ __forceinline__ void reflect4(const double in[4], double nx, double n
 
 // shared memory plan of k_btp_stage_simple (doubles)
 struct StageSmem {
-    int ops, nod, tmp, fq, tP, tR, rhs, lap, own, nbt, nbv, ownv, ff, lf, total;
+    int ops, nod, tmp, fq, tP, tR, rhs, lap, own, nbt, nbv, ownv, ff, lf, vF, lfq, total;
     __host__ __device__ StageSmem(int ngl, int nq) {
         int npts = ngl * ngl, nq2 = nq * nq, per = ngl * nq;
         int o = 0;
@@ -100,6 +108,8 @@ struct StageSmem {
         ownv = o; o += 4 * 5 * ngl;  // own viscosity statics
         ff = o; o += 4 * 3 * nq;     // face flux at quadrature points [s][f][iq]
         lf = o; o += 4 * 2 * ngl;    // LDG face flux at face nodes [s][c][n]
+        vF = o; o += 4 * nq2;        // method_visc 1: weighted flux variable Fk_u Fk_v | Fe_u Fe_v
+        lfq = o; o += 4 * 2 * nq;    // method_visc 1: LDG face flux at face quadrature points [s][c][iq]
         total = o;
     }
 };
@@ -121,6 +131,9 @@ __global__ void k_btp_stage_simple(StageArgs a) {
     double* ownv = sm + L.ownv;
     double* ff = sm + L.ff;
     double* lf = sm + L.lf;
+    double* vF = sm + L.vF;
+    double* lfq = sm + L.lfq;
+    const bool nodal_visc = a.has_visc && !a.visc_q, quad_visc = a.has_visc && a.visc_q;
     const double ksx = a.M.em[e * 5 + 0], ksy = a.M.em[e * 5 + 1], etx = a.M.em[e * 5 + 2], ety = a.M.em[e * 5 + 3],
                  J = a.M.em[e * 5 + 4];
     const size_t nbase = (size_t)e * npts, qbase = (size_t)e * nq2;
@@ -149,7 +162,7 @@ __global__ void k_btp_stage_simple(StageArgs a) {
     }
     __syncthreads();
     // ---- 2. LDG auxiliary variable G = grad(ub,vb) at the nodes (mod_laplacian_quad.F90:50-56)
-    if (a.has_visc && tid < npts) {
+    if (nodal_visc && tid < npts) {
         int m = tid / ngl, n = tid - m * ngl;
         double dk, de;
         nodal_grad(o, ngl, nod + 7 * npts, n, m, dk, de);
@@ -165,6 +178,7 @@ __global__ void k_btp_stage_simple(StageArgs a) {
     // ---- 3. interpolate pb,dpp,mx,my (+ bottom-layer primes) to the quadrature points
     const int NF = a.botfr ? 7 : 4;
     sf_pass1(o, ngl, nq, NF, nod, npts, tmp, nullptr);
+    if (quad_visc) sf_pass1(o, ngl, nq, 2, nod + 7 * npts, npts, sm + L.tR, sm + L.tP);   // ub, vb: A-pass in tR, B-pass in tP
     __syncthreads();
     // ---- 4. pointwise physics (mod_rhs_btp.F90:136-192)
     if (tid < nq2) {
@@ -202,12 +216,22 @@ __global__ void k_btp_stage_simple(StageArgs a) {
         fq[3 * nq2 + tid] = wq * (ksx * Fx2 + ksy * Fy2); fq[4 * nq2 + tid] = wq * (etx * Fx2 + ety * Fy2);
         fq[5 * nq2 + tid] = wq * sc_y;
         fq[6 * nq2 + tid] = wq * (ksx * Fx3 + ksy * Fy3); fq[7 * nq2 + tid] = wq * (etx * Fx3 + ety * Fy3);
+        if (quad_visc) {   // btp_create_laplacian_v2 + compute_laplacian_quad (mod_laplacian_quad.F90:125-159,613-642)
+            const double uk = sf_eval(o, ngl, nq, sm + L.tP, 0, i, j), ue = sf_eval_B(o, ngl, nq, sm + L.tR, 0, i, j);
+            const double vk = sf_eval(o, ngl, nq, sm + L.tP, 1, i, j), ve = sf_eval_B(o, ngl, nq, sm + L.tR, 1, i, j);
+            const double pq = a.vqP[Iq];
+            const double F0 = a.vqS[0][Iq] + pq * (ksx * uk + etx * ue), F1 = a.vqS[1][Iq] + pq * (ksy * uk + ety * ue);
+            const double F2 = a.vqS[2][Iq] + pq * (ksx * vk + etx * ve), F3 = a.vqS[3][Iq] + pq * (ksy * vk + ety * ve);
+            vF[0 * nq2 + tid] = -wq * (ksx * F0 + ksy * F1); vF[1 * nq2 + tid] = -wq * (ksx * F2 + ksy * F3);
+            vF[2 * nq2 + tid] = -wq * (etx * F0 + ety * F1); vF[3 * nq2 + tid] = -wq * (etx * F2 + ety * F3);
+        }
     }
     __syncthreads();
     // ---- 5. scatter to the nodes (field 1 has no source term)
     sf_scatter(o, ngl, nq, 1, nullptr, fq + 0 * nq2, fq + 1 * nq2, nq2, sm + L.tP, sm + L.tR, rhs, npts, false);
     sf_scatter(o, ngl, nq, 1, fq + 2 * nq2, fq + 3 * nq2, fq + 4 * nq2, nq2, sm + L.tP, sm + L.tR, rhs + npts, npts, false);
     sf_scatter(o, ngl, nq, 1, fq + 5 * nq2, fq + 6 * nq2, fq + 7 * nq2, nq2, sm + L.tP, sm + L.tR, rhs + 2 * npts, npts, false);
+    if (quad_visc) sf_scatter(o, ngl, nq, 2, nullptr, vF, vF + 2 * nq2, nq2, sm + L.tP, sm + L.tR, lap, npts, false);
 
     // ---- 6. face traces: own and neighbour (btp_extract_df) + LDG gradient traces and viscosity statics
     if (tid < 4 * ngl) {
@@ -220,7 +244,7 @@ __global__ void k_btp_stage_simple(StageArgs a) {
         double* po = own + (s * 7) * ngl + n;
         double* pn = nbt + (s * 7) * ngl + n;
         for (int v = 0; v < 3; ++v) { po[v * ngl] = ow[v]; pn[v * ngl] = nbv3[v]; }
-        if (a.has_visc) {
+        if (nodal_visc) {
             double go[4] = {nod[9 * npts + I], nod[10 * npts + I], nod[11 * npts + I], nod[12 * npts + I]}, gn[4];
             double so[5] = {a.bdg[0][nbase + I], a.bdg[1][nbase + I], a.bdg[2][nbase + I], a.bdg[3][nbase + I],
                             a.pbv[nbase + I]}, sn[5];
@@ -297,7 +321,15 @@ __global__ void k_btp_stage_simple(StageArgs a) {
         ff[(s * 3 + 2) * nq + iq] = sgn * wq * (nyl * Hf + flux_y);
     }
     // ---- 7b. LDG face flux at the face nodes, as written (mod_laplacian_quad.F90:427-519)
-    if (a.has_visc && tid >= 4 * nq && tid < 4 * nq + 4 * ngl) {
+    if (quad_visc) {   // create_rhs_laplacian_flux_quad (mod_laplacian_quad.F90:644-722) on the published face values
+        for (int t = tid; t < 4 * nq; t += blockDim.x) {
+            const int s = t / nq, iq = t - s * nq;
+            double fl[2];
+            vq_face_flux(a.M, a.trq_in, a.trq_stride, e, s, iq, o.wq[iq], fl);
+            lfq[(s * 2 + 0) * nq + iq] = fl[0]; lfq[(s * 2 + 1) * nq + iq] = fl[1];
+        }
+    }
+    if (nodal_visc && tid >= 4 * nq && tid < 4 * nq + 4 * ngl) {
         int t = tid - 4 * nq, s = t / ngl, n = t - s * ngl;
         int slot = e * 4 + s, nb = a.M.nbr[slot];
         bool left = (nb < 0) || (e < nb);
@@ -321,13 +353,13 @@ __global__ void k_btp_stage_simple(StageArgs a) {
         lf[(s * 2 + 1) * ngl + n] = sgn * wq * flux_qv;
     }
     // ---- 7c. LDG volume term (btp_compute_laplacian, mod_laplacian_quad.F90:357-390); collocation weak form
-    if (a.has_visc && tid < npts) {
+    if (nodal_visc && tid < npts) {
         // stage qq = pbprime_visc*G + btp_dpp_graduv in tmp (reuse): tmp[c][node], c=0..3
         double pv = a.pbv[nbase + tid];
         for (int v = 0; v < 4; ++v) tmp[v * npts + tid] = pv * nod[(9 + v) * npts + tid] + a.bdg[v][nbase + tid];
     }
     __syncthreads();
-    if (a.has_visc && tid < npts) {
+    if (nodal_visc && tid < npts) {
         int m = tid / ngl, n = tid - m * ngl;
         double l0 = 0.0, l1 = 0.0;
         for (int k = 0; k < ngl; ++k) {
@@ -358,7 +390,15 @@ __global__ void k_btp_stage_simple(StageArgs a) {
                 p0 += hi * ff[(s * 3 + 0) * nq + iq]; p1 += hi * ff[(s * 3 + 1) * nq + iq]; p2 += hi * ff[(s * 3 + 2) * nq + iq];
             }
             r0 += p0; r1 += p1; r2 += p2;
-            if (a.has_visc) { l0 += lf[(s * 2 + 0) * ngl + nf]; l1 += lf[(s * 2 + 1) * ngl + nf]; }
+            if (nodal_visc) { l0 += lf[(s * 2 + 0) * ngl + nf]; l1 += lf[(s * 2 + 1) * ngl + nf]; }
+            if (quad_visc) {
+                double v0 = 0.0, v1 = 0.0;
+                for (int iq = 0; iq < nq; ++iq) {
+                    double hi = o.A[nf + ngl * iq];
+                    v0 += hi * lfq[(s * 2 + 0) * nq + iq]; v1 += hi * lfq[(s * 2 + 1) * nq + iq];
+                }
+                l0 += v0; l1 += v1;
+            }
         }
         double mi = a.massinv[nbase + tid];
         r0 = mi * r0; r1 = mi * r1; r2 = mi * r2;
@@ -402,7 +442,7 @@ __global__ void k_btp_stage_simple(StageArgs a) {
         a.tr_out[TR_PBPERT * a.trstride + base] = nod[1 * npts + I];
         a.tr_out[TR_MX * a.trstride + base] = nod[2 * npts + I];
         a.tr_out[TR_MY * a.trstride + base] = nod[3 * npts + I];
-        if (a.has_visc) {
+        if (nodal_visc) {
             int m = I / ngl, nn = I - m * ngl;
             double dk, de;
             nodal_grad(o, ngl, nod + 7 * npts, nn, m, dk, de);
@@ -411,6 +451,14 @@ __global__ void k_btp_stage_simple(StageArgs a) {
             nodal_grad(o, ngl, nod + 8 * npts, nn, m, dk, de);
             a.tr_out[(TR_G + 2) * a.trstride + base] = ksx * dk + etx * de;
             a.tr_out[(TR_G + 3) * a.trstride + base] = ksy * dk + ety * de;
+        }
+    }
+    if (quad_visc) {   // face values of the flux variable of the new state
+        for (int t = tid; t < 4 * nq; t += blockDim.x) {
+            const int s = t / nq, iq = t - s * nq;
+            double F[4];
+            vq_face_point(o, ngl, nq, nod + 7 * npts, nod + 8 * npts, s, iq, ksx, ksy, etx, ety, a.vqP, a.vqS, qbase, F);
+            for (int c = 0; c < 4; ++c) a.trq_out[c * a.trq_stride + ((size_t)e * 4 + s) * nq + iq] = F[c];
         }
     }
 }

@@ -222,6 +222,17 @@ inline int halo_exchange_traces(Solver& S, const Planes& tr, int nv) {
     S.n_launches += 2;
     return 0;
 }
+// slot planes of any width (width = nq: face values at the face quadrature points, method_visc == 1; the reference's
+// create_communicator_quad / bcl_create_communicator(.,4,nlayers,nq), src/create_rhs_communicator.F90:82-134)
+inline int halo_exchange_slot_planes(Solver& S, double* p, size_t stride, int nv, int width) {
+    if (S.nhalo == 0) return 0;
+    size_t tot = (size_t)S.nhalo * nv * width;
+    k_pack_traces<<<(tot + 255) / 256, 256, 0, S.stream>>>(p, stride, S.d_halo_slot, S.nhalo, nv, width, S.d_send);
+    if (halo_sendrecv(S, (size_t)nv * width)) return -1;
+    k_unpack_traces<<<(tot + 255) / 256, 256, 0, S.stream>>>(p, stride, S.nslots, S.nhalo, nv, width, S.d_recv);
+    S.n_launches += 2;
+    return 0;
+}
 // several sets of nodal planes in ONE message per neighbour: send[(h*NPT + p)*ngl + n] with p running over the planes of all
 // segments (NPT in total)
 struct HaloSeg { const double* planes; int np; size_t stride; double* hout; size_t hstride; };

@@ -231,6 +231,10 @@ static void fill_stage_args(Solver& S, StageArgs& a, Planes& qb, const Planes& q
     for (int v = 0; v < 11; ++v) a.acc_f[v] = S.acc_f[v];
     a.g = S.g; a.cd = S.cd; a.alpha_bot = S.alpha[S.nl - 1]; a.visc = S.visc;
     a.botfr = S.botfr; a.has_visc = S.has_visc; a.acc_graduvb = 1;
+    if (S.visc_q) {
+        a.visc_q = 1; a.vqP = S.vq_P; a.trq_stride = S.trq[0].stride;
+        for (int c = 0; c < 4; ++c) a.vqS[c] = S.vq_S[c];
+    }
 }
 
 // run-time-size kernels need the shared-memory opt-in above 48 kB (nop 8: 58 kB for the simple stage kernel)
@@ -258,6 +262,20 @@ static int prime_traces(Solver& S, const double* const* in, int mode, double* tr
     return 0;
 }
 
+// method_visc == 1: face values of the flux variable of a barotropic state + their halo copies
+static int prime_visc_q(Solver& S, const Planes& qb, Planes& trq) {
+    VqPrimeArgs p; memset(&p, 0, sizeof(p));
+    p.M = S.mesh;
+    for (int v = 0; v < 3; ++v) p.qb[v] = qb[v];
+    p.pbprime_df = S.pbprime_df; p.P = S.vq_P;
+    for (int c = 0; c < 4; ++c) p.S[c] = S.vq_S[c];
+    p.trq = trq.p; p.trq_stride = trq.stride;
+    size_t sm = (sops_doubles_host(S.ngl, S.nq) + 2 * S.npts) * sizeof(double);
+    k_viscq_prime<<<S.nelem, threads_for(S), sm, S.stream>>>(p);
+    S.n_launches++;
+    return halo_exchange_slot_planes(S, trq.p, trq.stride, 4, S.nq);
+}
+
 static int pair_pack(Solver& S, const Planes& qb, const Planes& qprime, int cur);
 static void fill_pair_args(Solver& S, PairArgs& a);
 static int halo_exchange_trace_records(Solver& S, double* tr, int tside, cudaStream_t st = nullptr);
@@ -279,9 +297,11 @@ int rhs_btp_only(Solver& S, Planes& qb, const Planes& qprime, double* d_rhs_out)
     }
     const double* in[3] = {qb[0], qb[1], qb[2]};
     prime_traces(S, in, 0, S.trace[0].p);
-    if (halo_exchange_traces(S, S.trace[0], S.has_visc ? 7 : 3)) return -1;
+    if (halo_exchange_traces(S, S.trace[0], (S.has_visc && !S.visc_q) ? 7 : 3)) return -1;
+    if (S.visc_q && prime_visc_q(S, qb, S.trq[0])) return -1;
     StageArgs a; fill_stage_args(S, a, qb, qprime);
     a.tr_in = S.trace[0].p; a.tr_out = S.trace[1].p; a.rhs_only = 1;
+    if (S.visc_q) { a.trq_in = S.trq[0].p; a.trq_out = S.trq[1].p; }
     for (int v = 0; v < 3; ++v) a.rhs_out[v] = d_rhs_out + (size_t)v * S.npoin;
     StageSmem L(S.ngl, S.nq);
     smem_opt_in(k_btp_stage_simple, L.total * sizeof(double));
@@ -301,12 +321,13 @@ int btp_solve(Solver& S, const Planes& qb_in, Planes& qb, const Planes& qprime) 
     cudaMemsetAsync(S.acc_q.p, 0, S.acc_q.stride * S.acc_q.n * sizeof(double), S.stream);
     cudaMemsetAsync(S.acc_f.p, 0, S.acc_f.stride * S.acc_f.n * sizeof(double), S.stream);
     cudaMemsetAsync(S.qb2w.p, 0, S.qb2w.stride * 3 * sizeof(double), S.stream);
-    const int ntr = S.has_visc ? 7 : 3;
+    const int ntr = (S.has_visc && !S.visc_q) ? 7 : 3;
     int cur = 0;
     {
         const double* in[3] = {qb[0], qb[1], qb[2]};
         prime_traces(S, in, 0, S.trace[cur].p);
         if (halo_exchange_traces(S, S.trace[cur], ntr)) return -1;
+        if (S.visc_q && prime_visc_q(S, qb, S.trq[cur])) return -1;
     }
     cudaEvent_t e_start, e_stop;
     take_event_pair(S, 0, e_start, e_stop);
@@ -321,9 +342,11 @@ int btp_solve(Solver& S, const Planes& qb_in, Planes& qb, const Planes& qprime) 
             a.store_q0 = (ik == 1 && S.kstages > 1);
             a.store_q2 = (S.kstages == 5 && ik == 2);
             a.tr_in = S.trace[cur].p; a.tr_out = S.trace[cur ^ 1].p;
+            if (S.visc_q) { a.trq_in = S.trq[cur].p; a.trq_out = S.trq[cur ^ 1].p; }
             if (launch_stage(S, a)) return -1;
             cur ^= 1;
             if (halo_exchange_traces(S, S.trace[cur], ntr)) return -1;
+            if (S.visc_q && halo_exchange_slot_planes(S, S.trq[cur].p, S.trq[cur].stride, 4, S.nq)) return -1;
         }
     }
     cudaEventRecord(e_stop, S.stream);
@@ -539,6 +562,15 @@ int btp_bcl_coeffs(Solver& S, const Planes& qprime, const Planes& dpv) {
     if (use_layer_warp(S, 1)) HN_LAUNCH_LW(k_bcl_coeffs_w, (lw_coeffs_smem<5, 9>()), (lw_coeffs_smem<4, 7>()), S, a);
     else HN_LAUNCH_GQL(k_bcl_coeffs, S, sm, a);
     S.n_launches++;
+    if (S.visc_q) {   // method_visc == 1: S_c = sum_k dpprime_visc_q(k) grad_c(u'_k), P = sum_k dpprime_visc_q(k) at the quadrature points
+        VqCoeffArgs v; memset(&v, 0, sizeof(v));
+        v.M = S.mesh; v.qprime = qprime.p; v.dpv = dpv.p; v.nstride = qprime.stride; v.P = S.vq_P;
+        for (int c = 0; c < 4; ++c) v.S[c] = S.vq_S[c];
+        const size_t smv = (sops_doubles_host(S.ngl, S.nq) + 3 * S.npts + 6 * (size_t)S.ngl * S.nq) * sizeof(double);
+        smem_opt_in(k_viscq_coeffs, smv);
+        k_viscq_coeffs<<<S.nelem, threads_for(S), smv, S.stream>>>(v);
+        S.n_launches++;
+    }
     if (S.has_visc && S.nhalo > 0) {
         // graduv_dpp_face exchange (mod_barotropic_terms.F90:393): per-layer planes and their layer sums -- ONE message per
         // neighbour for the four arrays (the reference sends them one by one)
@@ -588,7 +620,20 @@ static int layer_mass_and_consistency(Solver& S, const Planes& qprime, const Pla
 static int momentum_update(Solver& S, const Planes& qprime_in, const Planes& dpv, const Planes& q_in, Planes& q, Planes& qprime_out, const Planes& qb, int full_prime,
                            double* rhs_only_out = nullptr) {
     size_t per = S.ngl * S.nq;
-    if (S.has_visc) {
+    if (S.visc_q) {   // bcl_create_laplacian_v2 (mod_laplacian_quad.F90:252-355)
+        VqLayerArgs l; memset(&l, 0, sizeof(l));
+        l.M = S.mesh; l.qprime = qprime_in.p; l.dpv = dpv.p; l.nstride = dpv.stride; l.ub_df = S.ave_n[1]; l.vb_df = S.ave_n[2];
+        l.trq = S.trq_l.p; l.trq_stride = S.trq_l.stride; l.massinv = S.massinv; l.rhs_visc = S.rhs_visc.p; l.visc = S.visc;
+        size_t sm1 = (sops_doubles_host(S.ngl, S.nq) + 3 * S.npts) * sizeof(double);
+        k_bcl_lapq_traces<<<S.nelem, threads_for(S), sm1, S.stream>>>(l);
+        S.n_launches++;
+        if (halo_exchange_slot_planes(S, S.trq_l.p, S.trq_l.stride, 4 * S.nl, S.nq)) return -1;
+        size_t sm2 = (sops_doubles_host(S.ngl, S.nq) + 3 * S.npts + 6 * per + 4 * (size_t)S.nq2 + 2 * S.npts + 8 * S.nq) * sizeof(double);
+        smem_opt_in(k_bcl_lapq_apply, sm2);
+        k_bcl_lapq_apply<<<S.nelem, threads_for(S), sm2, S.stream>>>(l);
+        S.n_launches++;
+        if (phase_check(S, "k_bcl_lapq")) return -1;
+    } else if (S.has_visc) {
         LapArgs l; memset(&l, 0, sizeof(l));
         l.M = S.mesh; l.dpv = dpv.p; l.dpp_graduv = S.dpp_graduv.p; l.nstride = dpv.stride;
         for (int v = 0; v < 4; ++v) l.graduvb[v] = S.ave_n[3 + v];
@@ -775,9 +820,6 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     if (d->ngl < 2 || d->ngl > HN_MAXNGL || d->nq > HN_MAXNQ || d->nlayers < 1 || d->nlayers > HN_MAXL || d->kstages < 1 || d->kstages > 5) {
         set_error("hnumo_init", "unsupported sizes (ngl<=9, nq<=17, nlayers<=20, kstages<=5)"); return -2;
     }
-    if (d->method_visc == 1) {
-        set_error("hnumo_init", "method_visc==1 (quadrature-point viscosity) is not implemented (SURVEY 8(f) rank 4)"); return -3;
-    }
     if (d->ad_mlswe > 0.0 && !(d->max_shear_dz > 0.0)) {
         // mod_create_rhs_mlswe.F90:204-205 divides by max_shear_dz (namelist default 0): the reference would work with an infinite coefficient
         set_error("hnumo_init", "ad_mlswe > 0 needs max_shear_dz > 0"); return -2;
@@ -804,6 +846,9 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     S.ad = d->ad_mlswe > 0.0 ? d->ad_mlswe : 0.0; S.max_shear_dz = d->max_shear_dz;
     if (getenv("HNUMO_FORCE_VISC")) S.has_visc = 1;   // debugging aid: run the LDG code path with visc == 0
     S.variant = d->stage_kernel_variant;
+    // method_visc == 1: LDG viscosity with the flux variable at the quadrature points (visc_q.cuh), run-time-size kernels
+    S.visc_q = (d->method_visc == 1 && S.has_visc) ? 1 : 0;
+    if (S.visc_q) S.variant = 1;
     for (int k = 0; k < S.nl; ++k) S.alpha[k] = d->alpha_mlswe[k];
     for (int ik = 0; ik < S.kstages; ++ik) {
         for (int c = 0; c < 3; ++c) S.ssprk_a[ik][c] = d->ssprk_a[ik + S.kstages * c];
@@ -938,11 +983,17 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     S.rhs_mom = palloc(S, std::max(3, 2 * nl), NP);   // also the 3-plane scratch of hnumo_rhs_btp
     S.rhs_visc = palloc(S, 2 * nl, NP);
     if (S.ad > 0.0) S.rhs_full = palloc(S, 2 * nl, NP);   // complete rhs_mom, handed from k_mom_faces_update to k_shear_update
+    if (S.visc_q) {
+        const size_t trq = (size_t)(S.nslots + S.nhalo) * S.nq;
+        S.vq_P = dalloc(S, NQ); S.vq_S = palloc(S, 4, NQ);
+        S.trq[0] = palloc(S, 4, trq); S.trq[1] = palloc(S, 4, trq); S.trq_l = palloc(S, 4 * nl, trq);
+    }
     S.stage_buf = dalloc(S, std::max((size_t)3 * nl * NP, 4 * NP));
     size_t hs = (size_t)std::max(S.nhalo, 1) * S.ngl;
     S.h_q = palloc(S, 3 * nl, hs); S.h_dp = palloc(S, nl, hs); S.h_dpv = palloc(S, nl, hs); S.h_dpg = palloc(S, 4 * nl, hs);
     S.h_gub = palloc(S, 4, hs); S.h_stat = palloc(S, 5, hs);
     S.halo_capacity = (size_t)std::max(8, 5 * nl + 5) * hs;   // largest message: the merged viscosity exchange, 5 nl + 5 planes
+    if (S.visc_q) S.halo_capacity = std::max(S.halo_capacity, (size_t)4 * nl * S.nq * std::max(S.nhalo, 1));
     {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, S.device) == cudaSuccess) S.num_sms = prop.multiProcessorCount;

@@ -113,6 +113,12 @@ struct Solver {
     Planes slmf_f;  // 2 slot: sum_layer_mass_flux_face
     Planes rhs_mom, rhs_visc;  // 2*nl nodal planes each
     Planes rhs_full;           // 2*nl, only when ad > 0
+    // method_visc == 1 (visc_q.cuh): S_c, P at the quadrature points; face values of the flux variable in slot planes of width nq
+    int visc_q = 0;
+    double* vq_P = nullptr;
+    Planes vq_S;               // 4 quad planes
+    Planes trq[2];             // 4 planes of (nslots + nhalo) * nq: barotropic flux variable, ping-pong over the stages
+    Planes trq_l;              // 4*nl planes: layers
     double* stage_buf = nullptr;  // AoS staging for upload/download
     // halo copies of neighbour nodal traces on processor faces: [plane][nhalo*ngl]
     Planes h_q, h_dp, h_dpv, h_dpg, h_gub, h_stat;

@@ -49,7 +49,9 @@ typedef struct hnumo_desc {
     int32_t kstages, N_btp;
     double dt, dt_btp;
     /* physics switches: mod_input botfr, cd_mlswe, method_visc, visc_mlswe, ad_mlswe; gravity as reset by the
-     * test case (9.806, src/initial_conditions.F90:97). method_visc==1 is rejected (-3).  ad_mlswe > 0 switches the vertical
+     * test case (9.806, src/initial_conditions.F90:97).  method_visc == 1 selects the LDG viscosity with the flux variable at the
+     * quadrature points (src/mod_laplacian_quad.F90:125-223,252-355; run-time-size kernels), any other value the nodal form
+     * (:32-121,227-248); both are skipped when visc_mlswe == 0.  ad_mlswe > 0 switches the vertical
      * shear stress between the layers on (src/mod_create_rhs_mlswe.F90:146-279) and needs max_shear_dz > 0 (last member). */
     int32_t botfr, method_visc;
     double gravity, cd_mlswe, visc_mlswe, ad_mlswe;

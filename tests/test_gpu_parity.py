@@ -181,6 +181,79 @@ def test_vertical_shear_stress(name):
     S.close()
 
 
+VISCQ_DECKS = {
+    "double_gyre": lambda: dict(hn.decks.SHIPPED["double_gyre"], nelx=6, nely=6, method_visc=1),
+    "synth3": lambda: dict(hn.decks.synthetic_double_gyre(6, 5, nop=4, nlayers=3), method_visc=1),
+    "noslip_rk3": lambda: dict(hn.decks.SHIPPED["double_gyre"], nelx=5, nely=4, x_boundary=(2, 2), kstages=3, botfr=2, cd_mlswe=1e-3, method_visc=1),
+    "nop3_5layers": lambda: dict(hn.decks.synthetic_double_gyre(4, 4, nop=3, nlayers=5), method_visc=1),
+    "nop8": lambda: dict(hn.decks.synthetic_double_gyre(3, 3, nop=8, nlayers=3), method_visc=1),
+    # a strong viscosity, so that an error in the term could not hide below the tolerance
+    "strong": lambda: dict(hn.decks.synthetic_double_gyre(5, 5, nop=4, nlayers=2), method_visc=1, visc_mlswe=5.0e4),
+}
+
+
+@pytest.mark.parametrize("name", list(VISCQ_DECKS))
+def test_quadrature_point_viscosity(name):
+    """method_visc == 1 (btp_create_laplacian_v2 / bcl_create_laplacian_v2, mod_laplacian_quad.F90:125-223,
+    252-355) against the oracle: the barotropic RHS and the layer momentum RHS on a developed state, then whole steps; and the
+    result differs from the nodal form (method_visc == 3) by far more than the tolerance, i.e. the other code path really ran."""
+    p = VISCQ_DECKS[name]()
+    deck, S, O = make_pair(p)
+    O.step(1)
+    sync_state_from_oracle(S, O)
+    O.btp_bcl_coeffs(); S.btp_bcl_coeffs()
+    r_o, r_g = O.rhs_btp(), S.rhs_btp()
+    assert rel_l2(r_g[:, 0], r_o[:, 0], floor=1e-30) < 1e-11
+    Hn = np.linalg.norm(O.get("H_bcl")) / np.sqrt(O.npoin_q)
+    scale = Hn * np.sqrt(deck["massinv"].max())
+    for v in (1, 2):
+        assert np.abs(r_g[:, v] - r_o[:, v]).max() <= 2e-14 * scale, (v, name, np.abs(r_g[:, v] - r_o[:, v]).max() / scale)
+    O.btp_substeps(); S.btp_substeps()
+    sync_state_from_oracle(S, O)          # same barotropic state on both sides for the layer phase (as in test_layer_phase_parity)
+    m_o, m_g = O.layer_momentum_rhs(), S.layer_momentum_rhs()
+    assert np.abs(m_g - m_o).max() <= 2e-14 * scale, (name, np.abs(m_g - m_o).max() / scale)
+    n = 3
+    assert S.step(n) == 0 and O.step(n) == 0
+    e = natural_errors(S, O, deck)
+    assert e["mass"] < 1e-10 and e["mom"] < 1e-11, e
+    O3 = oracle_lib.Oracle(dict(p, method_visc=3, affine_metrics=True))
+    assert O3.step(n + 1) == 0
+    qa = O.get("q_df").reshape(deck["nlayers"], -1, 3); q3 = O3.get("q_df").reshape(deck["nlayers"], -1, 3)
+    c = np.sqrt(deck["gravity"] * float(np.max(-deck["zbot_df"])))
+    differ = max(np.linalg.norm(qa[k, :, v] - q3[k, :, v]) / (c * np.linalg.norm(qa[k, :, 0])) for k in range(deck["nlayers"]) for v in (1, 2))
+    assert differ > 100 * e["mom"], (differ, e)
+    S.close()
+
+
+@pytest.mark.parametrize("nranks,partition", [(2, "rows"), (4, "morton")])
+def test_quadrature_point_viscosity_partitioned(nranks, partition):
+    """method_visc == 1 on a partition: the face values of the flux variable travel in one message per neighbour and stage
+    (width nq; create_communicator_quad, src/create_rhs_communicator.F90:82-134).  Like the nodal form, the as-written LDG face
+    flux takes the evaluating rank's element as the left one on a processor face, so the result depends on the partition at
+    O(visc) -- the same tolerance as test_partitioned_equals_single."""
+    params = dict(hn.decks.SHIPPED["double_gyre"], nelx=6, nely=8, method_visc=1)
+    if partition != "rows":
+        params["partition"] = partition
+    single = hn.decks.build_deck(params)
+    S = hn.Solver(single)
+    S.upload_state(single["q_df"], single["qb_df"], single["qprime_df"])
+    assert S.step(3) == 0
+    q1, qb1, qp1 = S.download_state()
+    S.close()
+    decks, outs = _run_partitioned(params, nranks, 3, gid=700 + nranks)
+    npts = single["npts"]
+    c = np.sqrt(single["gravity"] * 9928.0)
+    tol = 1e-10
+    for d, (q, qb, qp) in zip(decks, outs):
+        idx = (d["elem_global"][:, None] * npts + np.arange(npts)[None, :]).ravel()
+        assert rel_l2(qb[:, 0], qb1[idx, 0]) < tol
+        assert rel_l2(q[:, :, 0], q1[:, idx, 0]) < 10 * tol
+        for v in (2, 3):
+            assert np.linalg.norm(qb[:, v] - qb1[idx, v]) / (c * np.linalg.norm(qb1[idx, 0])) < tol
+        for v in (1, 2):
+            assert np.linalg.norm(q[:, :, v] - q1[:, idx, v]) / (c * np.linalg.norm(q1[:, idx, 0])) < tol
+
+
 def test_high_order_many_layers():
     """BASELINE config 5 in small: nop=8 (ngl=9, nq=17), 10 layers -- orders without a compile-time instantiation run the
     run-time-size kernels; nl > 3 uses the intent semantics of SURVEY 8 hazard 1 in both the oracle and the library"""

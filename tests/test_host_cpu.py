@@ -328,7 +328,6 @@ def test_fortran_d23_16_formatting(tmp_path):
 
 
 @pytest.mark.parametrize("change,code,text", [
-    (dict(method_visc=1), -3, "method_visc"),                      # quadrature-point viscosity: not implemented
     (dict(ad_mlswe=1.0e-3), -2, "max_shear_dz"),                   # vertical shear stress needs its length scale (division by max_shear_dz)
     (dict(nlayers=0), -2, "unsupported sizes"),
     (dict(kstages=6), -2, "unsupported sizes"),
