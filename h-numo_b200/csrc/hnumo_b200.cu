@@ -419,7 +419,8 @@ static int pair_pack(Solver& S, const Planes& qb, const Planes& qprime, int cur)
     p.pbv = S.pbprime_visc; p.pbn = S.pbn; p.hstat = S.h_stat.p; p.hstat_stride = S.h_stat.stride;
     p.rec = S.p_rec; p.tr = S.p_tr[cur];
     p.has_visc = S.has_visc;
-    k_pair_pack<<<S.nelem, 128, 2 * S.npts * sizeof(double), S.stream>>>(p);
+    static const int pack_threads = getenv("HNUMO_PACK_THREADS") ? atoi(getenv("HNUMO_PACK_THREADS")) : 128;
+    k_pair_pack<<<S.nelem, pack_threads, 2 * S.npts * sizeof(double), S.stream>>>(p);
     S.n_launches++;
     return halo_exchange_trace_records(S, S.p_tr[cur], D.TSIDE);
 }

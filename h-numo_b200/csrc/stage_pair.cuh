@@ -773,11 +773,13 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
             V::ld(Lr + 0 * NP + I, t0); V::ld(Lr + 1 * NP + I, t1); V::ld(Lr + 2 * NP + I, t2); V::ld(Lr + 3 * NP + I, t3);
             PR_FORC { l0[c] = -(t0[c] + t2[c]); l1[c] = -(t1[c] + t3[c]); }
         }
+        // a node lies on at most one eta-side (s = 0, 1) and one ksi-side (s = 2, 3): two gathers with a per-lane side instead of
+        // four predicated ones (same additions in the same order: sides in ascending order)
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const bool on = (s == 0) ? (m == 0) : (s == 1) ? (m == G - 1) : (s == 2) ? (n == 0) : (n == G - 1);
-            if (!on) continue;
-            const int nf = (s < 2) ? n : m;
+        for (int pass = 0; pass < 2; ++pass) {
+            const int s = (pass == 0) ? ((m == 0) ? 0 : (m == G - 1) ? 1 : -1) : ((n == 0) ? 2 : (n == G - 1) ? 3 : -1);
+            if (s < 0) continue;
+            const int nf = (pass == 0) ? n : m;
             double p0[NE], p1[NE], p2[NE];
             V::ld(T + (s * 3 + 0) * G + nf, p0); V::ld(T + (s * 3 + 1) * G + nf, p1); V::ld(T + (s * 3 + 2) * G + nf, p2);
             PR_FORC { r0[c] += p0[c]; r1[c] += p1[c]; r2[c] += p2[c]; }

@@ -108,6 +108,12 @@ def test_phase_parity(name, variant):
         a, b = S.get_array(nm), O.get(nm)
         assert np.linalg.norm(a - b) / np.sqrt(b.size) < 1e-11 * scale, nm
         assert rel_l2(a, b, floor=1e-30) < 1e-5 or np.linalg.norm(b) / np.sqrt(b.size) < 1e-9 * scale, nm
+    if deck["visc_mlswe"] != 0.0:
+        # graduvb_ave: time average of the LDG auxiliary variable grad(ub, vb) (mod_laplacian_quad.F90:56), compared directly; its
+        # scale is c / dx with 1/dx ~ sqrt(massinv) (the default kernel derives it after the loop from the nodal velocity sums)
+        a, b = S.get_array("graduvb_ave"), O.get("graduvb_ave")
+        assert np.linalg.norm(a - b) / np.sqrt(b.size) < 1e-11 * c * np.sqrt(deck["massinv"].max()), "graduvb_ave"
+        assert rel_l2(a, b, floor=1e-30) < 1e-5 or np.linalg.norm(b) / np.sqrt(b.size) < 1e-9 * c * np.sqrt(deck["massinv"].max()), "graduvb_ave"
     e = natural_errors(S, O, deck)
     assert e["mass"] < 1e-10 and e["mom"] < 1e-11, e
     S.close()
@@ -252,6 +258,23 @@ def test_quadrature_point_viscosity_partitioned(nranks, partition):
             assert np.linalg.norm(qb[:, v] - qb1[idx, v]) / (c * np.linalg.norm(qb1[idx, 0])) < tol
         for v in (1, 2):
             assert np.linalg.norm(q[:, :, v] - q1[:, idx, v]) / (c * np.linalg.norm(q1[:, idx, 0])) < tol
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("kstages", [1, 2, 4])
+def test_ssprk_stage_counts(kstages, variant):
+    """the SSPRK tables of mod_initial_mlswe.F90:652-678 other than the shipped (5,3) and the (3,3) of the no-slip deck: kstages = 1
+    (forward Euler), 2 and 4 -- the load/store pattern of the SSPRK work states in the stage kernel differs for each.  The low-order
+    schemes need a smaller barotropic step for stability."""
+    base = hn.decks.synthetic_double_gyre(6, 6, nop=4, nlayers=3)
+    cut = {1: 8.0, 2: 4.0, 4: 2.0}[kstages]
+    p = dict(hn.decks.synthetic_double_gyre(6, 6, nop=4, nlayers=3, dt_btp=base["dt_btp"] / cut, dt=base["dt_btp"] / cut * 10), kstages=kstages)
+    deck, S, O = make_pair(p, variant=variant)
+    assert deck["kstages"] == kstages
+    assert S.step(3) == 0 and O.step(3) == 0
+    e = natural_errors(S, O, deck)
+    assert e["mass"] < 1e-10 and e["mom"] < 1e-11, e
+    S.close()
 
 
 def test_high_order_many_layers():
