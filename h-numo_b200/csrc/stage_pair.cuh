@@ -174,9 +174,16 @@ __device__ __forceinline__ int pr_face_node(int s, int n) {
 #ifndef HN_BLK_MAXNREG
 #define HN_BLK_MAXNREG 96    // registers per thread of the block-per-element form: 96 -> 5 blocks of 128 threads per SM (no spills; 0.494 of the roofline vs 0.464 with 128 registers and 4 blocks)
 #endif
+#ifndef HN_WARP_MAXNREG
+#define HN_WARP_MAXNREG 128  // registers per thread of the warp-per-element form: 128 -> 16 warps per SM (96 -> 20 warps with 11.3 kB of shared
+                             // memory per warp was measured equal: 1.353 vs 1.360 ms per stage at 500x500 elements, profiles/r2_stage_kernel_experiments.md)
+#endif
+#ifndef HN_BLK_W
+#define HN_BLK_W 4           // warps per element of the block-per-element form at nop 8 (5: 1.308 ms, 6: 1.38-1.54 ms, 4: 1.231 ms per stage at 250x250)
+#endif
 template <int NT> __device__ __forceinline__ void pr_sync() { if (NT == 32) __syncwarp(); else __syncthreads(); }
 template <int G, int Q, int NE, int W, bool VISC, int BOTFR, bool BLK = false>
-__global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE == 2 ? (W == 4 ? 224 : 168) : 128) k_btp_stage_pair(const PairArgs a) {
+__global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE == 2 ? (W == 4 ? 224 : 168) : HN_WARP_MAXNREG) k_btp_stage_pair(const PairArgs a) {
     using R = PairRec<G, Q>;
     using V = PV<NE>;
     typedef typename V::T VT;
@@ -1086,7 +1093,7 @@ inline int launch_stage_pair(Solver& S, const PairArgs& a) {
     if (S.ngl == 5 && S.nq == 9) return launch_pair_t<5, 9>(S, a);
     if (S.ngl == 4 && S.nq == 7) return launch_pair_t<4, 7>(S, a);
     // nop 8: one element per block of 128 threads (81 nodes, 119 pass-2 lines, 68 face points fit; 289 quadrature points in 3 sweeps)
-    if (S.ngl == 9 && S.nq == 17) return launch_pair_w<9, 17, 1, 4, true>(S, a);   // (96 threads per element measured slower: 0.41 vs 0.47)
+    if (S.ngl == 9 && S.nq == 17) return launch_pair_w<9, 17, 1, HN_BLK_W, true>(S, a);   // (96 threads per element measured slower: 0.41 vs 0.47)
     if (S.ngl == 8 && S.nq == 15) return launch_pair_w<8, 15, 1, 4, true>(S, a);
     if (S.ngl == 7 && S.nq == 13) return launch_pair_w<7, 13, 1, 4, true>(S, a);
     if (S.ngl == 6 && S.nq == 11) return launch_pair_w<6, 11, 1, 4, true>(S, a);
