@@ -68,6 +68,8 @@ class Desc(C.Structure):
         ("nbh_proc", C.c_void_p), ("num_send_recv", C.c_void_p), ("nbh_send_recv", C.c_void_p),
         ("device", C.c_int32), ("stage_kernel_variant", C.c_int32),
         ("max_shear_dz", C.c_double),
+        ("point_metrics_q", C.c_void_p), ("point_metrics", C.c_void_p), ("face_geom_q", C.c_void_p), ("face_geom_n", C.c_void_p),
+        ("coord", C.c_void_p),
     ]
 
 
@@ -133,7 +135,7 @@ class Solver:
         self.deck = deck
         self._keep = []
         d = Desc()
-        d.abi_version = 2
+        d.abi_version = 3
         for k in ("nelem", "ngl", "nq", "nlayers", "nface", "kstages", "N_btp", "botfr", "method_visc", "rank", "nranks"):
             setattr(d, k, int(deck[k]))
         for k in ("dt", "dt_btp", "gravity", "cd_mlswe", "visc_mlswe", "ad_mlswe"):
@@ -151,7 +153,7 @@ class Solver:
             setattr(d, k, a.ctypes.data)
         for k in ("wnq", "wgl", "elem_metrics", "face_geom", "pbprime_df", "massinv", "coriolis_df", "tau_wind_df", "zbot_df",
                   "alpha_mlswe", "ssprk_beta"):
-            setattr(d, k, ptr(deck[k], np.float64))
+            setattr(d, k, ptr(deck[k], np.float64) if deck.get(k) is not None else None)   # elem_metrics / face_geom: None for general quadrilaterals
         d.face = ptr(deck["face"], np.int32)
         d.num_nbh = len(deck["nbh_proc"])
         d.nbh_proc = ptr(deck["nbh_proc"], np.int32) if d.num_nbh else None
@@ -160,6 +162,9 @@ class Solver:
         d.device = device
         d.stage_kernel_variant = variant
         d.max_shear_dz = float(deck.get("max_shear_dz", 0.0))
+        if deck.get("point_metrics_q") is not None:   # general quadrilaterals: geometry per point ((npoin_q,5), (npoin,5), (nface,nq,3), (nface,ngl,3), (npoin,2))
+            for k in ("point_metrics_q", "point_metrics", "face_geom_q", "face_geom_n", "coord"):
+                setattr(d, k, ptr(np.ascontiguousarray(deck[k], dtype=np.float64).reshape(-1), np.float64) if deck.get(k) is not None else None)
         self.h = C.c_void_p()
         rc = self.L.hnumo_init(C.byref(d), C.byref(self.h))
         if rc != 0:

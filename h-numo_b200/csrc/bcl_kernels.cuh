@@ -56,7 +56,8 @@ __global__ void k_bcl_coeffs(CoeffArgs a) {
     double Quu = 0, Quv = 0, Qvv = 0, H = 0, pprime = 0;             // quad thread accumulators
     double eu = 0, euv = 0, ev = 0, eH = 0, ppl = 0, ppr = 0;         // face-quad thread accumulators
     double bsum[4] = {0, 0, 0, 0}, pvs = 0;                           // nodal thread accumulators
-    const double ksx = a.M.em[e * 5 + 0], ksy = a.M.em[e * 5 + 1], etx = a.M.em[e * 5 + 2], ety = a.M.em[e * 5 + 3];
+    // metric terms of this thread's quadrature point (phases `tid < nq2`) and of its node (phases `tid < npts`); per element on affine meshes
+    const Met mq_ = met_q(a.M, e, tid < nq2 ? tid : 0), mn_ = met_n(a.M, e, tid < npts ? tid : 0);
     for (int k = 0; k < nl; ++k) {
         __syncthreads();
         if (tid < npts)
@@ -69,7 +70,8 @@ __global__ void k_bcl_coeffs(CoeffArgs a) {
             for (int v = 0; v < 3; ++v)
                 nv[v] = nb_nodal(a.M, a.qprime + (size_t)(v * nl + k) * a.nstride, a.hq + (size_t)(v * nl + k) * a.hstride, nb, nbs, n, ow[v]);
             if (nb == NBR_FREESLIP) {
-                double nx = a.M.fgeom[slot * 3], ny = a.M.fgeom[slot * 3 + 1];
+                const FGeo fgn_ = fg_n(a.M, slot, n);
+                double nx = fgn_.nx, ny = fgn_.ny;
                 double un = ow[1] * nx + ow[2] * ny;
                 nv[1] = ow[1] - 2.0 * un * nx; nv[2] = ow[2] - 2.0 * un * ny;
             } else if (nb == NBR_NOSLIP) { nv[1] = -ow[1]; nv[2] = -ow[2]; }
@@ -113,9 +115,9 @@ __global__ void k_bcl_coeffs(CoeffArgs a) {
             int m = tid / ngl, n = tid - m * ngl;
             double dk, de, gv[4];
             nodal_grad(o, ngl, nod + npts, n, m, dk, de);
-            gv[0] = ksx * dk + etx * de; gv[1] = ksy * dk + ety * de;
+            gv[0] = mn_.ksx * dk + mn_.etx * de; gv[1] = mn_.ksy * dk + mn_.ety * de;
             nodal_grad(o, ngl, nod + 2 * npts, n, m, dk, de);
-            gv[2] = ksx * dk + etx * de; gv[3] = ksy * dk + ety * de;
+            gv[2] = mn_.ksx * dk + mn_.etx * de; gv[3] = mn_.ksy * dk + mn_.ety * de;
             double d = a.dpv[(size_t)k * a.nstride + nbase + tid];
             for (int v = 0; v < 4; ++v) {
                 double t = d * gv[v];
@@ -170,7 +172,8 @@ __global__ void k_layer_mass(MassArgs a) {
     double* adv = tR + per;            // [npts]
     double* ff = adv + npts;           // [4][nq]
     const size_t nbase = (size_t)e * npts, qbase = (size_t)e * nq2;
-    const double ksx = a.M.em[e * 5 + 0], ksy = a.M.em[e * 5 + 1], etx = a.M.em[e * 5 + 2], ety = a.M.em[e * 5 + 3], J = a.M.em[e * 5 + 4];
+    // metric terms of this thread's quadrature point (phases `tid < nq2`) and of its node (phases `tid < npts`); per element on affine meshes
+    const Met mq_ = met_q(a.M, e, tid < nq2 ? tid : 0), mn_ = met_n(a.M, e, tid < npts ? tid : 0);
     double sx = 0, sy = 0, sfx = 0, sfy = 0;
     for (int k = 0; k < nl; ++k) {
         __syncthreads();
@@ -184,7 +187,8 @@ __global__ void k_layer_mass(MassArgs a) {
             for (int v = 0; v < 3; ++v)
                 nv[v] = nb_nodal(a.M, a.qprime + (size_t)(v * nl + k) * a.nstride, a.hq + (size_t)(v * nl + k) * a.hstride, nb, nbs, n, ow[v]);
             if (nb == NBR_FREESLIP) {
-                double nx = a.M.fgeom[slot * 3], ny = a.M.fgeom[slot * 3 + 1];
+                const FGeo fgn_ = fg_n(a.M, slot, n);
+                double nx = fgn_.nx, ny = fgn_.ny;
                 double un = ow[1] * nx + ow[2] * ny;
                 nv[1] = ow[1] - 2.0 * un * nx; nv[2] = ow[2] - 2.0 * un * ny;
             } else if (nb == NBR_NOSLIP) { nv[1] = -ow[1]; nv[2] = -ow[2]; }
@@ -200,16 +204,17 @@ __global__ void k_layer_mass(MassArgs a) {
             double udp = (q1 + a.ave_q[8][Iq]) * dp_temp;
             double vdp = (q2 + a.ave_q[9][Iq]) * dp_temp;
             sx = sx + udp; sy = sy + vdp;
-            double wq = o.wq[i] * o.wq[j] * J;
-            fq[tid] = wq * (ksx * udp + ksy * vdp);
-            fq[nq2 + tid] = wq * (etx * udp + ety * vdp);
+            double wq = o.wq[i] * o.wq[j] * mq_.J;
+            fq[tid] = wq * (mq_.ksx * udp + mq_.ksy * vdp);
+            fq[nq2 + tid] = wq * (mq_.etx * udp + mq_.ety * vdp);
         }
         if (tid < 4 * nq) {
             int s = tid / nq, iq = tid - s * nq, slot = e * 4 + s, nb = a.M.nbr[slot], nbs = a.M.nbslot[slot];
             bool left = (nb < 0) || (e < nb);
             int oslot = left ? slot : nb * 4 + nbs;
             size_t fo = (size_t)oslot * nq + iq;
-            double nxl = a.M.fgeom[slot * 3], nyl = a.M.fgeom[slot * 3 + 1], nlen = a.M.fgeom[slot * 3 + 2];
+            const FGeo fgq_ = fg_q(a.M, slot, iq);
+            double nxl = fgq_.nx, nyl = fgq_.ny, nlen = fgq_.len;
             double qo[3] = {0, 0, 0}, qn[3] = {0, 0, 0};
             for (int n = 0; n < ngl; ++n) {
                 double hi = o.A[n + ngl * iq];
@@ -287,7 +292,8 @@ __global__ void k_consistency(ConsArgs a) {
     double* adv = tR + per;
     double* ff = adv + npts;                   // [4][nq]
     const size_t nbase = (size_t)e * npts, qbase = (size_t)e * nq2;
-    const double ksx = a.M.em[e * 5 + 0], ksy = a.M.em[e * 5 + 1], etx = a.M.em[e * 5 + 2], ety = a.M.em[e * 5 + 3], J = a.M.em[e * 5 + 4];
+    // metric terms of this thread's quadrature point (phases `tid < nq2`) and of its node (phases `tid < npts`); per element on affine meshes
+    const Met mq_ = met_q(a.M, e, tid < nq2 ? tid : 0), mn_ = met_n(a.M, e, tid < npts ? tid : 0);
     // dpprime_df = q_df(1)/ (sum_k q_df(1) / pbprime_df)      (mod_splitting.F90:350-353)
     if (tid < npts) {
         double s = 0.0;
@@ -322,16 +328,17 @@ __global__ void k_consistency(ConsArgs a) {
             double weight = dp / a.pbprime_q[Iq];
             double udp = weight * (a.ave_q[6][Iq] - a.slmf_q[0][Iq]);
             double vdp = weight * (a.ave_q[7][Iq] - a.slmf_q[1][Iq]);
-            double wq = o.wq[i] * o.wq[j] * J;
-            fq[tid] = wq * (ksx * udp + ksy * vdp);
-            fq[nq2 + tid] = wq * (etx * udp + ety * vdp);
+            double wq = o.wq[i] * o.wq[j] * mq_.J;
+            fq[tid] = wq * (mq_.ksx * udp + mq_.ksy * vdp);
+            fq[nq2 + tid] = wq * (mq_.etx * udp + mq_.ety * vdp);
         }
         if (tid < 4 * nq) {
             int s = tid / nq, iq = tid - s * nq, slot = e * 4 + s, nb = a.M.nbr[slot], nbs = a.M.nbslot[slot];
             bool left = (nb < 0) || (e < nb);
             int oslot = left ? slot : nb * 4 + nbs;
             size_t fo = (size_t)oslot * nq + iq;
-            double nxl = a.M.fgeom[slot * 3], nyl = a.M.fgeom[slot * 3 + 1], nlen = a.M.fgeom[slot * 3 + 2];
+            const FGeo fgq_ = fg_q(a.M, slot, iq);
+            double nxl = fgq_.nx, nyl = fgq_.ny, nlen = fgq_.len;
             double qo = 0.0, qn = 0.0;
             for (int n = 0; n < ngl; ++n) {
                 double hi = o.A[n + ngl * iq];
@@ -392,7 +399,6 @@ __global__ void k_bcl_laplacian(LapArgs a) {
     double* qq = gub + 4 * npts;               // [4][npts]
     double* lf = qq + 4 * npts;                // [4][2][ngl]
     const size_t nbase = (size_t)e * npts;
-    const double ksx = a.M.em[e * 5 + 0], ksy = a.M.em[e * 5 + 1], etx = a.M.em[e * 5 + 2], ety = a.M.em[e * 5 + 3], J = a.M.em[e * 5 + 4];
     if (tid < npts) for (int v = 0; v < 4; ++v) gub[v * npts + tid] = a.graduvb[v][nbase + tid];
     for (int k = 0; k < nl; ++k) {
         __syncthreads();
@@ -404,7 +410,8 @@ __global__ void k_bcl_laplacian(LapArgs a) {
         if (tid >= npts && tid < npts + 4 * ngl) {
             int t = tid - npts, s = t / ngl, n = t - s * ngl, slot = e * 4 + s, nb = a.M.nbr[slot], nbs = a.M.nbslot[slot];
             bool left = (nb < 0) || (e < nb);
-            double nx = a.M.fgeom[slot * 3], ny = a.M.fgeom[slot * 3 + 1], nlen = a.M.fgeom[slot * 3 + 2];
+            const FGeo fgn_ = fg_n(a.M, slot, n);
+            double nx = fgn_.nx, ny = fgn_.ny, nlen = fgn_.len;
             int I = face_node(s, n, ngl);
             double go[4], gn[4], so[5], sn[5];
             for (int v = 0; v < 4; ++v) {
@@ -445,11 +452,12 @@ __global__ void k_bcl_laplacian(LapArgs a) {
             int m = tid / ngl, n = tid - m * ngl;
             double l0 = 0.0, l1 = 0.0;
             for (int kk = 0; kk < ngl; ++kk) {
-                double wk1 = o.wg[kk] * o.wg[m] * J * o.D[n + ngl * kk];
-                double wk2 = o.wg[n] * o.wg[kk] * J * o.D[m + ngl * kk];
                 int I1 = m * ngl + kk, I2 = kk * ngl + n;
-                l0 -= wk1 * (ksx * qq[I1] + ksy * qq[npts + I1]) + wk2 * (etx * qq[I2] + ety * qq[npts + I2]);
-                l1 -= wk1 * (ksx * qq[2 * npts + I1] + ksy * qq[3 * npts + I1]) + wk2 * (etx * qq[2 * npts + I2] + ety * qq[3 * npts + I2]);
+                const Met m1 = met_n(a.M, e, I1), m2 = met_n(a.M, e, I2);   // metric terms at the collocation point of the sum
+                double wk1 = o.wg[kk] * o.wg[m] * m1.J * o.D[n + ngl * kk];
+                double wk2 = o.wg[n] * o.wg[kk] * m2.J * o.D[m + ngl * kk];
+                l0 -= wk1 * (m1.ksx * qq[I1] + m1.ksy * qq[npts + I1]) + wk2 * (m2.etx * qq[I2] + m2.ety * qq[npts + I2]);
+                l1 -= wk1 * (m1.ksx * qq[2 * npts + I1] + m1.ksy * qq[3 * npts + I1]) + wk2 * (m2.etx * qq[2 * npts + I2] + m2.ety * qq[3 * npts + I2]);
             }
             if (m == 0) { l0 += lf[(0 * 2 + 0) * ngl + n]; l1 += lf[(0 * 2 + 1) * ngl + n]; }
             if (m == ngl - 1) { l0 += lf[(1 * 2 + 0) * ngl + n]; l1 += lf[(1 * 2 + 1) * ngl + n]; }
@@ -490,7 +498,8 @@ __global__ void k_mom_volume(MomVolArgs a) {
     double* tR = tP + 2 * per;                 // [2][per]
     double* out = tR + 2 * per;                // [2][npts]
     const size_t nbase = (size_t)e * npts, qbase = (size_t)e * nq2;
-    const double ksx = a.M.em[e * 5 + 0], ksy = a.M.em[e * 5 + 1], etx = a.M.em[e * 5 + 2], ety = a.M.em[e * 5 + 3], J = a.M.em[e * 5 + 4];
+    // metric terms of this thread's quadrature point (phases `tid < nq2`) and of its node (phases `tid < npts`); per element on affine meshes
+    const Met mq_ = met_q(a.M, e, tid < nq2 ? tid : 0), mn_ = met_n(a.M, e, tid < npts ? tid : 0);
     const double eps1 = 1.0e-20;
     const double Pstress = (a.g / a.alpha[0]) * 50.0, Pbstress = (a.g / a.alpha[nl - 1]) * 10.0;
     // per quadrature point, per layer
@@ -518,8 +527,8 @@ __global__ void k_mom_volume(MomVolArgs a) {
             if (qa) {
                 double dks = sf_eval(o, ngl, nq, tB, 0, i, j);    // d/dksi: B in first direction, A in second
                 double det = sf_eval_B(o, ngl, nq, tA, 0, i, j);  // d/deta
-                gradz1[k] = ksx * dks + etx * det;
-                gradz2[k] = ksy * dks + ety * det;
+                gradz1[k] = mq_.ksx * dks + mq_.etx * det;
+                gradz2[k] = mq_.ksy * dks + mq_.ety * det;
             }
         }
     }
@@ -552,7 +561,7 @@ __global__ void k_mom_volume(MomVolArgs a) {
         size_t Iq = qbase + tid;
         uu_def = a.ave_q[2][Iq] - s_uu; uv_def = a.ave_q[4][Iq] - s_uv; vv_def = a.ave_q[3][Iq] - s_vv;
         oosu = 1.0 / s_tu; oosv = 1.0 / s_tv;
-        wq = o.wq[i] * o.wq[j] * J;
+        wq = o.wq[i] * o.wq[j] * mq_.J;
         pbq = a.pbprime_q[Iq]; twx = a.tauwx_q[Iq]; twy = a.tauwy_q[Iq]; tbx = a.ave_q[10][Iq]; tby = a.ave_q[11][Iq]; Hav = a.ave_q[1][Iq];
     }
     double ppt = 0.0;  // pprime_temp(k)
@@ -580,10 +589,10 @@ __global__ void k_mom_volume(MomVolArgs a) {
             double Fx1 = Hq + var_uu, Fy1 = var_uv, Fx2 = var_vu, Fy2 = Hq + var_vv;
             fq[0 * nq2 + tid] = wq * source_x;
             fq[1 * nq2 + tid] = wq * source_y;
-            fq[2 * nq2 + tid] = wq * (ksx * Fx1 + ksy * Fy1);
-            fq[3 * nq2 + tid] = wq * (ksx * Fx2 + ksy * Fy2);
-            fq[4 * nq2 + tid] = wq * (etx * Fx1 + ety * Fy1);
-            fq[5 * nq2 + tid] = wq * (etx * Fx2 + ety * Fy2);
+            fq[2 * nq2 + tid] = wq * (mq_.ksx * Fx1 + mq_.ksy * Fy1);
+            fq[3 * nq2 + tid] = wq * (mq_.ksx * Fx2 + mq_.ksy * Fy2);
+            fq[4 * nq2 + tid] = wq * (mq_.etx * Fx1 + mq_.ety * Fy1);
+            fq[5 * nq2 + tid] = wq * (mq_.etx * Fx2 + mq_.ety * Fy2);
         }
         __syncthreads();
         sf_scatter(o, ngl, nq, 2, fq, fq + 2 * nq2, fq + 4 * nq2, nq2, tP, tR, out, npts, false);
@@ -638,7 +647,8 @@ __global__ void k_mom_faces_update(MomFaceArgs a) {
             nv[v] = nb_nodal(a.M, a.qprime + (size_t)(v * nl + k) * a.nstride, a.hq + (size_t)(v * nl + k) * a.hstride, nb, nbs, n, ow[v]);
         }
         if (nb == NBR_FREESLIP) {
-            double nx = a.M.fgeom[slot * 3], ny = a.M.fgeom[slot * 3 + 1];
+            const FGeo fgn_ = fg_n(a.M, slot, n);
+            double nx = fgn_.nx, ny = fgn_.ny;
             double un = ow[1] * nx + ow[2] * ny;
             nv[1] = ow[1] - 2.0 * un * nx; nv[2] = ow[2] - 2.0 * un * ny;
         } else if (nb == NBR_NOSLIP) { nv[1] = -ow[1]; nv[2] = -ow[2]; }
@@ -650,7 +660,8 @@ __global__ void k_mom_faces_update(MomFaceArgs a) {
         bool left = (nb < 0) || (e < nb);
         int oslot = left ? slot : nb * 4 + nbs;
         size_t fo = (size_t)oslot * nq + iq;
-        double nxl = a.M.fgeom[slot * 3], nyl = a.M.fgeom[slot * 3 + 1], nlen = a.M.fgeom[slot * 3 + 2];
+        const FGeo fgq_ = fg_q(a.M, slot, iq);
+            double nxl = fgq_.nx, nyl = fgq_.ny, nlen = fgq_.len;
         const double* tl = left ? ownq : nbq;
         const double* tr = left ? nbq : ownq;
         double ql0[LMAX], qr0[LMAX];
@@ -812,7 +823,8 @@ __global__ void k_mom_faces_update(MomFaceArgs a) {
                 if (!on) continue;
                 int slot = e * 4 + s, nb = a.M.nbr[slot];
                 if (nb == NBR_FREESLIP) {
-                    double nx = a.M.fgeom[slot * 3], ny = a.M.fgeom[slot * 3 + 1];
+                    const FGeo fgn_ = fg_n(a.M, slot, s < 2 ? n : m);
+                    double nx = fgn_.nx, ny = fgn_.ny;
                     double up = mxn * nx + myn * ny;
                     mxn = mxn - up * nx; myn = myn - up * ny;
                 } else if (nb == NBR_NOSLIP) { mxn = 0.0; myn = 0.0; }
@@ -889,7 +901,6 @@ __global__ void k_shear_update(ShearArgs a) {
     double* st = s3 + 3 * nl * npts;           // [2][nl][npts]: q_df_temp
     double* tq = st + 2 * nl * npts;           // [2][nl][nq2]: wq * gravity * (tau(k) - tau(k+1))
     const size_t nbase = (size_t)e * npts, qbase = (size_t)e * nq2;
-    const double J = a.M.em[e * 5 + 4];
     __syncthreads();
     if (a.stress_only) {
         for (int t = tid; t < 3 * nl * npts; t += blockDim.x) { const int vk = t / npts; s3[t] = a.q[(size_t)vk * a.nstride + nbase + (t - vk * npts)]; }
@@ -958,7 +969,7 @@ __global__ void k_shear_update(ShearArgs a) {
         tu[0] = 0.0; tv[0] = 0.0;
         for (int k = 1; k < nl; ++k) { tu[k] = coeff * (u[k - 1] - u[k]); tv[k] = coeff * (v[k - 1] - v[k]); }
         tu[nl] = 0.0; tv[nl] = 0.0;
-        const double wq = o.wq[i] * o.wq[j] * J;
+        const double wq = o.wq[i] * o.wq[j] * met_q(a.M, e, t).J;
         for (int k = 0; k < nl; ++k) {
             tq[(0 * nl + k) * nq2 + t] = wq * (a.g * (tu[k] - tu[k + 1]));
             tq[(1 * nl + k) * nq2 + t] = wq * (a.g * (tv[k] - tv[k + 1]));
@@ -994,7 +1005,8 @@ __global__ void k_shear_update(ShearArgs a) {
                 if (!on) continue;
                 const int slot = e * 4 + s, nb = a.M.nbr[slot];
                 if (nb == NBR_FREESLIP) {
-                    const double nx = a.M.fgeom[slot * 3], ny = a.M.fgeom[slot * 3 + 1];
+                    const FGeo fgn_ = fg_n(a.M, slot, s < 2 ? n : m);
+                    const double nx = fgn_.nx, ny = fgn_.ny;
                     const double up = mxn * nx + myn * ny;
                     mxn = mxn - up * nx; myn = myn - up * ny;
                 } else if (nb == NBR_NOSLIP) { mxn = 0.0; myn = 0.0; }

@@ -134,8 +134,7 @@ __global__ void k_btp_stage_simple(StageArgs a) {
     double* vF = sm + L.vF;
     double* lfq = sm + L.lfq;
     const bool nodal_visc = a.has_visc && !a.visc_q, quad_visc = a.has_visc && a.visc_q;
-    const double ksx = a.M.em[e * 5 + 0], ksy = a.M.em[e * 5 + 1], etx = a.M.em[e * 5 + 2], ety = a.M.em[e * 5 + 3],
-                 J = a.M.em[e * 5 + 4];
+    // metric terms and normals are read per point (met_q, met_n, fg_q, fg_n: per element / per side on affine meshes)
     const size_t nbase = (size_t)e * npts, qbase = (size_t)e * nq2;
     const bool acc = !a.rhs_only;
 
@@ -164,6 +163,8 @@ __global__ void k_btp_stage_simple(StageArgs a) {
     // ---- 2. LDG auxiliary variable G = grad(ub,vb) at the nodes (mod_laplacian_quad.F90:50-56)
     if (nodal_visc && tid < npts) {
         int m = tid / ngl, n = tid - m * ngl;
+        const Met mt = met_n(a.M, e, tid);
+        const double ksx = mt.ksx, ksy = mt.ksy, etx = mt.etx, ety = mt.ety;
         double dk, de;
         nodal_grad(o, ngl, nod + 7 * npts, n, m, dk, de);
         double g0 = ksx * dk + etx * de, g1 = ksy * dk + ety * de;
@@ -185,7 +186,9 @@ __global__ void k_btp_stage_simple(StageArgs a) {
         int j = tid / nq, i = tid - j * nq;
         double dp = sf_eval(o, ngl, nq, tmp, 0, i, j), dpp = sf_eval(o, ngl, nq, tmp, 1, i, j);
         double udp = sf_eval(o, ngl, nq, tmp, 2, i, j), vdp = sf_eval(o, ngl, nq, tmp, 3, i, j);
-        double wq = o.wq[i] * o.wq[j] * J;
+        const Met mt = met_q(a.M, e, tid);
+        const double ksx = mt.ksx, ksy = mt.ksy, etx = mt.etx, ety = mt.ety;
+        double wq = o.wq[i] * o.wq[j] * mt.J;
         double ub = udp / dp, vb = vdp / dp;
         double tb_u = 0.0, tb_v = 0.0;
         if (a.botfr) {
@@ -237,7 +240,8 @@ __global__ void k_btp_stage_simple(StageArgs a) {
     if (tid < 4 * ngl) {
         int s = tid / ngl, n = tid - s * ngl;
         int slot = e * 4 + s, nb = a.M.nbr[slot], nbs = a.M.nbslot[slot];
-        double nx = a.M.fgeom[slot * 3 + 0], ny = a.M.fgeom[slot * 3 + 1];
+        const FGeo fgn_ = fg_n(a.M, slot, n);   // nodal normal (normal_vector): ghost states are built at the face nodes
+        double nx = fgn_.nx, ny = fgn_.ny;
         int I = face_node(s, n, ngl);
         double ow[3] = {nod[1 * npts + I], nod[2 * npts + I], nod[3 * npts + I]}, nbv3[3];
         neighbour_state(a, e, s, n, nb, nbs, nx, ny, ow, nbv3);
@@ -274,7 +278,8 @@ __global__ void k_btp_stage_simple(StageArgs a) {
         int slot = e * 4 + s, nb = a.M.nbr[slot], nbs = a.M.nbslot[slot];
         bool left = (nb < 0) || (e < nb);
         int oslot = left ? slot : nb * 4 + nbs;
-        double nxl = a.M.fgeom[slot * 3 + 0], nyl = a.M.fgeom[slot * 3 + 1], nlen = a.M.fgeom[slot * 3 + 2];
+        const FGeo fgq_ = fg_q(a.M, slot, iq);  // normal_vector_q, jac_faceq
+        double nxl = fgq_.nx, nyl = fgq_.ny, nlen = fgq_.len;
         double nxr = -nxl, nyr = -nyl;
         const double* tl = (left ? own : nbt) + s * 7 * ngl;
         const double* tr = (left ? nbt : own) + s * 7 * ngl;
@@ -333,7 +338,8 @@ __global__ void k_btp_stage_simple(StageArgs a) {
         int t = tid - 4 * nq, s = t / ngl, n = t - s * ngl;
         int slot = e * 4 + s, nb = a.M.nbr[slot];
         bool left = (nb < 0) || (e < nb);
-        double nx = a.M.fgeom[slot * 3 + 0], ny = a.M.fgeom[slot * 3 + 1], nlen = a.M.fgeom[slot * 3 + 2];
+        const FGeo fgn_ = fg_n(a.M, slot, n);   // normal_vector, jac_face
+        double nx = fgn_.nx, ny = fgn_.ny, nlen = fgn_.len;
         const double* gl = (left ? own : nbt) + (s * 7 + 3) * ngl + n;
         const double* gr = (left ? nbt : own) + (s * 7 + 3) * ngl + n;
         const double* sl = (left ? ownv : nbv) + s * 5 * ngl + n;
@@ -364,11 +370,12 @@ __global__ void k_btp_stage_simple(StageArgs a) {
         double l0 = 0.0, l1 = 0.0;
         for (int k = 0; k < ngl; ++k) {
             // derivative of basis (n,m) at node (k,m): D(n,k) ; at node (n,k): D(m,k)
-            double wk1 = o.wg[k] * o.wg[m] * J * o.D[n + ngl * k];
-            double wk2 = o.wg[n] * o.wg[k] * J * o.D[m + ngl * k];
             int I1 = m * ngl + k, I2 = k * ngl + n;
-            l0 -= wk1 * (ksx * tmp[0 * npts + I1] + ksy * tmp[1 * npts + I1]) + wk2 * (etx * tmp[0 * npts + I2] + ety * tmp[1 * npts + I2]);
-            l1 -= wk1 * (ksx * tmp[2 * npts + I1] + ksy * tmp[3 * npts + I1]) + wk2 * (etx * tmp[2 * npts + I2] + ety * tmp[3 * npts + I2]);
+            const Met m1 = met_n(a.M, e, I1), m2 = met_n(a.M, e, I2);   // metric terms at the collocation point of the sum
+            double wk1 = o.wg[k] * o.wg[m] * m1.J * o.D[n + ngl * k];
+            double wk2 = o.wg[n] * o.wg[k] * m2.J * o.D[m + ngl * k];
+            l0 -= wk1 * (m1.ksx * tmp[0 * npts + I1] + m1.ksy * tmp[1 * npts + I1]) + wk2 * (m2.etx * tmp[0 * npts + I2] + m2.ety * tmp[1 * npts + I2]);
+            l1 -= wk1 * (m1.ksx * tmp[2 * npts + I1] + m1.ksy * tmp[3 * npts + I1]) + wk2 * (m2.etx * tmp[2 * npts + I2] + m2.ety * tmp[3 * npts + I2]);
         }
         lap[tid] = l0; lap[npts + tid] = l1;
     }
@@ -418,7 +425,8 @@ __global__ void k_btp_stage_simple(StageArgs a) {
                 if (!on) continue;
                 int slot = e * 4 + s, nb = a.M.nbr[slot];
                 if (nb == NBR_FREESLIP) {
-                    double nx = a.M.fgeom[slot * 3 + 0], ny = a.M.fgeom[slot * 3 + 1];
+                    const FGeo fgn_ = fg_n(a.M, slot, s < 2 ? n : m);
+                    double nx = fgn_.nx, ny = fgn_.ny;
                     double unl = qn[1] * nx + qn[2] * ny;
                     qn[1] = qn[1] - unl * nx; qn[2] = qn[2] - unl * ny;
                 } else if (nb == NBR_NOSLIP) { qn[1] = 0.0; qn[2] = 0.0; }
@@ -444,6 +452,8 @@ __global__ void k_btp_stage_simple(StageArgs a) {
         a.tr_out[TR_MY * a.trstride + base] = nod[3 * npts + I];
         if (nodal_visc) {
             int m = I / ngl, nn = I - m * ngl;
+            const Met mt = met_n(a.M, e, I);
+            const double ksx = mt.ksx, ksy = mt.ksy, etx = mt.etx, ety = mt.ety;
             double dk, de;
             nodal_grad(o, ngl, nod + 7 * npts, nn, m, dk, de);
             a.tr_out[(TR_G + 0) * a.trstride + base] = ksx * dk + etx * de;
@@ -457,7 +467,7 @@ __global__ void k_btp_stage_simple(StageArgs a) {
         for (int t = tid; t < 4 * nq; t += blockDim.x) {
             const int s = t / nq, iq = t - s * nq;
             double F[4];
-            vq_face_point(o, ngl, nq, nod + 7 * npts, nod + 8 * npts, s, iq, ksx, ksy, etx, ety, a.vqP, a.vqS, qbase, F);
+            vq_face_point(a.M, e, o, ngl, nq, nod + 7 * npts, nod + 8 * npts, s, iq, a.vqP, a.vqS, qbase, F);
             for (int c = 0; c < 4; ++c) a.trq_out[c * a.trq_stride + ((size_t)e * 4 + s) * nq + iq] = F[c];
         }
     }
@@ -492,7 +502,8 @@ __global__ void k_btp_prime_traces(PrimeArgs a) {
         int nv = (a.mode == 0) ? 3 : 7;
         for (int k = 0; k < nv; ++k) a.tr_out[k * a.trstride + base] = a.in[k][nbase + I];
         if (a.mode == 0 && a.has_visc) {
-            const double ksx = a.M.em[e * 5 + 0], ksy = a.M.em[e * 5 + 1], etx = a.M.em[e * 5 + 2], ety = a.M.em[e * 5 + 3];
+            const Met mt = met_n(a.M, e, I);
+            const double ksx = mt.ksx, ksy = mt.ksy, etx = mt.etx, ety = mt.ety;
             int m = I / ngl, nn = I - m * ngl;
             double dk, de;
             nodal_grad(o, ngl, u, nn, m, dk, de);
@@ -551,7 +562,8 @@ __global__ void k_btp_finalize(FinalizeArgs a) {
     }
     __syncthreads();
     if (a.derive_graduvb && tid < npts) {
-        const double ksx = a.M.em[e * 5 + 0], ksy = a.M.em[e * 5 + 1], etx = a.M.em[e * 5 + 2], ety = a.M.em[e * 5 + 3];
+        const Met mt = met_n(a.M, e, tid);
+        const double ksx = mt.ksx, ksy = mt.ksy, etx = mt.etx, ety = mt.ety;
         int m = tid / ngl, n = tid - m * ngl;
         double dk, de;
         nodal_grad(o, ngl, nod + 6 * npts, n, m, dk, de);
@@ -592,7 +604,8 @@ __global__ void k_btp_finalize(FinalizeArgs a) {
         int slot = e * 4 + s, nb = a.M.nbr[slot], nbs = a.M.nbslot[slot];
         bool left = (nb < 0) || (e < nb);
         if (left) {
-            double nxl = a.M.fgeom[slot * 3 + 0], nyl = a.M.fgeom[slot * 3 + 1];
+            const FGeo fgq_ = fg_q(a.M, slot, iq);
+            double nxl = fgq_.nx, nyl = fgq_.ny;
             double sl[3] = {0, 0, 0}, sr[3] = {0, 0, 0};
             for (int n = 0; n < ngl; ++n) {
                 double hi = o.A[n + ngl * iq];
@@ -603,7 +616,10 @@ __global__ void k_btp_finalize(FinalizeArgs a) {
                     for (int v = 0; v < 3; ++v) nv[v] = a.tr[v * a.tr_vs + rec * a.tr_rs + n];
                 } else {
                     nv[0] = ow[0]; nv[1] = ow[1]; nv[2] = ow[2];
-                    if (nb == NBR_FREESLIP) { double un = nxl * ow[1] + nyl * ow[2]; nv[1] = ow[1] - 2.0 * un * nxl; nv[2] = ow[2] - 2.0 * un * nyl; }
+                    if (nb == NBR_FREESLIP) {   // the ghost is built at the face nodes with the nodal normal, then interpolated
+                        const FGeo fgn_ = fg_n(a.M, slot, n);
+                        double un = fgn_.nx * ow[1] + fgn_.ny * ow[2]; nv[1] = ow[1] - 2.0 * un * fgn_.nx; nv[2] = ow[2] - 2.0 * un * fgn_.ny;
+                    }
                     else if (nb == NBR_NOSLIP) { nv[1] = -ow[1]; nv[2] = -ow[2]; }
                 }
                 for (int v = 0; v < 3; ++v) { sl[v] += hi * ow[v]; sr[v] += hi * nv[v]; }

@@ -107,12 +107,18 @@ __global__ void k_diag_partial(DiagArgs a) {
     const bool cell = act && m < ngl - 1 && n < ngl - 1;
     double dx = big, dy = big, cb_x = 0.0, cb_y = 0.0, c_x = 0.0, c_y = 0.0;
     if (cell) {
-        const double ksx = a.M.em[e * 5 + 0], ksy = a.M.em[e * 5 + 1], etx = a.M.em[e * 5 + 2], ety = a.M.em[e * 5 + 3];
-        const double det = ksx * ety - ksy * etx;
-        const double dks = c_ops.xg[n + 1] - c_ops.xg[n], det_ = c_ops.xg[m + 1] - c_ops.xg[m];
-        dx = (fabs(ety) * dks + fabs(ksy) * det_) / fabs(det);
-        dy = (fabs(etx) * dks + fabs(ksx) * det_) / fabs(det);
         const int c0 = tid, c1 = tid + 1, c2 = tid + ngl, c3 = tid + ngl + 1;
+        if (a.M.coord) {   // general quadrilaterals: extent of the four corner nodes, as courant_cube_mlswe takes it from coord (courant.F90:83-97)
+            const double* cx = a.M.coord + (size_t)e * npts; const double* cy = cx + (size_t)a.M.npoin;
+            dx = fmax(fmax(cx[c0], cx[c1]), fmax(cx[c2], cx[c3])) - fmin(fmin(cx[c0], cx[c1]), fmin(cx[c2], cx[c3]));
+            dy = fmax(fmax(cy[c0], cy[c1]), fmax(cy[c2], cy[c3])) - fmin(fmin(cy[c0], cy[c1]), fmin(cy[c2], cy[c3]));
+        } else {
+            const double ksx = a.M.em[e * 5 + 0], ksy = a.M.em[e * 5 + 1], etx = a.M.em[e * 5 + 2], ety = a.M.em[e * 5 + 3];
+            const double det = ksx * ety - ksy * etx;
+            const double dks = c_ops.xg[n + 1] - c_ops.xg[n], det_ = c_ops.xg[m + 1] - c_ops.xg[m];
+            dx = (fabs(ety) * dks + fabs(ksy) * det_) / fabs(det);
+            dy = (fabs(etx) * dks + fabs(ksx) * det_) / fabs(det);
+        }
         const double* bu = sm + (nl * 2 + 0) * npts; const double* bv = sm + (nl * 2 + 1) * npts;
         cb_x = fabs(bu[c0] / 4 + bu[c1] / 4 + bu[c2] / 4 + bu[c3] / 4);
         cb_y = fabs(bv[c0] / 4 + bv[c1] / 4 + bv[c2] / 4 + bv[c3] / 4);

@@ -81,7 +81,8 @@ __global__ void k_nodal_to_quad(Mesh M, const double* in, double* out, int mode)
     int e = blockIdx.x, tid = threadIdx.x;
     if (tid >= M.nq2) return;
     int j = tid / M.nq, i = tid - j * M.nq, ngl = M.ngl;
-    double ksx = M.em[e * 5 + 0], ksy = M.em[e * 5 + 1], etx = M.em[e * 5 + 2], ety = M.em[e * 5 + 3];
+    const Met mt = met_q(M, e, tid);
+    double ksx = mt.ksx, ksy = mt.ksy, etx = mt.etx, ety = mt.ety;
     double v = 0.0, sabs = 0.0;
     for (int m = 0; m < ngl; ++m)
         for (int n = 0; n < ngl; ++n) {
@@ -850,6 +851,15 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     // method_visc == 1: LDG viscosity with the flux variable at the quadrature points (visc_q.cuh), run-time-size kernels
     S.visc_q = (d->method_visc == 1 && S.has_visc) ? 1 : 0;
     if (S.visc_q) S.variant = 1;
+    // general quadrilaterals: geometry per point, run-time-size kernels (the element-record and warp-per-element kernels carry one
+    // Jacobian per element)
+    S.general = d->point_metrics_q != nullptr;
+    if (S.general) {
+        if (!d->point_metrics || !d->face_geom_q || !d->face_geom_n || !d->coord) {
+            set_error("hnumo_init", "general quadrilaterals need point_metrics_q, point_metrics, face_geom_q, face_geom_n and coord"); destroy_solver(H); return -2;
+        }
+        S.variant = 1; S.layer_warp = 0;
+    } else if (!d->elem_metrics || !d->face_geom) { set_error("hnumo_init", "elem_metrics / face_geom missing"); destroy_solver(H); return -2; }
     for (int k = 0; k < S.nl; ++k) S.alpha[k] = d->alpha_mlswe[k];
     for (int ik = 0; ik < S.kstages; ++ik) {
         for (int c = 0; c < 3; ++c) S.ssprk_a[ik][c] = d->ssprk_a[ik + S.kstages * c];
@@ -892,7 +902,8 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
         if (ilocl < 3 || ilocl > 6 || el < 0 || el >= S.nelem) { set_error("hnumo_init", "face table: only 2-D xy faces (local face 3..6) are supported"); destroy_solver(H); return -2; }
         int sl = el * 4 + slot_of(ilocl);
         S.face_owner_slot[f] = sl; S.face_er[f] = er;
-        const double* G = d->face_geom + (size_t)3 * f;
+        const double Gq0[3] = {0.0, 0.0, 0.0};   // general quadrilaterals: first face point (fgeom is not read by their kernels)
+        const double* G = S.general ? Gq0 : d->face_geom + (size_t)3 * f;
         fgeom[(size_t)sl * 3 + 0] = G[0]; fgeom[(size_t)sl * 3 + 1] = G[1]; fgeom[(size_t)sl * 3 + 2] = G[2];
         if (er > 0) {
             int sr = (er - 1) * 4 + slot_of(ilocr);
@@ -917,7 +928,40 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     S.d_fgeom = dalloc(S, (size_t)S.nslots * 3); S.d_em = dalloc(S, (size_t)S.nelem * 5);
     cudaStreamSynchronize(S.stream);
     cudaMemcpy(S.d_fgeom, fgeom.data(), fgeom.size() * sizeof(double), cudaMemcpyHostToDevice);
-    cudaMemcpy(S.d_em, d->elem_metrics, (size_t)S.nelem * 5 * sizeof(double), cudaMemcpyHostToDevice);
+    if (!S.general) cudaMemcpy(S.d_em, d->elem_metrics, (size_t)S.nelem * 5 * sizeof(double), cudaMemcpyHostToDevice);
+    else {
+        // per-point geometry as planes; the reference's Jacobians carry the quadrature weights, the kernels multiply by them
+        const size_t NQg = (size_t)S.npoin_q, NPg = (size_t)S.npoin, FQ = (size_t)S.nslots * S.nq, FN = (size_t)S.nslots * S.ngl;
+        std::vector<double> mq(5 * NQg), mn(5 * NPg), fq(3 * FQ, 0.0), fn(3 * FN, 0.0), cxy(2 * NPg), em((size_t)S.nelem * 5);
+        for (size_t I = 0; I < NQg; ++I) {
+            const int q = (int)(I % S.nq2), j = q / S.nq, i = q - j * S.nq;
+            for (int c = 0; c < 4; ++c) mq[c * NQg + I] = d->point_metrics_q[5 * I + c];
+            mq[4 * NQg + I] = d->point_metrics_q[5 * I + 4] / (d->wnq[i] * d->wnq[j]);
+        }
+        for (size_t I = 0; I < NPg; ++I) {
+            const int t = (int)(I % S.npts), m = t / S.ngl, n = t - m * S.ngl;
+            for (int c = 0; c < 4; ++c) mn[c * NPg + I] = d->point_metrics[5 * I + c];
+            mn[4 * NPg + I] = d->point_metrics[5 * I + 4] / (d->wgl[n] * d->wgl[m]);
+            cxy[I] = d->coord[2 * I]; cxy[NPg + I] = d->coord[2 * I + 1];
+        }
+        for (int e = 0; e < S.nelem; ++e) for (int c = 0; c < 5; ++c) em[(size_t)e * 5 + c] = mq[c * NQg + (size_t)e * S.nq2];
+        for (int f = 0; f < S.nface; ++f) {
+            const int sl = S.face_owner_slot[f], sr = S.face_right_slot[f];
+            for (int iq = 0; iq < S.nq; ++iq) {
+                const double* G = d->face_geom_q + ((size_t)f * S.nq + iq) * 3;
+                const double g3[3] = {G[0], G[1], G[2] / d->wnq[iq]};
+                for (int c = 0; c < 3; ++c) { fq[c * FQ + (size_t)sl * S.nq + iq] = g3[c]; if (sr >= 0) fq[c * FQ + (size_t)sr * S.nq + iq] = g3[c]; }
+            }
+            for (int n = 0; n < S.ngl; ++n) {
+                const double* G = d->face_geom_n + ((size_t)f * S.ngl + n) * 3;
+                const double g3[3] = {G[0], G[1], G[2] / d->wgl[n]};
+                for (int c = 0; c < 3; ++c) { fn[c * FN + (size_t)sl * S.ngl + n] = g3[c]; if (sr >= 0) fn[c * FN + (size_t)sr * S.ngl + n] = g3[c]; }
+            }
+        }
+        auto upg = [&](const std::vector<double>& h) { double* p = dalloc(S, h.size()); cudaStreamSynchronize(S.stream); cudaMemcpy(p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice); return p; };
+        S.d_mq = upg(mq); S.d_mn = upg(mn); S.d_fgq = upg(fq); S.d_fgn = upg(fn); S.d_coord = upg(cxy);
+        cudaMemcpy(S.d_em, em.data(), em.size() * sizeof(double), cudaMemcpyHostToDevice);
+    }
     if (S.nhalo > 0) {
         HN_INIT_CUDA(cudaMalloc(&S.d_halo_slot, S.nhalo * sizeof(int)));
         cudaMemcpy(S.d_halo_slot, S.halo_slot.data(), S.nhalo * sizeof(int), cudaMemcpyHostToDevice);
@@ -932,6 +976,7 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     Mesh& M = S.mesh;
     M.nelem = S.nelem; M.ngl = S.ngl; M.nq = S.nq; M.npts = S.npts; M.nq2 = S.nq2; M.nl = S.nl; M.npoin = S.npoin; M.npoin_q = S.npoin_q;
     M.nslots = S.nslots; M.nbr = S.d_nbr; M.nbslot = S.d_nbslot; M.fgeom = S.d_fgeom; M.em = S.d_em;
+    M.mq = S.d_mq; M.mn = S.d_mn; M.fgq = S.d_fgq; M.fgn = S.d_fgn; M.coord = S.d_coord;
     // nodal statics
     const size_t NP = S.npoin, NQ = S.npoin_q, NS = (size_t)S.nslots * S.nq;
     auto up = [&](const double* h, size_t n) { double* p = dalloc(S, n); cudaStreamSynchronize(S.stream); cudaMemcpy(p, h, n * sizeof(double), cudaMemcpyHostToDevice); return p; };
@@ -1388,6 +1433,9 @@ int hnumo_timing(hnumo_handle_t h, double* out8, int32_t reset) {
 
 int hnumo_set_option(hnumo_handle_t h, const char* key, double value) {
     HN_ENTER(h);
+    if (S.general && ((!strcmp(key, "stage_kernel_variant") && (int)value != 1) || (!strcmp(key, "layer_warp") && (int)value != 0))) {
+        set_error("hnumo_set_option", "general quadrilaterals run the run-time-size kernels only"); return -3;
+    }
     if (!strcmp(key, "stage_kernel_variant")) { S.variant = (int)value; return 0; }
     if (!strcmp(key, "use_graph")) { S.use_graph = (int)value; return 0; }
     if (!strcmp(key, "layer_warp")) { S.layer_warp = (int)value; return 0; }

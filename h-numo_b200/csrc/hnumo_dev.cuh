@@ -14,6 +14,47 @@ __device__ __forceinline__ int face_quad(int s, int iq, int nq) {
     return s == 0 ? iq : s == 1 ? (nq - 1) * nq + iq : s == 2 ? iq * nq : iq * nq + nq - 1;
 }
 
+// ---- geometry at a point.  Affine elements (bricks, parallelograms): five numbers per element and three per side.  General
+// quadrilaterals (isoparametric, src/metrics.F90, src/metrics_quad.F90, src/create_normals(_quad).F90): the same numbers per
+// quadrature point / node / face point.  Every use of the metric terms in the run-time-size kernels is pointwise, so the two cases
+// differ only in where the numbers come from.
+struct Met { double ksx, ksy, etx, ety, J; };
+struct FGeo { double nx, ny, len; };
+__device__ __forceinline__ Met met_elem(const Mesh& M, int e) {
+    const double* p = M.em + (size_t)e * 5;
+    Met m; m.ksx = p[0]; m.ksy = p[1]; m.etx = p[2]; m.ety = p[3]; m.J = p[4];
+    return m;
+}
+// quadrature point q = j*nq + i of element e
+__device__ __forceinline__ Met met_q(const Mesh& M, int e, int q) {
+    if (!M.mq) return met_elem(M, e);
+    const size_t I = (size_t)e * M.nq2 + q, S = (size_t)M.npoin_q;
+    Met m; m.ksx = M.mq[I]; m.ksy = M.mq[S + I]; m.etx = M.mq[2 * S + I]; m.ety = M.mq[3 * S + I]; m.J = M.mq[4 * S + I];
+    return m;
+}
+// node I = m*ngl + n of element e
+__device__ __forceinline__ Met met_n(const Mesh& M, int e, int I) {
+    if (!M.mn) return met_elem(M, e);
+    const size_t P = (size_t)e * M.npts + I, S = (size_t)M.npoin;
+    Met m; m.ksx = M.mn[P]; m.ksy = M.mn[S + P]; m.etx = M.mn[2 * S + P]; m.ety = M.mn[3 * S + P]; m.J = M.mn[4 * S + P];
+    return m;
+}
+// canonical (left-element) unit normal and edge Jacobian at face quadrature point iq / face node n of element side `slot`
+__device__ __forceinline__ FGeo fg_q(const Mesh& M, int slot, int iq) {
+    FGeo g;
+    if (!M.fgq) { g.nx = M.fgeom[slot * 3 + 0]; g.ny = M.fgeom[slot * 3 + 1]; g.len = M.fgeom[slot * 3 + 2]; return g; }
+    const size_t I = (size_t)slot * M.nq + iq, S = (size_t)M.nslots * M.nq;
+    g.nx = M.fgq[I]; g.ny = M.fgq[S + I]; g.len = M.fgq[2 * S + I];
+    return g;
+}
+__device__ __forceinline__ FGeo fg_n(const Mesh& M, int slot, int n) {
+    FGeo g;
+    if (!M.fgn) { g.nx = M.fgeom[slot * 3 + 0]; g.ny = M.fgeom[slot * 3 + 1]; g.len = M.fgeom[slot * 3 + 2]; return g; }
+    const size_t I = (size_t)slot * M.ngl + n, S = (size_t)M.nslots * M.ngl;
+    g.nx = M.fgn[I]; g.ny = M.fgn[S + I]; g.len = M.fgn[2 * S + I];
+    return g;
+}
+
 // Operator tables staged in shared memory by every "simple" kernel.
 struct SOps {
     const double *A, *B, *D, *wq, *wg;

@@ -35,6 +35,13 @@ struct Mesh {
     const int* nbslot;   // [nslots] neighbour's slot (interior), halo face index (NBR_HALO)
     const double* fgeom; // [nslots*3] canonical (left-element) unit normal nx,ny and edge jacobian
     const double* em;    // [nelem*5] ksi_x ksi_y eta_x eta_y |J|
+    // general (non-affine) quadrilaterals: geometry per point, nullptr on affine meshes (the kernels read them through met_q / met_n /
+    // fg_q / fg_n of hnumo_dev.cuh, which fall back to the per-element numbers above)
+    const double* mq;    // [5][npoin_q] ksiq_x ksiq_y etaq_x etaq_y jacq/(w_i w_j)      (mod_metrics, src/metrics_quad.F90)
+    const double* mn;    // [5][npoin]   ksi_x ksi_y eta_x eta_y jac/(w_i w_j)           (src/metrics.F90)
+    const double* fgq;   // [3][nslots*nq]  normal_vector_q(1:2), jac_faceq/w_iq at the face quadrature points (canonical left normal)
+    const double* fgn;   // [3][nslots*ngl] normal_vector(1:2), jac_face/w_n at the face nodes
+    const double* coord; // [2][npoin] node coordinates (mod_grid coord), read by the Courant diagnostics only
 };
 
 // 1-D operator tables (constant memory copies are in hnumo_ops.cu)
@@ -77,6 +84,8 @@ struct Solver {
     // connectivity
     int *d_nbr = nullptr, *d_nbslot = nullptr;
     double *d_fgeom = nullptr, *d_em = nullptr;
+    bool general = false;   // general quadrilaterals: per-point geometry (Mesh::mq, mn, fgq, fgn, coord)
+    double *d_mq = nullptr, *d_mn = nullptr, *d_fgq = nullptr, *d_fgn = nullptr, *d_coord = nullptr;
     // static nodal planes
     double *pbprime_df, *oop_df, *massinv, *coriolis_df, *tauw_df /*2*/, *zbot_df, *a_bcl, *b_bcl, *fdt2;
     // static quad planes (derived exactly like the reference set-up derives them)

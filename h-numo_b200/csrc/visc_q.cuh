@@ -65,7 +65,8 @@ __global__ void k_viscq_coeffs(VqCoeffArgs a) {
     double* tA = nod + 3 * npts;                // [3][per]
     double* tB = tA + 3 * per;                  // [3][per]
     const size_t nbase = (size_t)e * npts, qbase = (size_t)e * nq2;
-    const double ksx = a.M.em[e * 5 + 0], ksy = a.M.em[e * 5 + 1], etx = a.M.em[e * 5 + 2], ety = a.M.em[e * 5 + 3];
+    const Met mt = met_q(a.M, e, tid < nq2 ? tid : 0);   // metric terms at this thread's quadrature point
+    const double ksx = mt.ksx, ksy = mt.ksy, etx = mt.etx, ety = mt.ety;
     double P = 0.0, S0 = 0.0, S1 = 0.0, S2 = 0.0, S3 = 0.0;
     for (int k = 0; k < nl; ++k) {
         __syncthreads();
@@ -94,10 +95,11 @@ __global__ void k_viscq_coeffs(VqCoeffArgs a) {
 }
 
 // F_c = S_c + P grad_c(u,v) at boundary quadrature point iq of side s; u, v: nodal velocities of the element (shared memory)
-__device__ __forceinline__ void vq_face_point(const SOps& o, int ngl, int nq, const double* u, const double* v, int s, int iq,
-                                              double ksx, double ksy, double etx, double ety, const double* P, const double* const* S,
-                                              size_t qbase, double out[4]) {
+__device__ __forceinline__ void vq_face_point(const Mesh& M, int e, const SOps& o, int ngl, int nq, const double* u, const double* v, int s, int iq,
+                                              const double* P, const double* const* S, size_t qbase, double out[4]) {
     const int q = face_quad(s, iq, nq), j = q / nq, i = q - j * nq;
+    const Met mt = met_q(M, e, q);
+    const double ksx = mt.ksx, ksy = mt.ksy, etx = mt.etx, ety = mt.ety;
     double uk, ue, vk, ve;
     vq_grad_point(o, ngl, u, i, j, uk, ue);
     vq_grad_point(o, ngl, v, i, j, vk, ve);
@@ -124,7 +126,6 @@ __global__ void k_viscq_prime(VqPrimeArgs a) {
     double* u = sm + sops_doubles(ngl, nq);
     double* v = u + npts;
     const size_t nbase = (size_t)e * npts, qbase = (size_t)e * nq2;
-    const double ksx = a.M.em[e * 5 + 0], ksy = a.M.em[e * 5 + 1], etx = a.M.em[e * 5 + 2], ety = a.M.em[e * 5 + 3];
     for (int t = tid; t < npts; t += blockDim.x) {
         const double pb = a.qb[0][nbase + t] + a.pbprime_df[nbase + t];
         u[t] = a.qb[1][nbase + t] / pb; v[t] = a.qb[2][nbase + t] / pb;
@@ -133,7 +134,7 @@ __global__ void k_viscq_prime(VqPrimeArgs a) {
     for (int t = tid; t < 4 * nq; t += blockDim.x) {
         const int s = t / nq, iq = t - s * nq;
         double F[4];
-        vq_face_point(o, ngl, nq, u, v, s, iq, ksx, ksy, etx, ety, a.P, a.S, qbase, F);
+        vq_face_point(a.M, e, o, ngl, nq, u, v, s, iq, a.P, a.S, qbase, F);
         for (int c = 0; c < 4; ++c) a.trq[c * a.trq_stride + ((size_t)e * 4 + s) * nq + iq] = F[c];
     }
 }
@@ -143,7 +144,8 @@ __global__ void k_viscq_prime(VqPrimeArgs a) {
 // element e (left: +, right: -).
 __device__ __forceinline__ void vq_face_flux(const Mesh& M, const double* base, size_t cstride, int e, int s, int iq, double wq_iq, double out[2]) {
     const int nq = M.nq, slot = e * 4 + s, nb = M.nbr[slot], nbs = M.nbslot[slot];
-    const double nx = M.fgeom[slot * 3 + 0], ny = M.fgeom[slot * 3 + 1], nlen = M.fgeom[slot * 3 + 2];
+    const FGeo fgq_ = fg_q(M, slot, iq);
+    const double nx = fgq_.nx, ny = fgq_.ny, nlen = fgq_.len;
     double own[4], nbv[4];
     for (int c = 0; c < 4; ++c) own[c] = base[c * cstride + (size_t)slot * nq + iq];
     if (nb >= 0) { for (int c = 0; c < 4; ++c) nbv[c] = base[c * cstride + ((size_t)nb * 4 + nbs) * nq + iq]; }
@@ -189,7 +191,6 @@ __global__ void k_bcl_lapq_traces(VqLayerArgs a) {
     SOps o = load_sops(sm, ngl, nq);
     double* nod = sm + sops_doubles(ngl, nq);   // [3][npts]: dpv, U, V
     const size_t nbase = (size_t)e * npts;
-    const double ksx = a.M.em[e * 5 + 0], ksy = a.M.em[e * 5 + 1], etx = a.M.em[e * 5 + 2], ety = a.M.em[e * 5 + 3];
     for (int k = 0; k < nl; ++k) {
         __syncthreads();
         for (int t = tid; t < npts; t += blockDim.x) {
@@ -200,6 +201,8 @@ __global__ void k_bcl_lapq_traces(VqLayerArgs a) {
         __syncthreads();
         for (int t = tid; t < 4 * nq; t += blockDim.x) {
             const int s = t / nq, iq = t - s * nq, q = face_quad(s, iq, nq), j = q / nq, i = q - j * nq;
+            const Met mt = met_q(a.M, e, q);
+            const double ksx = mt.ksx, ksy = mt.ksy, etx = mt.etx, ety = mt.ety;
             const double d = vq_interp_point(o, ngl, nod, i, j);
             double uk, ue, vk, ve;
             vq_grad_point(o, ngl, nod + npts, i, j, uk, ue);
@@ -225,7 +228,8 @@ __global__ void k_bcl_lapq_apply(VqLayerArgs a) {
     double* lap = vF + 4 * nq2;                 // [2][npts]
     double* lfq = lap + 2 * npts;               // [4][2][nq]
     const size_t nbase = (size_t)e * npts;
-    const double ksx = a.M.em[e * 5 + 0], ksy = a.M.em[e * 5 + 1], etx = a.M.em[e * 5 + 2], ety = a.M.em[e * 5 + 3], J = a.M.em[e * 5 + 4];
+    const Met mt = met_q(a.M, e, tid < nq2 ? tid : 0);   // metric terms at this thread's quadrature point
+    const double ksx = mt.ksx, ksy = mt.ksy, etx = mt.etx, ety = mt.ety, J = mt.J;
     for (int k = 0; k < nl; ++k) {
         __syncthreads();
         for (int t = tid; t < npts; t += blockDim.x) {

@@ -222,6 +222,16 @@ def build_deck(params, rank=0, nranks=1):
     ty = (w0 * eyb + w1 * eyb + w2 * (eyb + 1) + w3 * (eyb + 1)) / 4.0
     X = (tx / nelx) * Lx + p["xdims"][0]
     Y = (ty / nely) * Ly + p["ydims"][0]
+    warp = float(p.get("mesh_warp", 0.0))
+    if warp != 0.0:
+        # general (curved, non-affine) quadrilaterals: the nodes of the brick are moved by a smooth displacement that vanishes
+        # in the wall-normal direction on the domain boundary (test aid; the reference reads such meshes from gmsh files)
+        kx, ky = float(max(1, nelx // 2)), float(max(1, nely // 2))
+        Xn, Yn = (X - p["xdims"][0]) / Lx, (Y - p["ydims"][0]) / Ly
+        ddx = warp * (Lx / nelx) * np.sin(PI_TRIG * kx * Xn) * np.cos(PI_TRIG * ky * Yn)
+        ddy = warp * (Ly / nely) * np.cos(PI_TRIG * kx * Xn) * np.sin(PI_TRIG * ky * Yn)
+        X = X + ddx
+        Y = Y + ddy
     x = X.reshape(-1)
     y = Y.reshape(-1)
     # face table (p4est.c:1590-1704): p4est faces f=0..3 (-x,+x,-y,+y) -> numa local faces 5,6,3,4
@@ -271,6 +281,11 @@ def build_deck(params, rank=0, nranks=1):
     fg = ntab[face[:, 4]]
     wg = B["wgl"]
     massinv = np.tile(1.0 / (wg[None, :] * wg[:, None] * (dx * dy / 4.0)), (nelem, 1, 1)).reshape(-1)
+    general = {}
+    if warp != 0.0:
+        general = _point_geometry(B, X, Y, face)
+        massinv = 1.0 / general["point_metrics"][:, 4]       # DG: mass = jac (create_mass.F90:24-31)
+        em = None; fg = None
     # ---- initial conditions (initial_conditions.F90)
     g = GRAVITY
     pi = PI_TRIG
@@ -382,7 +397,49 @@ def build_deck(params, rank=0, nranks=1):
         q_df=q, qb_df=qb, qprime_df=qprime, coord=np.stack([x, y], axis=1),
         elem_global=gl.copy(), npoin=npoin, npts=npts,
     )
+    deck.update(general)
     return deck
+
+
+def _point_geometry(B, X, Y, face):
+    """Per-point geometry of general quadrilaterals from the node coordinates X, Y [nelem, m, n], as the reference derives it:
+    nodal metrics (metrics.F90:40-127 with mod_gradient.F90:110-166), quadrature-point metrics (metrics_quad.F90:20-127 with
+    compute_local_gradient_quad_v3, mod_gradient.F90:175-260), face normals and Jacobians at the face nodes and face quadrature
+    points of the left element (create_normals.F90:17-215, create_normals_quad.F90:136-211).  Returns the arrays of the
+    hnumo_desc_t members point_metrics_q (npoin_q,5), point_metrics (npoin,5), face_geom_q (nface,nq,3), face_geom_n (nface,ngl,3)."""
+    ngl, nq = B["ngl"], B["nq"]
+    dpsi, psiq, dpsiq, wgl, wnq = B["dpsi"], B["psiq"], B["dpsiq"], B["wgl"], B["wnq"]
+
+    def metrics(xk, yk, xe, ye, w):
+        xj = xk * ye - yk * xe
+        return np.stack([ye / xj, -xe / xj, -yk / xj, xk / xj, (w[None, None, :] * w[None, :, None]) * np.abs(xj)], axis=-1)
+
+    # nodal: x_ksi(i,j) = sum_n dpsi(n,i) x(n,j), x_eta(i,j) = sum_n x(i,n) dpsi(n,j); arrays [e, j, i]
+    nk = [np.einsum("ni,ejn->eji", dpsi, A) for A in (X, Y)]
+    ne = [np.einsum("eni,nj->eji", A, dpsi) for A in (X, Y)]
+    # quadrature points: x_ksi(iq,jq) = sum_mn dpsiq(n,iq) psiq(m,jq) x(n,m)
+    qk = [np.einsum("ni,mj,emn->eji", dpsiq, psiq, A) for A in (X, Y)]
+    qe = [np.einsum("ni,mj,emn->eji", psiq, dpsiq, A) for A in (X, Y)]
+    nelem = X.shape[0]
+    out = dict(point_metrics=metrics(nk[0], nk[1], ne[0], ne[1], wgl).reshape(nelem * ngl * ngl, 5),
+               point_metrics_q=metrics(qk[0], qk[1], qe[0], qe[1], wnq).reshape(nelem * nq * nq, 5))
+    iel, iloc = face[:, 6] - 1, face[:, 4]
+
+    def face_geom(n1, dk, de, w):
+        l = np.arange(n1)[None, :]
+        il = iloc[:, None]
+        i = np.where(il == 3, l, np.where(il == 4, l, np.where(il == 5, 0, n1 - 1)))
+        j = np.where(il == 3, 0, np.where(il == 4, n1 - 1, l))
+        e = iel[:, None]
+        xk, yk, xe, ye = dk[0][e, j, i], dk[1][e, j, i], de[0][e, j, i], de[1][e, j, i]
+        nx = np.where(il == 3, yk, np.where(il == 4, -yk, np.where(il == 5, -ye, ye)))
+        ny = np.where(il == 3, -xk, np.where(il == 4, xk, np.where(il == 5, xe, -xe)))
+        nlen = np.sqrt(nx * nx + ny * ny)
+        return np.stack([nx / nlen, ny / nlen, w[None, :] * nlen], axis=-1)
+
+    out["face_geom_n"] = face_geom(ngl, nk, ne, wgl)
+    out["face_geom_q"] = face_geom(nq, qk, qe, wnq)
+    return out
 
 
 def diagnostics(deck, q_df):

@@ -9,7 +9,7 @@ module hnumo_b200_iface
     use iso_c_binding
     implicit none
 
-    integer(c_int32_t), parameter :: HNUMO_ABI_VERSION = 2
+    integer(c_int32_t), parameter :: HNUMO_ABI_VERSION = 3
 
     ! mirrors hnumo_desc_t field by field
     type, bind(C) :: hnumo_desc_t
@@ -30,6 +30,8 @@ module hnumo_b200_iface
         integer(c_int32_t) :: device
         integer(c_int32_t) :: stage_kernel_variant
         real(c_double)     :: max_shear_dz
+        type(c_ptr) :: point_metrics_q, point_metrics, face_geom_q, face_geom_n
+        type(c_ptr) :: coord
     end type hnumo_desc_t
 
     interface

@@ -17,37 +17,40 @@ module hnumo_b200_state
     type(c_ptr), save :: handle = c_null_ptr
     logical, save :: resident_valid = .false.
     real(c_double), allocatable, target, save :: elem_metrics(:,:), face_geom(:,:), ssprk_a_c(:,:)
+    ! general quadrilaterals (gmsh meshes, curved elements): the geometry per point (include/hnumo_b200.h, ABI 3)
+    logical, save :: general_quads = .false.
+    real(c_double), allocatable, target, save :: point_metrics_q(:,:), point_metrics(:,:), face_geom_q(:,:,:), face_geom_n(:,:,:), coord_c(:,:)
     integer(c_int32_t), allocatable, target, save :: face_c(:,:), nbh_proc_c(:), num_send_recv_c(:), nbh_send_recv_c(:)
 contains
 
     subroutine hnumo_b200_setup()
         ! everything ti_rk_bcl reads through `use` (src/ti_rk_bcl.F90:19-28 and the modules below it)
         use mpi
-        use mod_grid, only: nelem, npoin, nface, face, face_type
+        use mod_grid, only: nelem, npoin, npoin_q, nface, face, face_type, coord
         use mod_basis, only: ngl, nq, psiq, dpsiq, wnq, wgl, dpsi
         use mod_input, only: nlayers, kstages, dt, dt_btp, botfr, cd_mlswe, method_visc, visc_mlswe, ad_mlswe, max_shear_dz
         use mod_constants, only: gravity
-        use mod_metrics, only: ksiq_x, ksiq_y, etaq_x, etaq_y, jacq, massinv
-        use mod_face, only: normal_vector_q, jac_faceq
+        use mod_metrics, only: ksiq_x, ksiq_y, etaq_x, etaq_y, jacq, ksi_x, ksi_y, eta_x, eta_y, jac, massinv
+        use mod_face, only: normal_vector_q, jac_faceq, normal_vector, jac_face
         use mod_initial, only: pbprime_df, coriolis_df, tau_wind_df, zbot_df, alpha_mlswe, ssprk_a, ssprk_beta, &
                                N_btp
         use mod_parallel, only: num_nbh, nbh_proc, num_send_recv, nbh_send_recv
         use mod_mpi_utilities, only: irank, numproc
-        integer :: e, f, i, j, iq, ierr, ntot, ndev, local_rank, node_comm
+        integer :: e, f, i, j, iq, n, ip, ierr, ntot, ndev, local_rank, node_comm
         integer(c_int) :: rc
         real(c_double) :: tol, ref
         character(kind=c_char) :: id(128)
 
-        ! The library takes ONE metric set per element and ONE normal / edge Jacobian per face (affine bricks, conforming
-        ! faces; include/hnumo_b200.h).  Refuse anything else instead of integrating it wrongly: curved or gmsh quads have
-        ! per-point metrics, AMR meshes have non-conforming faces (face_type 21/12, src/mod_grid.F90:79).
+        ! Affine meshes (bricks, parallelograms: one metric set per element, one normal / edge Jacobian per face) run the optimised
+        ! kernels on elem_metrics / face_geom.  Anything else with conforming faces -- curved or gmsh quads -- is handed over
+        ! point by point (point_metrics_q ... coord) and runs the library's run-time-size kernels.  AMR meshes have
+        ! non-conforming faces (face_type 21/12, src/mod_grid.F90:79): refused.
+        general_quads = .false.
         do f = 1, nface
             if (face_type(f) /= 1 .and. face_type(f) /= 2) stop "hnumo_b200: non-conforming or unknown face_type (only 1, 2)"
             do iq = 2, nq
-                if (maxval(abs(normal_vector_q(1:2,iq,1,f) - normal_vector_q(1:2,1,1,f))) > 1.0e-12) &
-                    stop "hnumo_b200: face normal varies along a face (curved mesh): not supported"
-                if (abs(jac_faceq(iq,1,f)/wnq(iq) - jac_faceq(1,1,f)/wnq(1)) > 1.0e-10*abs(jac_faceq(1,1,f)/wnq(1))) &
-                    stop "hnumo_b200: edge Jacobian varies along a face (curved mesh): not supported"
+                if (maxval(abs(normal_vector_q(1:2,iq,1,f) - normal_vector_q(1:2,1,1,f))) > 1.0e-12) general_quads = .true.
+                if (abs(jac_faceq(iq,1,f)/wnq(iq) - jac_faceq(1,1,f)/wnq(1)) > 1.0e-10*abs(jac_faceq(1,1,f)/wnq(1))) general_quads = .true.
             end do
         end do
         do e = 1, nelem
@@ -57,10 +60,36 @@ contains
                 do i = 1, nq
                     if (abs(ksiq_x(i,j,1,e) - ksiq_x(1,1,1,e)) > tol .or. abs(ksiq_y(i,j,1,e) - ksiq_y(1,1,1,e)) > tol .or. &
                         abs(etaq_x(i,j,1,e) - etaq_x(1,1,1,e)) > tol .or. abs(etaq_y(i,j,1,e) - etaq_y(1,1,1,e)) > tol) &
-                        stop "hnumo_b200: metric terms vary inside an element (non-affine element): not supported"
+                        general_quads = .true.
                 end do
             end do
         end do
+        if (general_quads) then
+            allocate(point_metrics_q(5,npoin_q), point_metrics(5,npoin), face_geom_q(3,nq,nface), face_geom_n(3,ngl,nface), coord_c(2,npoin))
+            do e = 1, nelem
+                do j = 1, nq
+                    do i = 1, nq
+                        ip = (e-1)*nq*nq + (j-1)*nq + i          ! intma_dg_quad, src/mod_grid.F90:242-249
+                        point_metrics_q(:,ip) = (/ ksiq_x(i,j,1,e), ksiq_y(i,j,1,e), etaq_x(i,j,1,e), etaq_y(i,j,1,e), jacq(i,j,1,e) /)
+                    end do
+                end do
+                do j = 1, ngl
+                    do i = 1, ngl
+                        ip = (e-1)*ngl*ngl + (j-1)*ngl + i       ! intma_dg, src/mod_grid.F90:230-237
+                        point_metrics(:,ip) = (/ ksi_x(i,j,1,e), ksi_y(i,j,1,e), eta_x(i,j,1,e), eta_y(i,j,1,e), jac(i,j,1,e) /)
+                    end do
+                end do
+            end do
+            do f = 1, nface
+                do iq = 1, nq
+                    face_geom_q(1:2,iq,f) = normal_vector_q(1:2,iq,1,f); face_geom_q(3,iq,f) = jac_faceq(iq,1,f)
+                end do
+                do n = 1, ngl
+                    face_geom_n(1:2,n,f) = normal_vector(1:2,n,1,f); face_geom_n(3,n,f) = jac_face(n,1,f)
+                end do
+            end do
+            coord_c(1:2,1:npoin) = coord(1:2,1:npoin)
+        end if
 
         allocate(elem_metrics(5,nelem), face_geom(3,nface), face_c(8,nface), ssprk_a_c(kstages,3))
         do e = 1, nelem      ! bricks are affine: one metric set per element (include/hnumo_b200.h, elem_metrics)
@@ -119,6 +148,12 @@ contains
             d%gravity = gravity; d%cd_mlswe = cd_mlswe; d%visc_mlswe = visc_mlswe; d%ad_mlswe = ad_mlswe
             d%psiq = c_loc(psiq_a); d%dpsiq = c_loc(dpsiq_a); d%wnq = c_loc(wnq_a); d%wgl = c_loc(wgl_a); d%dpsi = c_loc(dpsi_a)
             d%face = c_loc(face_c); d%elem_metrics = c_loc(elem_metrics); d%face_geom = c_loc(face_geom)
+            d%point_metrics_q = c_null_ptr; d%point_metrics = c_null_ptr; d%face_geom_q = c_null_ptr; d%face_geom_n = c_null_ptr
+            d%coord = c_null_ptr
+            if (general_quads) then
+                d%point_metrics_q = c_loc(point_metrics_q); d%point_metrics = c_loc(point_metrics)
+                d%face_geom_q = c_loc(face_geom_q); d%face_geom_n = c_loc(face_geom_n); d%coord = c_loc(coord_c)
+            end if
             d%pbprime_df = c_loc(pbprime_a); d%massinv = c_loc(massinv_a); d%coriolis_df = c_loc(coriolis_a)
             d%tau_wind_df = c_loc(tauw_a); d%zbot_df = c_loc(zbot_a); d%alpha_mlswe = c_loc(alpha_a)
             d%ssprk_a = c_loc(ssprk_a_c); d%ssprk_beta = c_loc(beta_a)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define HNUMO_ABI_VERSION 2
+#define HNUMO_ABI_VERSION 3
 #define HNUMO_MAX_LAYERS 20 /* lakeAtrest supports 2..20 layers, src/initial_conditions.F90:130-169 */
 #define HNUMO_MAX_NGL 9     /* nop <= 8 (BASELINE config 5) */
 
@@ -65,7 +65,7 @@ typedef struct hnumo_desc {
     /* mesh: face(8,nface) of mod_grid (src/p4est.c:1590-1700): rows 5,6 local face of left/right element,
      * row 7 left element, row 8 right element (>0), 0 = processor boundary, -4 free slip, -2 no slip */
     const int32_t* face;
-    /* per-element affine geometry (bricks): elem_metrics(5,nelem) = ksiq_x, ksiq_y, etaq_x, etaq_y of
+    /* per-element affine geometry (bricks, parallelograms; general quadrilaterals: see point_metrics_q at the end): elem_metrics(5,nelem) = ksiq_x, ksiq_y, etaq_x, etaq_y of
      * mod_metrics at quadrature point (1,1,1,e) and |J| = jacq(1,1,1,e)/(wnq(1)*wnq(1)) */
     const double* elem_metrics;
     /* per-face geometry: face_geom(3,nface) = normal_vector_q(1:2,1,1,iface) (outward from the left element)
@@ -97,6 +97,22 @@ typedef struct hnumo_desc {
     /* mod_input max_shear_dz: upper bound of the shear-layer thickness of the vertical shear stress (only read when ad_mlswe > 0;
      * added with ABI version 2) */
     double max_shear_dz;
+    /* General (non-affine) quadrilaterals -- gmsh meshes, curved or skewed elements (src/metrics.F90, src/metrics_quad.F90,
+     * src/create_normals.F90, src/create_normals_quad.F90): the geometry per point, in the reference's own numbers.  All NULL on
+     * affine meshes (bricks, parallelograms), where elem_metrics / face_geom above describe an element by five numbers and a face by
+     * three; when point_metrics_q is given the other four must be given too, elem_metrics and face_geom are not read, and the step
+     * runs the run-time-size kernels (the optimised kernels assume one Jacobian per element).  Added with ABI version 3.
+     *   point_metrics_q(5,npoin_q) = ksiq_x, ksiq_y, etaq_x, etaq_y, jacq   of mod_metrics at every quadrature point (jacq with its
+     *                                quadrature weights, as the reference stores it)
+     *   point_metrics(5,npoin)     = ksi_x, ksi_y, eta_x, eta_y, jac        at every node (jac with its LGL weights)
+     *   face_geom_q(3,nq,nface)    = normal_vector_q(1:2,iq,1,iface), jac_faceq(iq,1,iface)   (outward from the left element)
+     *   face_geom_n(3,ngl,nface)   = normal_vector(1:2,n,1,iface), jac_face(n,1,iface)
+     *   coord(2,npoin)             = node coordinates of mod_grid (read by the Courant numbers of hnumo_diagnostics only) */
+    const double* point_metrics_q;
+    const double* point_metrics;
+    const double* face_geom_q;
+    const double* face_geom_n;
+    const double* coord;
 } hnumo_desc_t;
 
 /* ---- life cycle ----------------------------------------------------------------------------- */

@@ -89,6 +89,12 @@ struct Config {
     int affine_metrics;
     // vertical shear stress between the layers (mod_input ad_mlswe, max_shear_dz; mod_create_rhs_mlswe.F90:146-279); 0 = off
     double ad_mlswe, max_shear_dz;
+    // Test aid: the reference's metric, normal and operator-table code is written for general (isoparametric) quadrilaterals
+    // (gmsh meshes; metrics.F90, metrics_quad.F90, create_normals(_quad).F90), but its shipped cases are bricks.  mesh_warp != 0
+    // moves the nodes of the brick by  dx = w hx sin(pi kx X) cos(pi ky Y),  dy = w hy cos(pi kx X) sin(pi ky Y)
+    // (X, Y in [0,1], hx, hy element sizes, kx = max(1, nelx/2), ky = max(1, nely/2)): curved, non-affine elements, conforming
+    // (the displacement is a function of position), the domain boundary stays where it is.  affine_metrics must be 0.
+    double mesh_warp;
 };
 
 struct Oracle {

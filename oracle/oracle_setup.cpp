@@ -142,6 +142,16 @@ void Oracle::build_grid() {
                     coord(1, I) = y * (cfg.ydims[1] - cfg.ydims[0]) + cfg.ydims[0];
                 }
         }
+    if (cfg.mesh_warp != 0.0) {   // test aid, see Config::mesh_warp
+        const double pi = PI_TRIG, Lx = cfg.xdims[1] - cfg.xdims[0], Ly = cfg.ydims[1] - cfg.ydims[0];
+        const double kx = std::max(1, cfg.nelx / 2), ky = std::max(1, cfg.nely / 2);
+        for (int I = 0; I < npoin; ++I) {
+            const double X = (coord(0, I) - cfg.xdims[0]) / Lx, Y = (coord(1, I) - cfg.ydims[0]) / Ly;
+            const double ddx = cfg.mesh_warp * (Lx / cfg.nelx) * std::sin(pi * kx * X) * std::cos(pi * ky * Y);
+            const double ddy = cfg.mesh_warp * (Ly / cfg.nely) * std::cos(pi * kx * X) * std::sin(pi * ky * Y);
+            coord(0, I) += ddx; coord(1, I) += ddy;
+        }
+    }
     // faces: p4est.c:1560-1735.  p4est face f=0..3 (-x,+x,-y,+y) -> numa local face 5,6,3,4;
     // left element = lower element number; boundary: face(8) = -bc flag.
     static const int transform[4] = {4, 5, 2, 3};
@@ -644,7 +654,7 @@ Oracle::Oracle(const Config& c) : cfg(c) {
     build_grid();
     build_metrics();
     build_faces();
-    if (cfg.affine_metrics) make_metrics_affine();
+    if (cfg.affine_metrics && cfg.mesh_warp == 0.0) make_metrics_affine();
     build_tensor_tables();
     build_initial();
     allocate_variables();

@@ -29,6 +29,7 @@ class Config(C.Structure):
         ("synth_z", C.c_double * 33), ("synth_alpha", C.c_double * 32), ("synth_perturb", C.c_double),
         ("affine_metrics", C.c_int),
         ("ad_mlswe", C.c_double), ("max_shear_dz", C.c_double),
+        ("mesh_warp", C.c_double),
     ]
 
 
@@ -101,6 +102,7 @@ def make_config(deck):
     c.synth_perturb = deck.get("synth_perturb", 0.0)
     c.affine_metrics = 1 if deck.get("affine_metrics", False) else 0
     c.ad_mlswe, c.max_shear_dz = deck.get("ad_mlswe", 0.0), deck.get("max_shear_dz", 0.0)
+    c.mesh_warp = deck.get("mesh_warp", 0.0)
     return c
 
 

@@ -20,9 +20,19 @@ def make_pair(params, variant=0, oracle_metrics=True, affine=True):
     given those numbers (first point of each element / face), as the Fortran shim would do."""
     deck = hn.decks.build_deck(params)
     params = dict(params)
-    params["affine_metrics"] = affine
+    general = params.get("mesh_warp", 0.0) != 0.0
+    params["affine_metrics"] = affine and not general
     O = oracle_lib.Oracle(params)
-    if oracle_metrics:
+    if general and oracle_metrics:
+        # general quadrilaterals: the per-point geometry of the oracle (= of the reference's metrics / normals code), as the Fortran
+        # shim would pass mod_metrics and mod_face
+        nq, ngl, nf = O.nq, O.ngl, O.nface
+        deck["point_metrics_q"] = np.stack([O.get(k) for k in ("ksiq_x", "ksiq_y", "etaq_x", "etaq_y", "jacq")], axis=1)
+        deck["point_metrics"] = np.stack([O.get(k) for k in ("ksi_x", "ksi_y", "eta_x", "eta_y", "jac")], axis=1)
+        deck["face_geom_q"] = np.concatenate([O.get("normal_vector_q").reshape(nf, nq, 2), O.get("jac_faceq").reshape(nf, nq, 1)], axis=2)
+        deck["face_geom_n"] = np.concatenate([O.get("normal_vector").reshape(nf, ngl, 2), O.get("jac_face").reshape(nf, ngl, 1)], axis=2)
+        deck["massinv"] = O.get("massinv")
+    elif oracle_metrics:
         nq2, nq = O.nq * O.nq, O.nq
         em = deck["elem_metrics"]
         em[:, 0] = O.get("ksiq_x")[::nq2]; em[:, 1] = O.get("ksiq_y")[::nq2]

@@ -78,6 +78,11 @@ def test_static_derivations(name):
 def test_phase_parity(name, variant):
     """btp_bcl_coeffs_qdf, create_rhs_btp and ti_barotropic_ssprk_mlswe phase by phase on a developed state"""
     deck, S, O = make_pair(DECKS[name](), variant=variant)
+    check_barotropic_phases(deck, S, O, name)
+    S.close()
+
+
+def check_barotropic_phases(deck, S, O, name):
     O.step(1)
     sync_state_from_oracle(S, O)
     O.btp_bcl_coeffs(); S.btp_bcl_coeffs()
@@ -116,7 +121,6 @@ def test_phase_parity(name, variant):
         assert rel_l2(a, b, floor=1e-30) < 1e-5 or np.linalg.norm(b) / np.sqrt(b.size) < 1e-9 * c * np.sqrt(deck["massinv"].max()), "graduvb_ave"
     e = natural_errors(S, O, deck)
     assert e["mass"] < 1e-10 and e["mom"] < 1e-11, e
-    S.close()
 
 
 @pytest.mark.parametrize("variant", [0, 1])
@@ -448,6 +452,11 @@ def test_layer_phase_parity(name, lw):
     would show here.  lw: warp-per-element layer kernels (47 default, 63 all of them) / block-per-element kernels (0)."""
     deck, S, O = make_pair(DECKS[name]())
     S.set_option("layer_warp", lw)
+    check_layer_phases(deck, S, O)
+    S.close()
+
+
+def check_layer_phases(deck, S, O):
     O.step(1)
     sync_state_from_oracle(S, O)
     O.btp_bcl_coeffs(); S.btp_bcl_coeffs()
@@ -467,7 +476,6 @@ def test_layer_phase_parity(name, lw):
     for k in range(deck["nlayers"]):
         for v in (0, 1):
             assert np.abs(a[k, :, v] - b[k, :, v]).max() <= 2e-14 * Hn * hscale, (k, v, np.abs(a[k, :, v] - b[k, :, v]).max(), Hn * hscale)
-    S.close()
 
 
 @pytest.mark.parametrize("partition,nranks", [("rows", 2), ("morton", 4), ("blocks:3x2", 6)])

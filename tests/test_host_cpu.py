@@ -43,6 +43,42 @@ def test_deck_matches_oracle_setup(name):
     assert np.abs(nv[:, 0, :] - d["face_geom"][:, :2]).max() < 1e-12
 
 
+@pytest.mark.parametrize("nop", [4, 3])
+def test_general_quadrilateral_deck_matches_oracle(nop):
+    """mesh_warp: curved, non-affine elements.  The per-point geometry decks.py hands to the library (nodal and quadrature-point
+    metric terms, face normals and Jacobians at the face nodes and face quadrature points) is the one the oracle derives with the
+    reference's metrics / normals code (metrics.F90, metrics_quad.F90, create_normals(_quad).F90); the elements really are
+    non-affine (the metric terms vary by tens of percent inside an element)."""
+    p = dict(hn.decks.synthetic_double_gyre(6, 4, nop=nop, nlayers=3), mesh_warp=0.15)
+    d = hn.decks.build_deck(p)
+    o = oracle_lib.Oracle(p)
+    assert d["elem_metrics"] is None and d["face_geom"] is None
+    c = o.get("coord").reshape(-1, 2)
+    assert np.abs(d["coord"] - c).max() <= 1e-9 * 2.0e6
+    assert np.abs(d["coord"] - hn.decks.build_deck(dict(p, mesh_warp=0.0))["coord"]).max() > 0.1 * 2.0e6 / 6 * 0.15
+    ref_q = np.stack([o.get(k) for k in ("ksiq_x", "ksiq_y", "etaq_x", "etaq_y", "jacq")], axis=1)
+    ref_n = np.stack([o.get(k) for k in ("ksi_x", "ksi_y", "eta_x", "eta_y", "jac")], axis=1)
+    for a, b in ((d["point_metrics_q"], ref_q), (d["point_metrics"], ref_n)):
+        assert a.shape == b.shape
+        assert np.abs(a - b).max(axis=0).max() <= 1e-11 * np.abs(b).max(axis=0).min() or np.all(np.abs(a - b).max(axis=0) <= 1e-11 * np.abs(b).max(axis=0))
+    nq2 = o.nq ** 2
+    kx = ref_q[:, 0].reshape(-1, nq2)
+    assert (kx.max(axis=1) / kx.min(axis=1)).max() > 1.2          # non-affine: the metric terms vary inside an element
+    fq = np.concatenate([o.get("normal_vector_q").reshape(o.nface, o.nq, 2), o.get("jac_faceq").reshape(o.nface, o.nq, 1)], axis=2)
+    fn = np.concatenate([o.get("normal_vector").reshape(o.nface, o.ngl, 2), o.get("jac_face").reshape(o.nface, o.ngl, 1)], axis=2)
+    assert np.abs(d["face_geom_q"][..., :2] - fq[..., :2]).max() < 1e-11 and np.abs(d["face_geom_q"][..., 2] / fq[..., 2] - 1).max() < 1e-11
+    assert np.abs(d["face_geom_n"][..., :2] - fn[..., :2]).max() < 1e-11 and np.abs(d["face_geom_n"][..., 2] / fn[..., 2] - 1).max() < 1e-11
+    assert np.abs(d["massinv"] / o.get("massinv") - 1).max() < 1e-11
+    for k in ("q_df", "qb_df", "qprime_df"):
+        assert np.allclose(d[k].ravel(), o.get(k), rtol=1e-12, atol=0.0), k
+    # the oracle itself on the warped mesh: discrete mass conservation of the barotropic RHS and of a whole step
+    assert o.step(2) == 0
+    q = o.get("q_df").reshape(3, -1, 3)
+    mass0 = (d["q_df"][:, :, 0] / o.get("massinv")[None, :]).sum(axis=1)
+    mass1 = (q[:, :, 0] / o.get("massinv")[None, :]).sum(axis=1)
+    assert np.abs(mass1 / mass0 - 1).max() < 1e-13
+
+
 def test_synthetic_deck_matches_oracle():
     p = hn.decks.synthetic_double_gyre(6, 6, nop=4, nlayers=3)
     d = hn.decks.build_deck(p)
