@@ -228,6 +228,30 @@ def run_reference(args):
 
 
 # ---- GPU arm ------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Bind this rank's host threads -- and with them the first-touch placement of its page-locked state arrays -- to the NUMA node
+    its GPU hangs off, the way `mpirun --bind-to numa` places the ranks of the Fortran program.  Without it the N ranks of a
+    multi-GPU run stream their state over PCIe through whichever socket the kernel happened to start them on.  Returns the node
+    number, or None when the topology is not visible (then nothing is changed)."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 class Comm:
     """torch.distributed plumbing of one run (barrier, reductions over the ranks)"""
 
@@ -240,6 +264,7 @@ class Comm:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
         torch.cuda.set_device(self.local_rank)
+        self.numa_node = bind_to_gpu_numa_node(torch, self.local_rank) if self.world > 1 else None
         self.dist = None
         if self.world > 1:
             import torch.distributed as dist
@@ -413,6 +438,7 @@ def run_leg(hn, comm, args, nelx, nely, nop, layers, steps, warmup, do_e2e):
         "config": {"nelem": nelx * nely, "npoin": npoin_global, "stages_per_step": stages_per_step, "dt": params["dt"], "dt_btp": deck["dt_btp"],
                    "processor_faces_per_rank_max": nfaces_proc, "neighbour_ranks_max": nnbh,
                    "resident_gb_per_rank": resident / 1e9,
+                   "host_numa_node_rank0": comm.numa_node,   # ranks are bound to the NUMA node of their GPU (None: topology not visible)
                    "stage_kernel_variant": args.variant, "options": args.opt},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "k_btp_stage_pair (fused barotropic SSPRK stage, element records)" if args.variant == 0 else "k_btp_stage_simple",

@@ -421,7 +421,11 @@ static int pair_pack(Solver& S, const Planes& qb, const Planes& qprime, int cur)
     p.rec = S.p_rec; p.tr = S.p_tr[cur];
     p.has_visc = S.has_visc;
     static const int pack_threads = getenv("HNUMO_PACK_THREADS") ? atoi(getenv("HNUMO_PACK_THREADS")) : 128;
-    k_pair_pack<<<S.nelem, pack_threads, 2 * S.npts * sizeof(double), S.stream>>>(p);
+    const size_t psm = 2 * S.npts * sizeof(double);
+    if (S.ngl == 5 && S.nq == 9) k_pair_pack<5, 9><<<S.nelem, pack_threads, psm, S.stream>>>(p);
+    else if (S.ngl == 9 && S.nq == 17) k_pair_pack<9, 17><<<S.nelem, pack_threads, psm, S.stream>>>(p);
+    else if (S.ngl == 4 && S.nq == 7) k_pair_pack<4, 7><<<S.nelem, pack_threads, psm, S.stream>>>(p);
+    else k_pair_pack<0, 0><<<S.nelem, pack_threads, psm, S.stream>>>(p);
     S.n_launches++;
     return halo_exchange_trace_records(S, S.p_tr[cur], D.TSIDE);
 }

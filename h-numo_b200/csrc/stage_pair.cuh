@@ -913,11 +913,13 @@ struct PairPackArgs {
 };
 // planes -> records, once per substep loop (block per element): header, state, statics, initial traces.
 // The running sums (ACCN, ACCQ, face sums) and the SSPRK work states are zeroed.
+// (G_, Q_ > 0: compile-time sizes -- the index arithmetic of the copy loops is division-heavy; 0: run-time sizes)
+template <int G_, int Q_>
 __global__ void k_pair_pack(PairPackArgs a) {
     extern __shared__ double sm[];
     __shared__ int s_flags;
     const PairDims& D = a.D;
-    const int G = D.G, Q = D.Q, NP = D.NP, NQ2 = D.NQ2;
+    const int G = G_ ? G_ : D.G, Q = Q_ ? Q_ : D.Q, NP = G * G, NQ2 = Q * Q;
     const int e = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const size_t nbase = (size_t)e * NP, qbase = (size_t)e * NQ2;
     double* r = a.rec + (size_t)e * D.REC;
