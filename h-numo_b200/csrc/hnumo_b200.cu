@@ -51,7 +51,16 @@ static bool use_pair(const Solver& S) { return S.variant == 0 && S.p_rec != null
 
 // warp-per-element layer kernels (layer_warp.cuh): nop 3 and 4, layer count compile-time for 2 and 3
 // S.layer_warp is a bit mask: 1 coeffs, 2 layer mass, 4 consistency, 8 laplacian, 16 momentum volume, 32 momentum faces + update
-static bool use_layer_warp(const Solver& S, int bit) { return (S.layer_warp & bit) && ((S.ngl == 5 && S.nq == 9) || (S.ngl == 4 && S.nq == 7)); }
+static bool use_layer_warp(const Solver& S, int bit) {
+    if (!(S.layer_warp & bit) || !((S.ngl == 5 && S.nq == 9) || (S.ngl == 4 && S.nq == 7))) return false;
+    // the face kernel stages the traces of every layer per warp (448 nl doubles at nop 4): beyond ~6 layers the block-per-element
+    // form runs instead (at the reference's maximum of 20 layers the warp form would need more shared memory than an SM has)
+    if (bit == 32) {
+        const size_t b = (size_t)LW_WARPS * sizeof(double) * (S.ngl == 5 ? lw_mface_doubles<5, 9>(S.nl) : lw_mface_doubles<4, 7>(S.nl));
+        if (b > 100 * 1024) return false;
+    }
+    return true;
+}
 // SM59 / SM47: dynamic shared memory (bytes) of the (5,9) / (4,7) instantiation
 #define HN_LAUNCH_LW(kern, SM59, SM47, S, args)                                                                              \
     do {                                                                                                                     \
