@@ -71,13 +71,22 @@ struct PairRec {
     static constexpr int ST = LineGeom<G, Q>::ST;
     static constexpr int S_NOD = 0;                 // 0 dpp 1 mx 2 my 3 pb 4 pp 5 up 6 vp 7 u 8 v ; later 4..7 = LDG flux variable
     static constexpr int S_X = S_NOD + 9 * NP;      // 8 quadrature-point arrays; later rhs, face traces, face fluxes
-    static constexpr int X_RHS = 0, X_FL = 3 * NP, X_FR = X_FL + 16 * G, X_LF = X_FR + 16 * G, X_FF = X_LF + 8 * G;
+    // Face phases 7b-7d of the warp form (nop 3, 4): row and side strides are chosen so that the shared-memory word index stays
+    // congruent to the lane number modulo 16 across the four sides -- the natural strides (8 Q per side, Q per row) cost one
+    // bank-conflict replay per half-warp that straddles a side (62 of 980 data-pipe wavefronts per element with the gradient-line
+    // lanes below; profiles/tools/bank_model.py).  The block form (nop 5-8) keeps the natural strides.
+    static constexpr bool WARPF = (G <= 5);
+    static constexpr int TR7 = WARPF ? 10 : Q;                                        // interpolated traces T[s][L/R x var][iq]: row stride (even, = 2 mod 4)
+    static constexpr int TS7 = WARPF ? LineGeom<G, Q>::pick(8 * TR7, Q) : 8 * Q;      // ... side stride (= Q mod 16)
+    static constexpr int FR7 = WARPF ? 10 : Q;                                        // face fluxes X_FF[s][field][iq]
+    static constexpr int FS7 = WARPF ? LineGeom<G, Q>::pick(3 * FR7, Q) : 3 * Q;
+    static constexpr int X_RHS = 0, X_FL = 3 * NP, X_FR = X_FL + 16 * G + (WARPF ? 2 : 0), X_LF = X_FR + 16 * G, X_FF = X_LF + 8 * G;
     static constexpr int S_T = S_X + 8 * SX;        // pass-1 results; later interpolated traces, projected face fluxes
     static constexpr int T_SZ = 8 * ST;
     static constexpr int S_L = S_T + T_SZ;          // LDG: 0..3 gradient lines / laplacian lines, 4..7 G, 8..11 Z
     static constexpr int S_TOTAL = S_L + 12 * NP;
-    static_assert(X_FF + 12 * Q <= 8 * SX, "face work does not fit in X");
-    static_assert(32 * Q <= T_SZ && 7 * ST <= T_SZ, "T too small");
+    static_assert(X_FF + 4 * FS7 <= 8 * SX, "face work does not fit in X");
+    static_assert(4 * TS7 <= T_SZ && 7 * ST <= T_SZ, "T too small");
     static size_t smem_bytes(int ne, int warps) { return (size_t)warps * ((size_t)S_TOTAL * ne + (size_t)HDR * ne) * sizeof(double); }
 };
 
@@ -205,6 +214,10 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
     constexpr int J2B = BLK ? 4 * G : 0, J2C = BLK ? 64 : 0;   // phase 2: bottom-layer rows, LDG gradient lines
     constexpr int J5A = BLK ? 64 : 0;                           // phase 5: the B.Fe + A.S contraction
     constexpr int J6B = BLK ? 32 : 0, J6C = BLK ? 32 + 4 * G : 0;   // phase 6: LDG laplacian lines, face traces
+    // The 4 G lines of a gradient phase: in the warp form the row lines (along ksi) take the first half-warp and the column lines
+    // (along eta) the second -- a row lane and a column lane of one half-warp hit the same bank with different words otherwise
+    constexpr bool GSPLIT = !BLK && 2 * G <= 16;
+    auto grad_lane = [](int lj) { return GSPLIT ? (lj >= 0 && lj < 32 && (lj & 15) < 2 * G) : (lj >= 0 && lj < 4 * G); };
     // (splitting scatter pass 2 into its B.TB and A.TA halves on two warps was measured neutral: 1.435 vs 1.422 ms)
     static_assert(!BLK || (J2B + 3 * G <= J2C && J2C + 4 * G <= NT && J5A + 3 * Q <= NT && 3 * Q <= J5A && 3 * G <= J6B && J6C + 4 * G <= NT),
                   "job lane ranges");
@@ -398,8 +411,8 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
             const int lj = lane - J2B, f = 4 + lj / G, m = lj % G;
             pl_n2q<NE, G, Q, false, 1, 1>(nod + f * NP + m * G, T + f * ST + m * TM);
         }
-        if (VISC && lane >= J2C && lane < J2C + 4 * G) {
-            const int lj = lane - J2C, kind = lj / (2 * G), r = lj - kind * 2 * G, f = r / G, l = r - f * G;
+        if (VISC && grad_lane(lane - J2C)) {
+            const int lj = lane - J2C, kind = GSPLIT ? lj >> 4 : lj / (2 * G), r = GSPLIT ? (lj & 15) : lj - kind * 2 * G, f = r / G, l = r - f * G;
             const int stride = kind ? G : 1, off = kind ? l : l * G;
             pl_grad<NE, G, false>(nod + (7 + f) * NP + off, Lr + (2 * kind + f) * NP + off, stride);
         }
@@ -566,8 +579,8 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
         for (int n = 0; n < G; ++n) V::st(X + R::X_RHS + f * NP + m * G + n, r[n]);
     }
     // LDG volume lines (btp_compute_laplacian): lapX[c][m'][n'] = sum_n D(n',n) Zxi_c[m'][n]; lapE[c][m'][n'] = sum_m D(m',m) Zeta_c[m][n']
-    if (VISC && lane >= J6B && lane < J6B + 4 * G) {
-        const int lj = lane - J6B, kind = lj / (2 * G), r = lj - kind * 2 * G, cc = r / G, l = r - cc * G;
+    if (VISC && grad_lane(lane - J6B)) {
+        const int lj = lane - J6B, kind = GSPLIT ? lj >> 4 : lj / (2 * G), r = GSPLIT ? (lj & 15) : lj - kind * 2 * G, cc = r / G, l = r - cc * G;
         const int stride = kind ? G : 1, off = kind ? l : l * G;
         pl_grad<NE, G, true>(Lr + (8 + 2 * kind + cc) * NP + off, Lr + (2 * kind + cc) * NP + off, stride);
     }
@@ -665,7 +678,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
     // ---- 7b. interpolate the traces to the face quadrature points: one (side, L/R, variable) line per lane
     if (NT == 32 || lane < 32) {
         const int s = lane >> 3, side = (lane >> 2) & 1, var = lane & 3;   // var: 0 pb 1 pbpert 2 mx 3 my
-        pl_n2q<NE, G, Q, false, 1, 1>(X + R::X_FL + side * 16 * G + (var * 4 + s) * G, T + lane * Q);
+        pl_n2q<NE, G, Q, false, 1, 1>(X + (side ? R::X_FR : R::X_FL) + (var * 4 + s) * G, T + s * R::TS7 + (side * 4 + var) * R::TR7);
     }
     // update operands of node I, one phase ahead
     double mi[NE], q0v[3][NE], q2v[3][NE];
@@ -689,11 +702,12 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
         const bool pvalid = (it + 1) * NT <= 4 * Q || it * NT + lane < 4 * Q;
         {
             const int s = p / Q, iq = p - s * Q;
-            const VT* Lp = T + (s * 8) * Q + iq;
-            const VT* Rp = T + (s * 8 + 4) * Q + iq;
+            constexpr int TR7 = R::TR7;
+            const VT* Lp = T + s * R::TS7 + iq;
+            const VT* Rp = Lp + 4 * TR7;
             double pbL[NE], ppL[NE], mxL[NE], myL[NE], pbR[NE], ppR[NE], mxR[NE], myR[NE];
-            V::ld(Lp, pbL); V::ld(Lp + Q, ppL); V::ld(Lp + 2 * Q, mxL); V::ld(Lp + 3 * Q, myL);
-            V::ld(Rp, pbR); V::ld(Rp + Q, ppR); V::ld(Rp + 2 * Q, mxR); V::ld(Rp + 3 * Q, myR);
+            V::ld(Lp, pbL); V::ld(Lp + TR7, ppL); V::ld(Lp + 2 * TR7, mxL); V::ld(Lp + 3 * TR7, myL);
+            V::ld(Rp, pbR); V::ld(Rp + TR7, ppR); V::ld(Rp + 2 * TR7, mxR); V::ld(Rp + 3 * TR7, myR);
             const double wq0 = c_ops.wq[iq];
             double f0[NE], f1[NE], f2[NE];
             PR_FORC {
@@ -742,8 +756,8 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
                 const double sgn = left ? -wq : wq;
                 f0[c] = sgn * flux; f1[c] = sgn * (nxl * Hf + flux_x); f2[c] = sgn * (nyl * Hf + flux_y);
             }
-            VT* ff = X + R::X_FF + (s * 3) * Q + iq;
-            V::st(ff, f0); V::st(ff + Q, f1); V::st(ff + 2 * Q, f2);
+            VT* ff = X + R::X_FF + s * R::FS7 + iq;
+            V::st(ff, f0); V::st(ff + R::FR7, f1); V::st(ff + 2 * R::FR7, f2);
         }
     }
     if (BULK) pr_fence_async_smem();
@@ -763,7 +777,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
     // ---- 7d. project the face fluxes onto the face nodes: one (side, field) line per lane -> T[0 .. 12G)
     if (lane < 12) {
         double pr[G][NE];
-        pl_q2n_acc<NE, G, Q, false, 1, true>(X + R::X_FF + lane * Q, pr);
+        pl_q2n_acc<NE, G, Q, false, 1, true>(X + R::X_FF + (lane / 3) * R::FS7 + (lane % 3) * R::FR7, pr);
 #pragma unroll
         for (int n = 0; n < G; ++n) V::st(T + lane * G + n, pr[n]);
     }
@@ -839,8 +853,8 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
     PR_STAMP(10);
     // ---- 9. traces of the new state (+ LDG gradient) for the next stage
     if (VISC) {
-        if (lane < 4 * G) {
-            const int kind = lane / (2 * G), r = lane - kind * 2 * G, f = r / G, l = r - f * G;
+        if (grad_lane(lane)) {
+            const int kind = GSPLIT ? lane >> 4 : lane / (2 * G), r = GSPLIT ? (lane & 15) : lane - kind * 2 * G, f = r / G, l = r - f * G;
             const int stride = kind ? G : 1, off = kind ? l : l * G;
             pl_grad<NE, G, false>(nod + (7 + f) * NP + off, Lr + (2 * kind + f) * NP + off, stride);
         }
