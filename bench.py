@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--cpu-cores", type=int, default=0, help="CPU instances of the baseline (default: every core this process may run on)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-host", default="caller", choices=["caller", "torch-pinned"], help="host arrays of the e2e leg: ordinary allocations that the "
+                    "library page-locks on first use (default; what the Fortran shim passes), or torch pinned buffers")
     ap.add_argument("--no-config5", action="store_true", help="skip the BASELINE config 5 leg (nop 8, 10 layers, 500x500)")
     ap.add_argument("--no-cross-check", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library tuning option key=value (hnumo_set_option)")
@@ -412,9 +414,16 @@ def run_leg(hn, comm, args, nelx, nely, nop, layers, steps, warmup, do_e2e):
     e2e = None
     if do_e2e:
         nl, npn = deck["nlayers"], deck["npoin"]
-        q = torch.from_numpy(deck["q_df"].copy()).pin_memory()
-        qb = torch.from_numpy(deck["qb_df"].copy()).pin_memory()
-        qp = torch.from_numpy(deck["qprime_df"].copy()).pin_memory()
+        if args.e2e_host == "torch-pinned":
+            q = torch.from_numpy(deck["q_df"].copy()).pin_memory()
+            qb = torch.from_numpy(deck["qb_df"].copy()).pin_memory()
+            qp = torch.from_numpy(deck["qprime_df"].copy()).pin_memory()
+            host_note = "pinned (torch)"
+        else:
+            # ordinary host arrays, as the Fortran driver's allocatables are: the library page-locks the caller's arrays once
+            # (cudaHostRegister in hnumo_ti_rk_bcl, first call = the warm-up call below) and copies from / to them directly
+            q = torch.from_numpy(deck["q_df"].copy()); qb = torch.from_numpy(deck["qb_df"].copy()); qp = torch.from_numpy(deck["qprime_df"].copy())
+            host_note = "caller's ordinary arrays, page-locked once by the library (cudaHostRegister)"
         S.download_state((q.numpy(), qb.numpy(), qp.numpy()))
         n_e2e = max(1, min(steps, 2))
         S.ti_rk_bcl(q.numpy(), qb.numpy(), qp.numpy())  # warm the path
@@ -428,7 +437,7 @@ def run_leg(hn, comm, args, nelx, nely, nop, layers, steps, warmup, do_e2e):
         e2e_s = comm.max(t1 - t0)
         nbytes = (3 * nl + 4 + 3 * nl) * npn * 8
         e2e = {"value": 3.0 * npoin_global * stages_per_step * n_e2e / e2e_s, "unit": "DOF-updates/s", "h2d_bytes_per_step": nbytes,
-               "d2h_bytes_per_step": nbytes, "steps": n_e2e, "ms_per_step": 1e3 * e2e_s / n_e2e, "host_buffers": "pinned (torch)"}
+               "d2h_bytes_per_step": nbytes, "steps": n_e2e, "ms_per_step": 1e3 * e2e_s / n_e2e, "host_buffers": host_note}
         launches += S.timing(reset=True)["launches"]
     nfaces_proc = int(comm.max(len(deck["nbh_send_recv"])))
     nnbh = int(comm.max(len(deck["nbh_proc"])))
