@@ -99,7 +99,7 @@ struct PairArgs {
     double a1, a2, a3, dtt, g, cd_g, cd_alpha, visc;   // cd_g = cd/g (botfr 1), cd_alpha = cd/alpha_bottom (botfr 2)
     int botfr, load_q0, load_q2, store_q0, store_q2;
     int prefetch, pf_dist;   // L2 prefetch: bit 0: own record tail at start; bits 1,2: head (header, state, nodal statics and sums) and
-                             // quadrature statics of the record pf_dist units ahead (default 6); bits 3-5: experiments, slower
+                             // quadrature statics of the record pf_dist units ahead
     // element subsets of a launch (halo exchange overlapped with interior work):
     //   part 0: every element; part 1: the `count` elements of `elist` (those with a processor face);
     //   part 2: every element that has no processor face (warps of the others leave once their header has arrived)
@@ -150,19 +150,10 @@ __device__ __forceinline__ void pr_red(double* p, double v) { }
 __device__ __forceinline__ void pr_red(double* p, double v) { atomicAdd(p, v); }
 #endif
 
-// Bulk running sums: the contributions of one element are staged in shared memory in the layout of the sum arrays of its
-// record and added to them by ONE asynchronous bulk reduction (cp.reduce.async.bulk .add.f64, executed by the TMA unit)
-// instead of one RED instruction per 32 values: under load every global store/RED instruction holds the issuing warp
-// for 70-150 cycles (profiles/phase_timing.py with -DHN_PAIR_DIAG), 46 of them per element.  Every address still
-// receives exactly one add per launch: bitwise the same sums.
-__device__ __forceinline__ void pr_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void pr_bulk_add(double* gdst, const double* ssrc, uint32_t bytes) {
-    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
-                 ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void pr_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void pr_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ double* pr_align16(double* p) { return reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15); }
+// (Running sums by ONE asynchronous bulk reduction per sum array -- cp.reduce.async.bulk .add.f64 from a shared-memory staging
+//  area -- were measured slower than the RED instructions, 1.567 vs 1.533 ms per stage at 500x500 elements: the pointwise phase
+//  waits for the memory system, not for the issue of the REDs.  profiles/r1_stage_kernel_experiments.md; the code path was removed
+//  in round 2.)
 
 __device__ __forceinline__ void pr_prefetch_l2(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
@@ -198,14 +189,6 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
     typedef typename V::T VT;
     constexpr int NP = R::NP, NQ2 = R::NQ2, SX = R::SX, ST = R::ST, TM = R::TM;
     constexpr int NT = BLK ? 32 * W : 32;
-    // Running sums by bulk reduction: measured SLOWER than the RED instructions (1.567 vs 1.533 ms per stage at 500x500: the time
-    // of the pointwise phase is the wait for the quadrature statics under a saturated memory system, not the issue of the REDs;
-    // profiles/r1_stage_kernel_experiments.md), so it is compiled only on request.
-#ifdef HN_PAIR_BULK
-    constexpr bool BULK = !BLK && NE == 1;
-#else
-    constexpr bool BULK = false;
-#endif
     constexpr int NQIT = (NQ2 + NT - 1) / NT, NFIT = (4 * Q + NT - 1) / NT;
     static_assert(NP <= NT && 4 * G <= NT && 3 * Q <= NT && 12 <= NT && R::HDR <= NT, "polynomial order too high for this lane mapping");
     static_assert(!BLK || NE == 1, "block-per-element mode advances one element");
@@ -221,11 +204,6 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
     // (splitting scatter pass 2 into its B.TB and A.TA halves on two warps was measured neutral: 1.435 vs 1.422 ms)
     static_assert(!BLK || (J2B + 3 * G <= J2C && J2C + 4 * G <= NT && J5A + 3 * Q <= NT && 3 * Q <= J5A && 3 * G <= J6B && J6C + 4 * G <= NT),
                   "job lane ranges");
-    static_assert(!BULK || (6 * NQ2 + 2 <= R::T_SZ + 4 * NP && 6 * NP + 2 <= 8 * NP), "staging of the quadrature / nodal sums");
-    // staging of the face sums of the 4 sides: behind the face work in X, behind the interpolated traces in T, in Lr[4..11]
-    constexpr int FS_X = (8 * SX - R::X_FF - 12 * Q - 2) / R::ASIDE, FS_T = (R::T_SZ - 32 * Q - 2) / R::ASIDE, FS_L = (8 * NP - 2) / R::ASIDE;
-    static_assert(!BULK || FS_X + FS_T + FS_L >= 4, "staging of the face sums");
-    static_assert(!BULK || ((6 * NQ2 * 8) % 16 == 0 && (R::ASIDE * 8) % 16 == 0 && (6 * NP * 8) % 16 == 0), "bulk sizes are multiples of 16 bytes");
     extern __shared__ __align__(16) double sm_all[];
     const int lane = BLK ? (int)threadIdx.x : (int)(threadIdx.x & 31), warp = BLK ? 0 : (int)(threadIdx.x >> 5);
     const int unit = BLK ? (int)blockIdx.x : (int)(blockIdx.x * W + warp);
@@ -295,15 +273,8 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
             // the head of the record (header, state, nodal statics and sums) of the unit that follows one wave later
             if ((a.prefetch & 2) && a.part != 1 && (long)(unit + a.pf_dist) * NE + lane < a.nelem)
                 pr_prefetch_l2(p + (size_t)a.pf_dist * NE * R::REC, (uint32_t)(R::O_QST * sizeof(double)));
-            // ... its face coefficients and neighbour viscosity statics (bit 3)
-            if ((a.prefetch & 8) && a.part != 1 && (long)(unit + a.pf_dist) * NE + lane < a.nelem)
-                pr_prefetch_l2(p + (size_t)a.pf_dist * NE * R::REC + R::O_FST, (uint32_t)((R::O_Q0 - R::O_FST) * sizeof(double)));
-            // ... its quadrature running sums, the RED targets of phase 4 (bit 4), its four trace records of the previous stage,
-            //     which its neighbours read (bit 5)
-            if ((a.prefetch & 16) && a.part != 1 && (long)(unit + a.pf_dist) * NE + lane < a.nelem)
-                pr_prefetch_l2(p + (size_t)a.pf_dist * NE * R::REC + R::O_ACCQ, (uint32_t)((R::O_FST - R::O_ACCQ) * sizeof(double)));
-            if ((a.prefetch & 32) && a.part != 1 && (long)(unit + a.pf_dist) * NE + lane < a.nelem)
-                pr_prefetch_l2(a.tr_in + ((size_t)(unit + a.pf_dist) * NE + lane) * 4 * R::TSIDE, (uint32_t)(4 * R::TSIDE * sizeof(double)));
+            // (also prefetching its face coefficients, its quadrature running sums or its trace records was measured slower:
+            //  1.44-1.51 against 1.43 ms per stage at 500x500 elements, profiles/r1_stage_kernel_experiments.md)
             // ... and its quadrature statics (bit 2)
             if ((a.prefetch & 4) && a.part != 1 && (long)(unit + a.pf_dist) * NE + lane < a.nelem)
                 pr_prefetch_l2(p + (size_t)a.pf_dist * NE * R::REC + R::O_QST, (uint32_t)((R::O_ACCQ - R::O_QST) * sizeof(double)));
@@ -331,10 +302,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
             const double rpb = pr_rcp(pb[c]);
             u[c] = mx[c] * rpb; v[c] = my[c] * rpb;
             const double t = 1.0 + dpp[c] * oop[c];
-            if (BULK) {   // staged in Lr[4..11] (free until the LDG part of phase 3)
-                double* sg = pr_align16(reinterpret_cast<double*>(Lr + 4 * NP)) + I;
-                sg[0] = t * t; sg[NP] = u[c]; sg[2 * NP] = v[c]; sg[3 * NP] = dpp[c]; sg[4 * NP] = mx[c]; sg[5 * NP] = my[c];
-            } else if (ok[c]) {
+            if (ok[c]) {
                 double* r = rec[c];
                 pr_red(r + R::O_ACCN + I, t * t); pr_red(r + R::O_ACCN + NP + I, u[c]); pr_red(r + R::O_ACCN + 2 * NP + I, v[c]);
                 pr_red(r + R::O_ACCN + 3 * NP + I, dpp[c]); pr_red(r + R::O_ACCN + 4 * NP + I, mx[c]); pr_red(r + R::O_ACCN + 5 * NP + I, my[c]);
@@ -343,14 +311,8 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
         V::st(nod + 0 * NP + I, dpp); V::st(nod + 1 * NP + I, mx); V::st(nod + 2 * NP + I, my); V::st(nod + 3 * NP + I, pb);
         if (botfr) { V::st(nod + 4 * NP + I, pp); V::st(nod + 5 * NP + I, up); V::st(nod + 6 * NP + I, vp); }
         V::st(nod + 7 * NP + I, u); V::st(nod + 8 * NP + I, v);
-        if (BULK) pr_fence_async_smem();
     }
     pr_sync<NT>();
-    if (BULK && lane == 0) {
-        static_assert((6 * NP * 8) % 16 == 0 || !BULK, "bulk size");
-        pr_bulk_add(rec[0] + R::O_ACCN, pr_align16(reinterpret_cast<double*>(Lr + 4 * NP)), 6 * NP * 8);
-        pr_bulk_commit();
-    }
     PR_STAMP(1);
     // per-element geometry and flags (registers)
     double ksx[NE], ksy[NE], etx[NE], ety[NE], J[NE];
@@ -366,19 +328,6 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
         PR_FORC {
             if (lane == c && (flags[c] & (PF_GZ | PF_TWY)) && (long)(unit + a.pf_dist) * NE + c < a.nelem)
                 pr_prefetch_l2(rec[c] + (size_t)a.pf_dist * NE * R::REC + R::O_QSTR, (uint32_t)(pr_pad2(R::QST_RARE * NQ2) * sizeof(double)));
-        }
-    }
-    // face coefficients of the four sides (own record for owned sides, the owner's record otherwise) and the neighbour
-    // viscosity statics -> L2 now that the header says where they are: they are loaded in phase 6 and used in phase 7 (bit 6)
-    if ((a.prefetch & 64) && NE == 1 && lane < 5) {
-        const int* hi = reinterpret_cast<const int*>(hdr + 18);
-        if (lane < 4) {
-            const int nb = hi[lane];
-            const bool left = (nb < 0) || (e[0] < nb);
-            const double* cf = left ? rec[0] + R::O_FST + lane * R::FSIDE : a.rec + (size_t)nb * R::REC + R::O_FST + (hi[4 + lane] - 4 * nb) * R::FSIDE;
-            pr_prefetch_l2(cf, (uint32_t)(R::FSIDE * sizeof(double)));
-        } else {
-            pr_prefetch_l2(rec[0] + R::O_VST, (uint32_t)(4 * R::VSIDE * sizeof(double)));
         }
     }
     // neighbour traces and owned face sums -> L2 (the header has just told us where they are): one 128-byte line per lane
@@ -416,7 +365,6 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
             const int stride = kind ? G : 1, off = kind ? l : l * G;
             pl_grad<NE, G, false>(nod + (7 + f) * NP + off, Lr + (2 * kind + f) * NP + off, stride);
         }
-        if (BULK && lane == 0) pr_bulk_wait_read();   // the staged nodal sums have been read: Lr[4..11] may be rewritten
     }
     pr_sync<NT>();
     PR_STAMP(2);
@@ -488,13 +436,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
                 const double qu = ub * udp[c] + ope * s_uu;
                 const double quv = ub * vdp[c] + ope * s_uv;
                 const double qv = vb * vdp[c] + ope * s_vv;
-                if (BULK) {   // staged in T and Lr[0..3] (contiguous; free between phase 3 and the stores of phase 5)
-                    if (qvalid) {
-                        double* sg = pr_align16(reinterpret_cast<double*>(T)) + q;
-                        sg[0] = qu; sg[NQ2] = qv; sg[2 * NQ2] = quv; sg[3 * NQ2] = ope2; sg[4 * NQ2] = ub; sg[5 * NQ2] = vb;
-                        if (BOTFR == 2) { double* rr_ = rec[c] + R::O_ACCQR + q; pr_red(rr_, tb_u); pr_red(rr_ + NQ2, tb_v); }
-                    }
-                } else if (qvalid && ok[c]) {
+                if (qvalid && ok[c]) {
                     double* ra = rec[c] + R::O_ACCQ + q;
                     pr_red(ra, qu); pr_red(ra + NQ2, qv); pr_red(ra + 2 * NQ2, quv);
                     pr_red(ra + 3 * NQ2, ope2); pr_red(ra + 4 * NQ2, ub); pr_red(ra + 5 * NQ2, vb);
@@ -540,22 +482,13 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
             }
         }
     }
-    if (BULK) pr_fence_async_smem();
     pr_sync<NT>();
-    if (BULK && lane == 0) {
-        pr_bulk_add(rec[0] + R::O_ACCQ, pr_align16(reinterpret_cast<double*>(T)), 6 * NQ2 * 8);
-        pr_bulk_commit();
-    }
     PR_STAMP(4);
     // ---- 5. scatter pass 1 (contraction over j): lane (f,i) -> TB_f = A.Fk_f, TA_f = B.Fe_f + A.S_f, as T[f][m][i], T[3+f][m][i]
     if (lane < 3 * Q) {
         const int f = lane / Q, i = lane - f * Q;
         double tb[G][NE];
         pl_q2n_acc<NE, G, Q, false, Q, true>(X + f * SX + i, tb);
-        if (BULK) {   // the staged quadrature sums (in T) must have been read before T is rewritten
-            if (lane == 0) pr_bulk_wait_read();
-            __syncwarp((1u << (3 * Q < 32 ? 3 * Q : 31)) - 1u);
-        }
 #pragma unroll
         for (int m = 0; m < G; ++m) V::st(T + f * ST + m * TM + i, tb[m]);
     }
@@ -731,17 +664,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
                 const double qvv = 0.5 * (vl * myL[c] + vr * myR[c]) + ope_e * s_vve;
                 const double e2 = ope_e * ope_e;
                 const double Hf = e2 * s_He;
-                if (BULK) {   // staged per side: sides 0..2 behind the face work in X, side 3 behind the traces in T
-                    if (left && pvalid) {
-                        const double ol = 1.0 + ppL[c] * fc[it][9][c], orr = 1.0 + ppR[c] * fc[it][10][c];
-                        double* sg = (s < FS_X ? pr_align16(reinterpret_cast<double*>(X) + R::X_FF + 12 * Q) + s * R::ASIDE
-                                      : s < FS_X + FS_T ? pr_align16(reinterpret_cast<double*>(T) + 32 * Q) + (s - FS_X) * R::ASIDE
-                                                        : pr_align16(reinterpret_cast<double*>(Lr + 4 * NP)) + (s - FS_X - FS_T) * R::ASIDE) + iq;
-                        sg[0] = quu; sg[Q] = quv; sg[2 * Q] = qvu; sg[3 * Q] = qvv; sg[4 * Q] = ol * ol; sg[5 * Q] = orr * orr; sg[6 * Q] = e2;
-                        sg[7 * Q] = ul; sg[8 * Q] = ur; sg[9 * Q] = vl; sg[10 * Q] = vr;
-                        if (11 * Q < R::ASIDE && iq == 0) sg[11 * Q] = 0.0;   // pad word of the side
-                    }
-                } else if (left && pvalid && ok[c]) {
+                if (left && pvalid && ok[c]) {
                     const double ol = 1.0 + ppL[c] * fc[it][9][c], orr = 1.0 + ppR[c] * fc[it][10][c];
                     double* af = a.accf + ((size_t)e[c] * 4 + s) * R::ASIDE + iq;
                     pr_red(af, quu); pr_red(af + Q, quv); pr_red(af + 2 * Q, qvu); pr_red(af + 3 * Q, qvv);
@@ -760,19 +683,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
             V::st(ff, f0); V::st(ff + R::FR7, f1); V::st(ff + 2 * R::FR7, f2);
         }
     }
-    if (BULK) pr_fence_async_smem();
     pr_sync<NT>();
-    if (BULK && lane < 4) {   // one bulk reduction per owned side
-        const int nb = reinterpret_cast<const int*>(hdr + 18)[lane];
-        if ((nb < 0) || (e[0] < nb)) {
-            const int s = lane;
-            const double* sg = s < FS_X ? pr_align16(reinterpret_cast<double*>(X) + R::X_FF + 12 * Q) + s * R::ASIDE
-                               : s < FS_X + FS_T ? pr_align16(reinterpret_cast<double*>(T) + 32 * Q) + (s - FS_X) * R::ASIDE
-                                                 : pr_align16(reinterpret_cast<double*>(Lr + 4 * NP)) + (s - FS_X - FS_T) * R::ASIDE;
-            pr_bulk_add(a.accf + ((size_t)e[0] * 4 + lane) * R::ASIDE, sg, R::ASIDE * 8);
-            pr_bulk_commit();
-        }
-    }
     PR_STAMP(8);
     // ---- 7d. project the face fluxes onto the face nodes: one (side, field) line per lane -> T[0 .. 12G)
     if (lane < 12) {
@@ -879,7 +790,6 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
             }
         }
     }
-    if (BULK && lane < 4) pr_bulk_wait_read();   // the staged face sums must have been read before the shared memory is released
     PR_STAMP(15);
 }
 
