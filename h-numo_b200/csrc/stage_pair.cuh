@@ -54,15 +54,16 @@ struct PairRec {
     // face statics per side: cL cR cLR lam oop_edge Quu_e Quv_e Qvv_e Hbcl_e 1/pbl 1/pbr (copy of the owner's values)
     static constexpr int FSIDE = pr_pad2(11 * Q);
     static constexpr int O_FST = O_ACCQ + pr_pad2(6 * NQ2);
-    // neighbour's viscosity statics at the face nodes (ghosts resolved): bdg0..3, pbv, and the neighbour's pbprime
-    static constexpr int VSIDE = pr_pad2(6 * G);
+    // the neighbour's pbprime at the face nodes.  (The neighbour's LDG statics are not needed: a trace record carries the flux
+    // variable q = pbprime_visc grad(ub,vb) + btp_dpp_graduv of its element, which is all the face flux reads of the other side.)
+    static constexpr int VSIDE = pr_pad2(G);
     static constexpr int O_VST = O_FST + 4 * FSIDE;
     static constexpr int O_Q0 = O_VST + 4 * VSIDE, O_Q2 = O_Q0 + QBSZ;         // SSPRK work states
     static constexpr int O_QSTR = O_Q2 + QBSZ;                                   // rare quadrature statics 7..9
     static constexpr int O_ACCQR = O_QSTR + pr_pad2(QST_RARE * NQ2);             // rare quadrature sums 6,7
     static constexpr int REC = O_ACCQR + pr_pad2(2 * NQ2);
     static constexpr int ASIDE = pr_pad2(11 * Q);   // face sums, separate array [slot][ASIDE]
-    static constexpr int TSIDE = pr_pad2(7 * G);    // trace record [slot][7][G]: pbpert mx my G0..G3
+    static constexpr int TSIDE = pr_pad2(7 * G);    // trace record [slot][7][G]: pbpert mx my q0..q3 (LDG flux variable)
     // shared memory per warp, in units of NE doubles.  The strides SX, ST, TM are padded so that in the line phases
     // (lane = Q*f + i, or lane = G*f + m) the word index is congruent to the lane number modulo 16: no bank conflicts
     // (profiles/smem_conflicts.py).
@@ -391,7 +392,6 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
                 z0[c] = w * (ksx[c] * q0[c] + ksy[c] * q1[c]); z1[c] = w * (ksx[c] * q2[c] + ksy[c] * q3[c]);
                 z2[c] = w * (etx[c] * q0[c] + ety[c] * q1[c]); z3[c] = w * (etx[c] * q2[c] + ety[c] * q3[c]);
             }
-            V::st(Lr + 4 * NP + I, g0); V::st(Lr + 5 * NP + I, g1); V::st(Lr + 6 * NP + I, g2); V::st(Lr + 7 * NP + I, g3);
             V::st(nod + 4 * NP + I, q0); V::st(nod + 5 * NP + I, q1); V::st(nod + 6 * NP + I, q2); V::st(nod + 7 * NP + I, q3);
             V::st(Lr + 8 * NP + I, z0); V::st(Lr + 9 * NP + I, z1); V::st(Lr + 10 * NP + I, z2); V::st(Lr + 11 * NP + I, z3);
         }
@@ -461,8 +461,8 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
             }
         }
     }
-    // neighbour traces and the neighbour's viscosity statics of face node (s,n), issued one phase ahead
-    double tn[7][NE], vs[6][NE];
+    // neighbour traces (state and LDG flux variable) and the neighbour's pbprime of face node (s,n), issued one phase ahead
+    double tn[7][NE], pbnp[NE];
     const int lf = lane - J6C;                     // face node owned by this lane (0 <= lf < 4G)
     const bool face_lane = lf >= 0 && lf < 4 * G;
     const int fs = face_lane ? lf / G : 0, fn = face_lane ? lf - fs * G : 0;
@@ -474,12 +474,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
 #pragma unroll
                 for (int k = 0; k < (VISC ? 7 : 3); ++k) tn[k][c] = t[k * G];
             }
-            const double* vp_ = rec[c] + R::O_VST + fs * R::VSIDE + fn;
-            vs[5][c] = vp_[5 * G];
-            if (VISC) {
-#pragma unroll
-                for (int k = 0; k < 5; ++k) vs[k][c] = vp_[k * G];
-            }
+            pbnp[c] = rec[c][R::O_VST + fs * R::VSIDE + fn];
         }
     }
     pr_sync<NT>();
@@ -523,10 +518,10 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
         const int s = fs, n = fn, I = pr_face_node<G>(s, n);
         double ow0[NE], ow1[NE], ow2[NE], pbo[NE];
         V::ld(nod + 0 * NP + I, ow0); V::ld(nod + 1 * NP + I, ow1); V::ld(nod + 2 * NP + I, ow2); V::ld(nod + 3 * NP + I, pbo);
-        double go[4][NE], qo[4][NE];
+        double qo[4][NE];
         if (VISC) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { V::ld(Lr + (4 + k) * NP + I, go[k]); V::ld(nod + (4 + k) * NP + I, qo[k]); }
+            for (int k = 0; k < 4; ++k) V::ld(nod + (4 + k) * NP + I, qo[k]);
         }
         double L0[NE], L1[NE], L2[NE], L3[NE], R0[NE], R1[NE], R2[NE], R3[NE], lfu[NE], lfv[NE];
         const double wgn = c_ops.wg[n];
@@ -543,29 +538,23 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
                 if (nb == NBR_FREESLIP) { const double un = nx * ow1[c] + ny * ow2[c]; n1 = ow1[c] - 2.0 * un * nx; n2 = ow2[c] - 2.0 * un * ny; }
                 else if (nb == NBR_NOSLIP) { n1 = -ow1[c]; n2 = -ow2[c]; }
             }
-            const double pbn = n0 + vs[5][c];
+            const double pbn = n0 + pbnp[c];
             L0[c] = left ? pbo[c] : pbn; R0[c] = left ? pbn : pbo[c];
             L1[c] = left ? ow0[c] : n0;  R1[c] = left ? n0 : ow0[c];
             L2[c] = left ? ow1[c] : n1;  R2[c] = left ? n1 : ow1[c];
             L3[c] = left ? ow2[c] : n2;  R3[c] = left ? n2 : ow2[c];
             if (VISC) {
-                double gn[4];
-                if (tr >= 0) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) gn[k] = tn[3 + k][c];
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) gn[k] = go[k][c];
-                    if (nb == NBR_FREESLIP) {
-                        double un = go[0][c] * nx + go[1][c] * ny;
-                        gn[0] = go[0][c] - 2.0 * un * nx; gn[1] = go[1][c] - 2.0 * un * ny;
-                        un = go[2][c] * nx + go[3][c] * ny;
-                        gn[2] = go[2][c] - 2.0 * un * nx; gn[3] = go[3][c] - 2.0 * un * ny;
-                    }
-                }
+                // the other side's flux variable: published by the neighbour, or -- at a wall -- the ghost of the own one: gradient and
+                // statics of the ghost are the mirror images of the own ones (mod_laplacian_quad.F90:85-98), and the mirror is linear
                 double fo_[4], fn_[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { fo_[k] = qo[k][c]; fn_[k] = vs[4][c] * gn[k] + vs[k][c]; }
+                for (int k = 0; k < 4; ++k) { fo_[k] = qo[k][c]; fn_[k] = (tr >= 0) ? tn[3 + k][c] : qo[k][c]; }
+                if (tr < 0 && nb == NBR_FREESLIP) {
+                    double un = qo[0][c] * nx + qo[1][c] * ny;
+                    fn_[0] = qo[0][c] - 2.0 * un * nx; fn_[1] = qo[1][c] - 2.0 * un * ny;
+                    un = qo[2][c] * nx + qo[3][c] * ny;
+                    fn_[2] = qo[2][c] - 2.0 * un * nx; fn_[3] = qo[3][c] - 2.0 * un * ny;
+                }
                 double fl[4], fr[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { fl[k] = left ? fo_[k] : fn_[k]; fr[k] = left ? fn_[k] : fo_[k]; }
@@ -771,22 +760,31 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
         }
         pr_sync<NT>();
         PR_STAMP(11);
+        // flux variable of the new state at every node (the lanes that hold pbprime_visc and btp_dpp_graduv) -> Lr[4..7]
+        if (lane < NP) {
+            const int I = lane;
+            double dku[NE], dkv[NE], deu[NE], dev[NE], q0[NE], q1[NE], q2[NE], q3[NE];
+            V::ld(Lr + 0 * NP + I, dku); V::ld(Lr + 1 * NP + I, dkv); V::ld(Lr + 2 * NP + I, deu); V::ld(Lr + 3 * NP + I, dev);
+            PR_FORC {
+                const double g0 = ksx[c] * dku[c] + etx[c] * deu[c], g1 = ksy[c] * dku[c] + ety[c] * deu[c];
+                const double g2 = ksx[c] * dkv[c] + etx[c] * dev[c], g3 = ksy[c] * dkv[c] + ety[c] * dev[c];
+                q0[c] = pv[c] * g0 + bd[0][c]; q1[c] = pv[c] * g1 + bd[1][c];
+                q2[c] = pv[c] * g2 + bd[2][c]; q3[c] = pv[c] * g3 + bd[3][c];
+            }
+            V::st(Lr + 4 * NP + I, q0); V::st(Lr + 5 * NP + I, q1); V::st(Lr + 6 * NP + I, q2); V::st(Lr + 7 * NP + I, q3);
+        }
+        pr_sync<NT>();
     }
     if (face_lane) {
         const int s = fs, n = fn, I = pr_face_node<G>(s, n);
-        double t0[NE], t1[NE], t2[NE], dku[NE], dkv[NE], deu[NE], dev[NE];
+        double t0[NE], t1[NE], t2[NE], q0[NE], q1[NE], q2[NE], q3[NE];
         V::ld(nod + 0 * NP + I, t0); V::ld(nod + 1 * NP + I, t1); V::ld(nod + 2 * NP + I, t2);
-        if (VISC) { V::ld(Lr + 0 * NP + I, dku); V::ld(Lr + 1 * NP + I, dkv); V::ld(Lr + 2 * NP + I, deu); V::ld(Lr + 3 * NP + I, dev); }
+        if (VISC) { V::ld(Lr + 4 * NP + I, q0); V::ld(Lr + 5 * NP + I, q1); V::ld(Lr + 6 * NP + I, q2); V::ld(Lr + 7 * NP + I, q3); }
         PR_FORC {
             if (ok[c]) {
                 double* to = a.tr_out + ((size_t)e[c] * 4 + s) * R::TSIDE + n;
                 to[0] = t0[c]; to[G] = t1[c]; to[2 * G] = t2[c];
-                if (VISC) {
-                    to[3 * G] = ksx[c] * dku[c] + etx[c] * deu[c];
-                    to[4 * G] = ksy[c] * dku[c] + ety[c] * deu[c];
-                    to[5 * G] = ksx[c] * dkv[c] + etx[c] * dev[c];
-                    to[6 * G] = ksy[c] * dkv[c] + ety[c] * dev[c];
-                }
+                if (VISC) { to[3 * G] = q0[c]; to[4 * G] = q1[c]; to[5 * G] = q2[c]; to[6 * G] = q3[c]; }
             }
         }
     }
@@ -901,24 +899,12 @@ __global__ void k_pair_pack(PairPackArgs a) {
         int s = t / G, n = t - s * G, slot = e * 4 + s, nb = a.M.nbr[slot], nbs = a.M.nbslot[slot];
         int I = face_node(s, n, G);
         double nx = a.M.fgeom[slot * 3 + 0], ny = a.M.fgeom[slot * 3 + 1];
-        double* vs = r + D.O_VST + s * D.VSIDE + n;
-        double so[5] = {0, 0, 0, 0, 0}, sn[5] = {0, 0, 0, 0, 0};
+        r[D.O_VST + s * D.VSIDE + n] = a.pbn[(size_t)slot * G + n];
+        double so[5] = {0, 0, 0, 0, 0};   // own LDG statics at the face node: btp_dpp_graduv, pbprime_visc
         if (a.has_visc) {
             for (int k = 0; k < 4; ++k) so[k] = a.bdg[k][nbase + I];
             so[4] = a.pbv[nbase + I];
-            if (nb >= 0) {
-                size_t In = (size_t)nb * NP + face_node(nbs, n, G);
-                for (int k = 0; k < 4; ++k) sn[k] = a.bdg[k][In];
-                sn[4] = a.pbv[In];
-            } else if (nb == NBR_HALO) {
-                for (int k = 0; k < 5; ++k) sn[k] = a.hstat[k * a.hstat_stride + (size_t)nbs * G + n];
-            } else {
-                for (int k = 0; k < 5; ++k) sn[k] = so[k];
-                if (nb == NBR_FREESLIP) reflect4(so, nx, ny, sn);
-            }
         }
-        for (int k = 0; k < 5; ++k) vs[k * G] = sn[k];
-        vs[5 * G] = a.pbn[(size_t)slot * G + n];
         // traces of the initial state of the loop (the stage kernel publishes the later ones)
         double* tr = a.tr + ((size_t)e * 4 + s) * D.TSIDE + n;
         for (int k = 0; k < 3; ++k) tr[k * G] = a.qb[k][nbase + I];
@@ -933,7 +919,7 @@ __global__ void k_pair_pack(PairPackArgs a) {
             }
             g4[0] = ksx * dku + etx * deu; g4[1] = ksy * dku + ety * deu; g4[2] = ksx * dkv + etx * dev; g4[3] = ksy * dkv + ety * dev;
         }
-        for (int k = 0; k < 4; ++k) tr[(3 + k) * G] = g4[k];
+        for (int k = 0; k < 4; ++k) tr[(3 + k) * G] = so[4] * g4[k] + so[k];   // LDG flux variable, as the stage kernel publishes it
     }
 }
 // state records -> planes after the loop
