@@ -426,7 +426,7 @@ static int pair_pack(Solver& S, const Planes& qb, const Planes& qprime, int cur)
     const double* fstp[11] = {S.cL, S.cR, S.cLR, S.lam, S.oop_edge, S.Quu_e, S.Quv_e, S.Qvv_e, S.Hbcl_e, S.pbl, S.pbr};
     for (int v = 0; v < 11; ++v) p.fstp[v] = fstp[v];
     for (int v = 0; v < 4; ++v) p.bdg[v] = S.btp_dpp_graduv[v];
-    p.pbv = S.pbprime_visc; p.pbn = S.pbn; p.hstat = S.h_stat.p; p.hstat_stride = S.h_stat.stride;
+    p.pbv = S.pbprime_visc; p.pbn = S.pbn;
     p.rec = S.p_rec; p.tr = S.p_tr[cur];
     p.has_visc = S.has_visc;
     static const int pack_threads = getenv("HNUMO_PACK_THREADS") ? atoi(getenv("HNUMO_PACK_THREADS")) : 128;

@@ -461,22 +461,12 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
             }
         }
     }
-    // neighbour traces (state and LDG flux variable) and the neighbour's pbprime of face node (s,n), issued one phase ahead
+    // neighbour traces (state and LDG flux variable) and the neighbour's pbprime of face node (s,n): requested after scatter pass 1
+    // (right behind the 18 REDs of the pointwise phase they queued up in the LSU: -0.5 % of the stage time when issued one phase later)
     double tn[7][NE], pbnp[NE];
     const int lf = lane - J6C;                     // face node owned by this lane (0 <= lf < 4G)
     const bool face_lane = lf >= 0 && lf < 4 * G;
     const int fs = face_lane ? lf / G : 0, fn = face_lane ? lf - fs * G : 0;
-    if (face_lane) {
-        PR_FORC {
-            const int tr = reinterpret_cast<const int*>(hdr + c * R::HDR + 18)[4 + fs];
-            if (tr >= 0) {
-                const double* t = a.tr_in + (size_t)tr * R::TSIDE + fn;
-#pragma unroll
-                for (int k = 0; k < (VISC ? 7 : 3); ++k) tn[k][c] = t[k * G];
-            }
-            pbnp[c] = rec[c][R::O_VST + fs * R::VSIDE + fn];
-        }
-    }
     pr_sync<NT>();
     PR_STAMP(4);
     // ---- 5. scatter pass 1 (contraction over j): lane (f,i) -> TB_f = A.Fk_f, TA_f = B.Fe_f + A.S_f, as T[f][m][i], T[3+f][m][i]
@@ -497,6 +487,18 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
     }
     pr_sync<NT>();
     PR_STAMP(5);
+    if (face_lane) {
+        PR_FORC {
+            const int tr = reinterpret_cast<const int*>(hdr + c * R::HDR + 18)[4 + fs];
+            if (tr >= 0) {
+                const double* t = a.tr_in + (size_t)tr * R::TSIDE + fn;
+#pragma unroll
+                for (int k = 0; k < (VISC ? 7 : 3); ++k) tn[k][c] = t[k * G];
+            }
+            pbnp[c] = rec[c][R::O_VST + fs * R::VSIDE + fn];
+        }
+    }
+
     // ---- 6. scatter pass 2 (contraction over i): lane (f,m) -> rhs[f][m][n] = B.TB_f + A.TA_f
     if (lane < 3 * G) {
         const int f = lane / G, m = lane - f * G;
@@ -828,8 +830,6 @@ struct PairPackArgs {
     const double* bdg[4];
     const double* pbv;
     const double* pbn;
-    const double* hstat;      // halo copies of (bdg0..3, pbv) traces
-    size_t hstat_stride;
     double *rec, *tr;
     int has_visc;
 };
