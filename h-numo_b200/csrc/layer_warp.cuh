@@ -14,6 +14,16 @@
 #include "bcl_kernels.cuh"
 #include "line_ops.cuh"
 
+#ifndef LW_MINB_A
+#define LW_MINB_A 4   // resident blocks per SM the register allocation of the coefficient / mass / consistency / laplacian kernels aims at
+#endif
+#ifndef LW_MINB_L
+#define LW_MINB_L 4   // ... of the layer laplacian kernel
+#endif
+#ifndef LW_MINB_F
+#define LW_MINB_F 4   // ... of the momentum face kernel (128 registers, 16 B of spills: 583 against 700 us per launch at 62 500 elements with 3 blocks
+                      //     and 158 registers; the other kernels are slower with 3 blocks and equal with 5)
+#endif
 namespace hn {
 
 constexpr int LW_WARPS = 4;   // warps (elements) per block
@@ -153,7 +163,7 @@ __device__ __forceinline__ void lw_qprime_traces(const Mesh& M, const double* qp
 // ================================================================================================================================
 // btp_bcl_coeffs_qdf (mod_barotropic_terms.F90:219-409)
 template <int G, int Q, int NL_>
-__global__ void __launch_bounds__(32 * LW_WARPS, 4) k_bcl_coeffs_w(CoeffArgs a) {
+__global__ void __launch_bounds__(32 * LW_WARPS, LW_MINB_A) k_bcl_coeffs_w(CoeffArgs a) {
     using W = LW<G, Q>;
     constexpr int NP = W::NP, NQ2 = W::NQ2, SX = W::SX, ST = W::ST;
     constexpr int PER_WARP = 3 * NP + 4 * ST + 3 * SX + 24 * G + 24 * Q + 4 * NP;
@@ -268,7 +278,7 @@ __host__ __device__ constexpr int lw_mass_doubles() { return 3 * G * G + 2 * LW<
 template <int G, int Q>
 constexpr size_t lw_mass_smem() { return (size_t)LW_WARPS * lw_mass_doubles<G, Q>() * sizeof(double); }
 template <int G, int Q, int NL_>
-__global__ void __launch_bounds__(32 * LW_WARPS, 4) k_layer_mass_w(MassArgs a) {
+__global__ void __launch_bounds__(32 * LW_WARPS, LW_MINB_A) k_layer_mass_w(MassArgs a) {
     using W = LW<G, Q>;
     constexpr int NP = W::NP, NQ2 = W::NQ2, SX = W::SX, ST = W::ST;
     extern __shared__ double sm_all[];
@@ -386,7 +396,7 @@ __host__ __device__ constexpr int lw_cons_doubles() { return G * G + 2 * LW<G, Q
 template <int G, int Q>
 constexpr size_t lw_cons_smem() { return (size_t)LW_WARPS * lw_cons_doubles<G, Q>() * sizeof(double); }
 template <int G, int Q, int NL_>
-__global__ void __launch_bounds__(32 * LW_WARPS, 4) k_consistency_w(ConsArgs a) {
+__global__ void __launch_bounds__(32 * LW_WARPS, LW_MINB_A) k_consistency_w(ConsArgs a) {
     using W = LW<G, Q>;
     constexpr int NP = W::NP, NQ2 = W::NQ2, SX = W::SX, ST = W::ST;
     extern __shared__ double sm_all[];
@@ -503,7 +513,7 @@ __host__ __device__ constexpr int lw_lap_doubles() { return 8 * G * G + 8 * G; }
 template <int G, int Q>
 constexpr size_t lw_lap_smem() { return (size_t)LW_WARPS * lw_lap_doubles<G, Q>() * sizeof(double); }
 template <int G, int Q, int NL_>
-__global__ void __launch_bounds__(32 * LW_WARPS, 4) k_bcl_laplacian_w(LapArgs a) {
+__global__ void __launch_bounds__(32 * LW_WARPS, LW_MINB_L) k_bcl_laplacian_w(LapArgs a) {
     constexpr int NP = G * G;
     extern __shared__ double sm_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -790,7 +800,7 @@ __global__ void __launch_bounds__(32 * LW_WARPS, 3) k_mom_volume_w(MomVolArgs a)
 template <int G, int Q>
 __host__ __device__ constexpr int lw_mface_doubles(int nl) { return 24 * nl * G + 24 * nl * Q + 8 * nl * Q + 8 * nl * G; }
 template <int G, int Q, int NL_>
-__global__ void __launch_bounds__(32 * LW_WARPS, 3) k_mom_faces_update_w(MomFaceArgs a) {
+__global__ void __launch_bounds__(32 * LW_WARPS, LW_MINB_F) k_mom_faces_update_w(MomFaceArgs a) {
     using W = LW<G, Q>;
     constexpr int NP = W::NP;
     constexpr int LMAX = NL_ ? NL_ : HN_MAXL;
