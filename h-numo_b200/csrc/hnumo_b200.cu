@@ -670,7 +670,13 @@ static int momentum_update(Solver& S, const Planes& qprime_in, const Planes& dpv
     size_t sm = (sops_doubles_host(S.ngl, S.nq) + 5 * S.npts + 6 * per + 6 * S.nq2 + 4 * per + 2 * S.npts) * sizeof(double);
     if (use_layer_warp(S, 16))
         HN_LAUNCH_LW(k_mom_volume_w, (LW_WARPS * sizeof(double) * lw_mvol_doubles<5, 9>(S.nl)), (LW_WARPS * sizeof(double) * lw_mvol_doubles<4, 7>(S.nl)), S, v);
-    else HN_LAUNCH_GQL(k_mom_volume, S, sm, v);
+    else if (S.mom_volume_batched && S.ngl == 5 && S.nq == 9 && S.nl == 3) {
+        const size_t smb = mom_volume_b_doubles<5, 9, 3>() * sizeof(double);
+        smem_opt_in(k_mom_volume_b<5, 9, 3>, smb); k_mom_volume_b<5, 9, 3><<<S.nelem, threads_for(S), smb, S.stream>>>(v);
+    } else if (S.mom_volume_batched && S.ngl == 5 && S.nq == 9 && S.nl == 2) {
+        const size_t smb = mom_volume_b_doubles<5, 9, 2>() * sizeof(double);
+        smem_opt_in(k_mom_volume_b<5, 9, 2>, smb); k_mom_volume_b<5, 9, 2><<<S.nelem, threads_for(S), smb, S.stream>>>(v);
+    } else HN_LAUNCH_GQL(k_mom_volume, S, sm, v);
     S.n_launches++;
     if (phase_check(S, "k_mom_volume")) return -1;
     MomFaceArgs f; memset(&f, 0, sizeof(f));
@@ -1452,6 +1458,7 @@ int hnumo_set_option(hnumo_handle_t h, const char* key, double value) {
     if (!strcmp(key, "stage_kernel_variant")) { S.variant = (int)value; return 0; }
     if (!strcmp(key, "use_graph")) { S.use_graph = (int)value; return 0; }
     if (!strcmp(key, "layer_warp")) { S.layer_warp = (int)value; return 0; }
+    if (!strcmp(key, "mom_volume_batched")) { S.mom_volume_batched = (int)value; return 0; }
     if (!strcmp(key, "pair_prefetch")) { S.pair_prefetch = (int)value; return 0; }
     if (!strcmp(key, "pair_pf_dist")) { S.pair_pf_dist = (int)value; return 0; }
     if (!strcmp(key, "overlap")) { S.overlap = (int)value; return 0; }

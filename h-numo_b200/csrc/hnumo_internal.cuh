@@ -170,6 +170,7 @@ struct Solver {
     // Default 47: the momentum volume kernel is faster in its block-per-element form (1.37 vs 1.57 ms per launch at 62 500
     // elements: the warp form interpolates every layer twice), see profiles/r2_layer_kernels.md
     int layer_warp = 47;
+    int mom_volume_batched = 1;   // momentum volume term with all layers of an element in flight (nop 4, 2 or 3 layers)
     std::vector<void*> allocs;
 };
 
