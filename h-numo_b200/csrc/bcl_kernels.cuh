@@ -605,8 +605,8 @@ __global__ void k_mom_volume(MomVolArgs a) {
 
 // Same operator with ALL layers of an element in flight (compile-time layer count, small): one interpolation sweep for the nl+1
 // interface elevations, one for the 5 nl layer fields, one weak-form scatter for the 2 nl momentum components -- 8 block barriers per
-// element instead of 11 nl + 3, and every sweep keeps all threads busy.  Per-field arithmetic (and therefore the result) is that of
-// k_mom_volume bit for bit.
+// element instead of 11 nl + 3, and every sweep keeps all threads busy.  Per-field arithmetic is that of k_mom_volume (the results
+// agree to the last bits: the compiler may contract the multiply-adds of the two kernels differently).
 template <int G_, int Q_, int NL_>
 constexpr size_t mom_volume_b_doubles() { return (size_t)(2 * G_ * Q_ + G_ * G_ + Q_ + G_) + 5 * NL_ * G_ * G_ + 5 * NL_ * G_ * Q_ + (NL_ + 1) * G_ * Q_ + 6 * NL_ * Q_ * Q_ + 4 * NL_ * G_ * Q_ + 2 * NL_ * G_ * G_; }
 #ifndef HN_MVB_MAXNREG

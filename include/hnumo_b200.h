@@ -220,7 +220,10 @@ int hnumo_timing(hnumo_handle_t h, double* out8, int32_t reset);
  *                          partitions without processor faces; bitwise the same result)
  *   "overlap"              1 (default) / 0: boundary elements + halo exchange on a second stream, overlapped with the interior
  *   "stage_kernel_variant" as hnumo_desc_t.stage_kernel_variant (effective if the records were allocated at init)
- *   "pair_prefetch", "pair_pf_dist"   L2 prefetch bits / distance of the stage kernel (sweeps) */
+ *   "pair_prefetch", "pair_pf_dist"   L2 prefetch bits / distance of the stage kernel (sweeps)
+ *   "layer_warp"           bit mask of the warp-per-element layer kernels (1 coefficients, 2 layer mass, 4 consistency, 8 laplacian,
+ *                          16 momentum volume, 32 momentum faces + update; default 47); cleared bits run the block-per-element forms
+ *   "mom_volume_batched"              1 (default): layer momentum volume term with all layers of an element in flight (nop 4, 2-3 layers); 0: layer by layer */
 int hnumo_set_option(hnumo_handle_t h, const char* key, double value);
 
 #ifdef __cplusplus

@@ -478,6 +478,29 @@ def check_layer_phases(deck, S, O):
             assert np.abs(a[k, :, v] - b[k, :, v]).max() <= 2e-14 * Hn * hscale, (k, v, np.abs(a[k, :, v] - b[k, :, v]).max(), Hn * hscale)
 
 
+@pytest.mark.parametrize("name", ["synth3", "double_gyre"])
+def test_batched_momentum_volume_equals_the_layerwise_one(name):
+    """k_mom_volume_b (all layers of an element in one sweep) against k_mom_volume (layer by layer) on the same developed state: the
+    same per-field arithmetic up to the compiler's choice of FMA contractions -- the layer momentum RHS agrees to round-off of the
+    cancelling pressure terms (ten times tighter than the bound against the oracle in test_layer_phase_parity), bitwise at 2 layers"""
+    deck = hn.decks.build_deck(DECKS[name]())
+    S = hn.Solver(deck)
+    S.upload_state(deck["q_df"], deck["qb_df"], deck["qprime_df"])
+    assert S.step(1) == 0
+    S.btp_bcl_coeffs(); S.btp_substeps()
+    Hq = S.get_array("H_bcl")
+    scale = np.linalg.norm(Hq) / np.sqrt(Hq.size) * np.sqrt(deck["massinv"].max())
+    rhs = []
+    for batched in (1, 0):
+        S.set_option("mom_volume_batched", batched)
+        rhs.append(S.layer_momentum_rhs().copy())
+    assert np.abs(rhs[0]).max() > 0.0
+    assert np.abs(rhs[0] - rhs[1]).max() <= 2e-15 * scale, (np.abs(rhs[0] - rhs[1]).max(), scale)
+    if deck["nlayers"] == 2:
+        assert np.array_equal(rhs[0], rhs[1])
+    S.close()
+
+
 @pytest.mark.parametrize("partition,nranks", [("rows", 2), ("morton", 4), ("blocks:3x2", 6)])
 def test_halo_exchange_pattern(partition, nranks):
     """hnumo_halo_exchange (the device replacement of create_nbhs_face_df / send_bound_dg_general_df): every rank sends a nodal
