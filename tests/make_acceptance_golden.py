@@ -33,6 +33,9 @@ def cases():
         "double_gyre": (dict(hn.decks.SHIPPED["double_gyre"]), 0, 1),
         "double_gyre_spunup": (dict(hn.decks.SHIPPED["double_gyre"]), 200, 1),
         "synth3_64x64": (hn.decks.synthetic_double_gyre(64, 64, nop=4, nlayers=3), 0, 4),
+        # general (curved, non-affine) quadrilaterals: the per-point geometry path of the library (the "metrics" floor is zero here:
+        # there is only one way to evaluate the metric terms of a curved element)
+        "synth3_curved_32x32": (dict(hn.decks.synthetic_double_gyre(32, 32, nop=4, nlayers=3), mesh_warp=0.15), 0, 2),
     }
 
 

@@ -3,7 +3,7 @@ relative L2 error of at most 1e-11 per field after 100 steps; mass conservation 
 at rest to machine precision".
 
 For every BASELINE configuration that fits a test -- bump, lake, the shipped 25x25 double gyre, the same double gyre after a
-200-step spin-up (a developed flow), a 64x64 synthetic 3-layer double gyre -- the CUDA library advances 100 baroclinic steps
+200-step spin-up (a developed flow), a 64x64 synthetic 3-layer double gyre, a 32x32 one on curved (non-affine) elements -- the CUDA library advances 100 baroclinic steps
 (20 000 .. 56 000 barotropic stages) through the C-ABI and is compared, field by field, with the CPU oracle's result of the
 same 100 steps (committed by tests/make_acceptance_golden.py: 100 oracle steps take minutes per case).  The measured plain
 relative L2 error of every field is written to profiles/parity_r2.json next to the ROUND-OFF FLOOR of that field: the
@@ -67,7 +67,7 @@ def _run_gpu(params, fx, lib_path=None):
     return deck, (q, qb, qp), d0, d1
 
 
-@pytest.mark.parametrize("name", ["bump", "lake", "double_gyre", "double_gyre_spunup", "synth3_64x64"])
+@pytest.mark.parametrize("name", ["bump", "lake", "double_gyre", "double_gyre_spunup", "synth3_64x64", "synth3_curved_32x32"])
 def test_100_steps_match_the_oracle_per_field(name):
     path = os.path.join(HERE, "golden", "acceptance_%s.npz" % name)
     if not os.path.exists(path):
