@@ -897,9 +897,8 @@ __global__ void k_pair_pack(PairPackArgs a) {
     __syncthreads();
     if (tid == 0) { int* hi = reinterpret_cast<int*>(r + 22); hi[0] = s_flags; hi[1] = 0; }
     for (int t = tid; t < 4 * G; t += nt) {
-        int s = t / G, n = t - s * G, slot = e * 4 + s, nb = a.M.nbr[slot], nbs = a.M.nbslot[slot];
+        int s = t / G, n = t - s * G, slot = e * 4 + s;
         int I = face_node(s, n, G);
-        double nx = a.M.fgeom[slot * 3 + 0], ny = a.M.fgeom[slot * 3 + 1];
         r[D.O_VST + s * D.VSIDE + n] = a.pbn[(size_t)slot * G + n];
         double so[5] = {0, 0, 0, 0, 0};   // own LDG statics at the face node: btp_dpp_graduv, pbprime_visc
         if (a.has_visc) {
