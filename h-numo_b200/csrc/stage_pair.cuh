@@ -500,6 +500,7 @@ __global__ void __launch_bounds__(32 * W) __maxnreg__(BLK ? HN_BLK_MAXNREG : NE 
         }
     }
 
+
     // ---- 6. scatter pass 2 (contraction over i): lane (f,m) -> rhs[f][m][n] = B.TB_f + A.TA_f
     if (lane < 3 * G) {
         const int f = lane / G, m = lane - f * G;
