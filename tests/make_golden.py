@@ -19,6 +19,8 @@ CASES = {
     "double_gyre_4x4": (dict(hn.decks.SHIPPED["double_gyre"], nelx=4, nely=4), 3),
     "synth3_nop4_4x3": (hn.decks.synthetic_double_gyre(4, 3, nop=4, nlayers=3), 2),
     "synth_nop8_5layers_2x2": (hn.decks.synthetic_double_gyre(2, 2, nop=8, nlayers=5), 1),
+    # curved (non-affine) elements: per-point metric terms, face normals and Jacobians (Config::mesh_warp)
+    "synth3_curved_nop4_4x3": (dict(hn.decks.synthetic_double_gyre(4, 3, nop=4, nlayers=3), mesh_warp=0.15), 2),
 }
 
 

@@ -149,7 +149,7 @@ def test_fin_file_passes_the_reference_ci_check(bump108, tmp_path):
         assert emax < tol and emin < tol, (layer, field, emax, emin)
 
 
-@pytest.mark.parametrize("name", ["bump_4x4", "double_gyre_4x4", "synth3_nop4_4x3", "synth_nop8_5layers_2x2"])
+@pytest.mark.parametrize("name", ["bump_4x4", "double_gyre_4x4", "synth3_nop4_4x3", "synth_nop8_5layers_2x2", "synth3_curved_nop4_4x3"])
 def test_oracle_matches_committed_fields(name):
     """Field-level fixtures generated by tests/make_golden.py pin the oracle against accidental change: mass-like fields to
     1e-12 relative L2, momentum-like fields to 1e-11 of their natural scale c*|dp| (round-off may differ with the number of
