@@ -845,6 +845,11 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
         // mod_create_rhs_mlswe.F90:204-205 divides by max_shear_dz (namelist default 0): the reference would work with an infinite coefficient
         set_error("hnumo_init", "ad_mlswe > 0 needs max_shear_dz > 0"); return -2;
     }
+    if (d->point_metrics_q) {   // general quadrilaterals: all five per-point arrays or none
+        if (!d->point_metrics || !d->face_geom_q || !d->face_geom_n || !d->coord) {
+            set_error("hnumo_init", "general quadrilaterals need point_metrics_q, point_metrics, face_geom_q, face_geom_n and coord"); return -2;
+        }
+    } else if (!d->elem_metrics || !d->face_geom) { set_error("hnumo_init", "elem_metrics / face_geom missing"); return -2; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("hnumo_init", "no CUDA device: this library has no CPU fallback"); return -1; }
     hnumo_handle_s* H = new hnumo_handle_s();
@@ -872,13 +877,8 @@ int hnumo_init(const hnumo_desc_t* d, hnumo_handle_t* out) {
     if (S.visc_q) S.variant = 1;
     // general quadrilaterals: geometry per point, run-time-size kernels (the element-record and warp-per-element kernels carry one
     // Jacobian per element)
-    S.general = d->point_metrics_q != nullptr;
-    if (S.general) {
-        if (!d->point_metrics || !d->face_geom_q || !d->face_geom_n || !d->coord) {
-            set_error("hnumo_init", "general quadrilaterals need point_metrics_q, point_metrics, face_geom_q, face_geom_n and coord"); destroy_solver(H); return -2;
-        }
-        S.variant = 1; S.layer_warp = 0;
-    } else if (!d->elem_metrics || !d->face_geom) { set_error("hnumo_init", "elem_metrics / face_geom missing"); destroy_solver(H); return -2; }
+    S.general = d->point_metrics_q != nullptr;   // (completeness of the descriptor was checked above, before any device work)
+    if (S.general) { S.variant = 1; S.layer_warp = 0; }
     for (int k = 0; k < S.nl; ++k) S.alpha[k] = d->alpha_mlswe[k];
     for (int ik = 0; ik < S.kstages; ++ik) {
         for (int c = 0; c < 3; ++c) S.ssprk_a[ik][c] = d->ssprk_a[ik + S.kstages * c];

@@ -368,6 +368,8 @@ def test_fortran_d23_16_formatting(tmp_path):
     (dict(nlayers=0), -2, "unsupported sizes"),
     (dict(kstages=6), -2, "unsupported sizes"),
     (dict(ngl=12), -2, "unsupported sizes"),
+    (dict(elem_metrics=None), -2, "elem_metrics"),                 # affine mesh without its per-element geometry
+    (dict(point_metrics_q=np.zeros((4 * 81, 5))), -2, "general quadrilaterals need"),   # per-point geometry given only in part
 ])
 def test_init_rejects_unsupported_configurations(hn_lib, change, code, text):
     """argument validation happens before any device work: same answers with and without a GPU"""
